@@ -1,0 +1,117 @@
+/* vitmarl_b200 -- C ABI of the B200-native rollout-and-encode hot path.
+ *
+ * Drop-in boundary for the three reference call sites of hiepday3324/ViT-MARL (the
+ * reference is pure Python/JAX; it has no FFI of its own, so these entry points are what
+ * a jax.ffi / XLA custom-call binding -- or the ctypes binding in vitmarl_b200/_capi.py --
+ * binds; INTEGRATION.md shows the reference-side stubs):
+ *
+ *   order-book step  gymnax_exchange/jaxob/JaxOrderBookArrays.py:720-752
+ *                    scan_through_entire_array_save_bidask (called under jax.vmap from
+ *                    gymnax_exchange/jaxen/marl_env.py:377-384), :665-685 scan_through_entire_array
+ *   read-outs        JaxOrderBookArrays.py:881-898 get_best_bid_and_ask_inclQuants,
+ *                    :1075-1106 get_L2_state, :1108-1140 get_vision_L2_state
+ *   observation      gymnax_exchange/jaxen/vision_env.py:2709-2721 _get_obs_vision,
+ *                    :2804-2854 normalize_vision_obs; marl_env.py:392-393,467,685-711
+ *                    (_ffill_best_prices + mid price)
+ *   encoder          flax `module.apply({'params': p}, x[B,H,W,C])` convention of
+ *                    gymnax_exchange/networks/vision_agent.py:16-24 (the ViT itself is
+ *                    builder-specified: docs/VIT_SPEC.md) and its VJP used by
+ *                    jaxrl/MARL/ippo_rnn_JAXMARL.py:423-475.
+ *
+ * Conventions: every pointer is caller-owned DEVICE memory unless the function name ends
+ * in _host; no allocation, no synchronisation, work is only enqueued on `stream`
+ * (a cudaStream_t passed as void*).  Returns 0 or a negative VITMARL_E* code; never aborts.
+ * All book / message / trade arrays are int32, row-major, layouts of
+ * gymnax_exchange/jaxob/jaxob_constants.py:36-52,76-83.
+ */
+#ifndef VITMARL_B200_H_
+#define VITMARL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITMARL_OK 0
+#define VITMARL_EINVAL (-1)       /* bad shape / null pointer / misaligned buffer           */
+#define VITMARL_EUNSUPPORTED (-2) /* cancel_mode 2/3 (PRNG-dependent), simulator_mode 1      */
+#define VITMARL_ECUDA (-3)        /* launch failure (cudaGetLastError)                      */
+#define VITMARL_ENODEVICE (-4)    /* no sm_100 device                                       */
+
+#define VITMARL_ABI_VERSION 1
+
+int vitmarl_abi_version(void);
+/* Human-readable text for the last CUDA error seen by this thread (static storage). */
+const char* vitmarl_last_error(void);
+
+/* ---- stage 1: order-book step ------------------------------------------------------ */
+
+/* Replaces job.scan_through_entire_array_save_bidask under vmap (JaxOrderBookArrays.py:720-752):
+ * for each of E environments process M messages [type, side, qty, price, oid, tid, t_s, t_ns]
+ * in order through add / cancel / match (lines 62-330, 356-478, 617-661) and record the best
+ * ask / best bid [price, volume at price] after each of the LAST n_keep messages (lines 881-898).
+ *   asks_in/bids_in  [E,N,6]  (may alias asks_out/bids_out: in-place update)
+ *   trades_in        [E,T,8]  or NULL -> trades start at -1 (marl_env.py:377)
+ *   msgs             [E,M,8]
+ *   trades_out       [E,T,8]
+ *   best_asks/bids   [E,n_keep,2] or NULL (scan_through_entire_array, lines 665-685)
+ *   cancel_mode      JAXLOB_Configuration.cancel_mode (0 or 1; 2/3 -> VITMARL_EUNSUPPORTED)
+ *   init_id          JAXLOB_Configuration.init_id (-2)
+ * Limits: 1 <= N <= 256, 1 <= T <= 1024, M >= 0, 0 <= n_keep. */
+int vitmarl_lob_step(void* stream, int E, int N, int T, int M, int n_keep,
+                     const int32_t* asks_in, const int32_t* bids_in, const int32_t* trades_in,
+                     const int32_t* msgs,
+                     int32_t* asks_out, int32_t* bids_out, int32_t* trades_out,
+                     int32_t* best_asks, int32_t* best_bids,
+                     int cancel_mode, int32_t init_id);
+
+/* Replaces job.get_best_bid_and_ask_inclQuants under vmap (JaxOrderBookArrays.py:881-898).
+ *   best_ask/best_bid [E,2] */
+int vitmarl_lob_best_bid_ask(void* stream, int E, int N, const int32_t* asks, const int32_t* bids,
+                             int32_t* best_ask, int32_t* best_bid);
+
+/* ---- stage 2: observation render --------------------------------------------------- */
+
+#define VITMARL_IMG_NONE 0
+#define VITMARL_IMG_U8 1   /* uint8 {0,1}          */
+#define VITMARL_IMG_BF16 2 /* bfloat16 {0.0,1.0}   */
+
+/* Replaces job.get_vision_L2_state (JaxOrderBookArrays.py:1108-1140) and, when `norm` and
+ * `mid_price` are given, ExecutionAgent.normalize_vision_obs (vision_env.py:2804-2854);
+ * optionally also rasterises the book (docs/RENDER_SPEC.md; builder-defined).
+ *   raw        int32 [E,n_levels,2,2]  (level, (price, volume), (ask, bid))      or NULL
+ *   l2         int32 [E,4*n_levels]    get_L2_state layout (lines 1075-1106)      or NULL
+ *   mid_price  float [E]               WorldState.mid_price                       or NULL
+ *   norm       float [E,n_levels,3,2]  (level, (gap, log1p vol, log1p cum), (ask,bid)) or NULL
+ *   image      [E,H,W,2] of img_dtype  (channel 0 ask, 1 bid)                     or NULL
+ * Limits: n_levels <= 32, W % 8 == 0, 2*H <= 12*N. */
+int vitmarl_lob_render(void* stream, int E, int N, int n_levels, int tick_size,
+                       const int32_t* asks, const int32_t* bids, const float* mid_price,
+                       int32_t* raw, int32_t* l2, float* norm,
+                       void* image, int img_dtype, int H, int W);
+
+/* Fused environment step = vitmarl_lob_step (trades start at -1, n_keep = M)
+ *   + _ffill_best_prices on both best-price tracks and the new mid price
+ *     (marl_env.py:392-393, 466-467, 685-711)
+ *   + vitmarl_lob_render on the updated book with that mid price
+ * in ONE kernel: the book is read once and written once per step.
+ *   last_ask_price/last_bid_price [E]   previous step's final best prices
+ *                                       (state.world_state.best_asks[-1,0] / best_bids[-1,0])
+ *   best_asks/best_bids [E,M,2]         forward-filled
+ *   mid_price [E] float                 (ffilled bid[-1] + ask[-1]) / 2
+ * raw / l2 / norm / image as in vitmarl_lob_render (each nullable). Requires M >= 1. */
+int vitmarl_env_step(void* stream, int E, int N, int T, int M,
+                     const int32_t* asks_in, const int32_t* bids_in, const int32_t* msgs,
+                     const int32_t* last_ask_price, const int32_t* last_bid_price,
+                     int32_t* asks_out, int32_t* bids_out, int32_t* trades_out,
+                     int32_t* best_asks, int32_t* best_bids, float* mid_price,
+                     int n_levels, int tick_size, int32_t* raw, int32_t* l2, float* norm,
+                     void* image, int img_dtype, int H, int W,
+                     int cancel_mode, int32_t init_id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITMARL_B200_H_ */

@@ -1,0 +1,738 @@
+// Order-book step + observation render for sm_100a: ONE WARP PER ENVIRONMENT.
+//
+// What it replaces (reference, pure JAX): gymnax_exchange/jaxob/JaxOrderBookArrays.py
+//   scan_through_entire_array_save_bidask :720-752  (lax.scan of cond_type_side_save_bidask :617-661)
+//   add_order :62-83, cancel_order :93-138, match_order/_match_against_* :171-330,
+//   get_best_bid_and_ask_inclQuants :881-898, get_L2_state :1075-1106, get_vision_L2_state :1108-1140
+// and gymnax_exchange/jaxen/vision_env.py:2804-2854 (normalize_vision_obs),
+//     gymnax_exchange/jaxen/marl_env.py:392-393,466-467,685-711 (_ffill_best_prices, mid price).
+//
+// B200 design (not a translation of the XLA program, which runs ~40 small fused loops over
+// [100,6] arrays per message and, under vmap, executes all five switch branches):
+//   * a warp owns one environment for the whole step; both book sides live in REGISTERS
+//     (row r = j*32 + lane, RPL = ceil(N/32) rows per lane, 6 fields x 2 sides);
+//   * book sides / trades are moved with the TMA engine as 1-D bulk copies
+//     (cp.async.bulk global<->shared + mbarrier), one instruction per 2.4 KB side, so the
+//     LSU only sees the AoS<->register transposition in shared memory;
+//   * messages are read as coalesced 32-byte rows (one message per lane, 2x LDG.128) and
+//     broadcast with SHFL; per-message best bid/ask are kept in lane registers and written
+//     as coalesced 8-byte rows per 32 messages;
+//   * "first index" / min / max / sum over the N rows are REDUX.{MIN,MAX,SUM} + VOTE.BALLOT;
+//   * only the branch a message selects is executed (warp-uniform control flow).
+// Bit-exactness: every quirk of the reference is reproduced; the
+// shortcuts taken on the fast path (touching only the modified row when wiping, checking
+// only `price` when looking for an empty row) are guarded by per-side invariants that are
+// established at load time and fall back to the literal full-array form otherwise.
+//
+// HBM bytes per env-step (N=T=100): 2*(2*N*24) + T*32 + M*32 + 2*M*8 = 12800 + 48*M.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "../../include/vitmarl_b200.h"
+
+namespace vitmarl {
+
+constexpr int kWarpsPerCta = 4;
+constexpr int MAXINT = 2147483647;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct LobParams {
+  int E, N, T, M, n_keep;
+  int32_t init_id;
+  const int32_t* asks_in; const int32_t* bids_in; const int32_t* trades_in; const int32_t* msgs;
+  int32_t* asks_out; int32_t* bids_out; int32_t* trades_out;
+  int32_t* best_asks; int32_t* best_bids;
+  // fused env-step extras
+  int do_step;            // 0: render-only kernel (books are read, not written)
+  int do_ffill;           // ffill best prices + mid price
+  const int32_t* last_ask_price; const int32_t* last_bid_price;
+  float* mid_out;
+  // render
+  int do_render; int n_levels; int tick;
+  const float* mid_in;    // render-only: mid price input (nullable -> no norm)
+  int32_t* raw; int32_t* l2; float* norm;
+  void* image; int img_dtype; int H; int W;
+  int bulk_ok;            // 1: TMA bulk copies usable (16-byte aligned, N even)
+};
+
+// ---------------------------------------------------------------- one book side in registers
+template <int RPL>
+struct Side {
+  int p[RPL], q[RPL], oid[RPL], tid[RPL], ts[RPL], tns[RPL];
+  int best;      // bids: max(price) | asks: min(price, -1 -> MAXINT)   (over existing rows)
+  int vol;       // volume at the reported best price (Q10 semantics)
+  bool simple;   // every row: (price == -1) <=> (any field == -1)      -> fast empty-row search
+  bool clean;    // every row: qty > 0 or row is all -1                 -> touched-row wipe
+};
+
+template <int RPL>
+__device__ __forceinline__ void wipe_row(Side<RPL>& s, int j) {
+  s.p[j] = -1; s.q[j] = -1; s.oid[j] = -1; s.tid[j] = -1; s.ts[j] = -1; s.tns[j] = -1;
+}
+
+// JOBA:85-90 on the whole side (literal form)
+template <int RPL>
+__device__ __forceinline__ void wipe_all(Side<RPL>& s) {
+#pragma unroll
+  for (int j = 0; j < RPL; ++j)
+    if (s.q[j] <= 0) wipe_row(s, j);
+  s.clean = true;
+}
+
+// After modifying row `idx`: JOBA:85-90.  Fast path touches only that row.
+template <int RPL>
+__device__ __forceinline__ void wipe_after(Side<RPL>& s, int idx, int lane) {
+  if (!s.clean) { wipe_all(s); return; }
+#pragma unroll
+  for (int j = 0; j < RPL; ++j)
+    if (j * 32 + lane == idx && s.q[j] <= 0) wipe_row(s, j);
+}
+
+// first row index (ascending) whose predicate holds, -1 if none
+template <int RPL>
+__device__ __forceinline__ int first_index(const bool (&pred)[RPL]) {
+  int idx = -1;
+#pragma unroll
+  for (int j = RPL - 1; j >= 0; --j) {
+    unsigned b = __ballot_sync(FULL, pred[j]);
+    if (b) idx = j * 32 + __ffs(b) - 1;
+  }
+  return idx;
+}
+
+// JOBA:846-865 + :833-844 -> cached (best, vol) of one side
+template <int RPL, bool IS_BID>
+__device__ __forceinline__ void refresh_best(Side<RPL>& s, int N, int lane) {
+  int m = IS_BID ? (int)0x80000000 : MAXINT;
+#pragma unroll
+  for (int j = 0; j < RPL; ++j) {
+    bool ex = j * 32 + lane < N;
+    if (IS_BID) { if (ex) m = max(m, s.p[j]); }
+    else        { if (ex) m = min(m, s.p[j] == -1 ? MAXINT : s.p[j]); }
+  }
+  m = IS_BID ? __reduce_max_sync(FULL, m) : __reduce_min_sync(FULL, m);
+  s.best = m;
+  int bp = (!IS_BID && m == MAXINT) ? -1 : m;
+  int v = 0;
+#pragma unroll
+  for (int j = 0; j < RPL; ++j)
+    if (j * 32 + lane < N && s.p[j] == bp) v = wadd(v, s.q[j]);
+  s.vol = __reduce_add_sync(FULL, v);
+}
+
+template <int RPL, bool IS_BID>
+__device__ __forceinline__ int best_price_out(const Side<RPL>& s) {
+  return (!IS_BID && s.best == MAXINT) ? -1 : s.best;
+}
+
+// JOBA:240-267 literal (Q9)
+template <int RPL, bool IS_BID>
+__device__ __forceinline__ int top_index(const Side<RPL>& s, int N, int lane) {
+  const int best = s.best;  // == maxPrice (bids) / minPrice incl. MAXINT (asks)
+  int t[RPL];
+  int ms = MAXINT;
+#pragma unroll
+  for (int j = 0; j < RPL; ++j) {
+    bool ex = j * 32 + lane < N;
+    t[j] = (s.p[j] == best) ? s.ts[j] : MAXINT;
+    if (ex) ms = min(ms, t[j]);
+  }
+  ms = __reduce_min_sync(FULL, ms);
+  int mn = MAXINT;
+#pragma unroll
+  for (int j = 0; j < RPL; ++j) {
+    bool ex = j * 32 + lane < N;
+    t[j] = (t[j] == ms) ? s.tns[j] : MAXINT;
+    if (ex) mn = min(mn, t[j]);
+  }
+  mn = __reduce_min_sync(FULL, mn);
+  bool pred[RPL];
+#pragma unroll
+  for (int j = 0; j < RPL; ++j) pred[j] = (j * 32 + lane < N) && (t[j] == mn);
+  int idx = first_index<RPL>(pred);
+  return idx < 0 ? N - 1 : idx;
+}
+
+// broadcast one field of row `idx` to the warp
+template <int RPL>
+__device__ __forceinline__ int row_field(const int (&f)[RPL], int idx) {
+  // (selected per lane, not by the uniform idx>>5: the latter is turned into a dynamically
+  //  indexed load by the compiler, which demotes the register arrays to local memory)
+  const int lane = threadIdx.x & 31;
+  int v = 0;
+#pragma unroll
+  for (int j = 0; j < RPL; ++j)
+    if (j * 32 + lane == idx) v = f[j];
+  return __shfl_sync(FULL, v, idx & 31);
+}
+
+struct Msg { int type, side, qty, price, oid, tid, ts, tns; };
+
+// JOBA:171-330 : match the incoming order against `book` (Q6, Q7, Q11)
+template <int RPL, bool IS_BID_BOOK>
+__device__ __forceinline__ int match_against(Side<RPL>& book, const Msg& m, int32_t* tr, int N, int T, int lane) {
+  int qtm = m.qty;
+  // exact quick reject: if no existing row can satisfy the price condition the loop body never runs
+  bool possible = IS_BID_BOOK ? (book.best >= m.price) : (book.best <= m.price);
+  if (!(possible && qtm > 0)) return qtm;
+  bool modified = false;
+  for (;;) {
+    int top = top_index<RPL, IS_BID_BOOK>(book, N, lane);
+    int tp = row_field<RPL>(book.p, top);
+    bool cross = IS_BID_BOOK ? (tp >= m.price) : (tp <= m.price);
+    if (!(cross && qtm > 0 && tp != -1)) break;
+    int q_top = row_field<RPL>(book.q, top);
+    int o_top = row_field<RPL>(book.oid, top);
+    int t_top = row_field<RPL>(book.tid, top);
+    int d = wsub(q_top, qtm);
+    int newq = d > 0 ? d : 0;
+    qtm = wsub(qtm, q_top);
+    // first free trade slot: column 4 == -1 (Q6); none -> last row
+    int e = -1;
+    for (int base = 0; base < T && e < 0; base += 32) {
+      int r = base + lane;
+      bool free_ = (r < T) && (tr[r * 8 + 4] == -1);
+      unsigned b = __ballot_sync(FULL, free_);
+      if (b) e = base + __ffs(b) - 1;
+    }
+    if (e < 0) e = T - 1;
+    if (lane == 0) {
+      int4* dst = reinterpret_cast<int4*>(tr + e * 8);
+      dst[0] = make_int4(tp, wmul(wsub(0, m.side), wsub(q_top, newq)), o_top, m.oid);
+      dst[1] = make_int4(m.ts, m.tns, t_top, m.tid);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < RPL; ++j)
+      if (j * 32 + lane == top) book.q[j] = newq;
+    wipe_after(book, top, lane);
+    refresh_best<RPL, IS_BID_BOOK>(book, N, lane);
+    modified = true;
+  }
+  (void)modified;
+  return qtm;
+}
+
+// JOBA:62-83 (Q1, Q2, Q3)
+template <int RPL, bool IS_BID>
+__device__ __forceinline__ void add_order(Side<RPL>& s, const Msg& m, int qrem, int N, int lane) {
+  bool pred[RPL];
+  if (s.simple) {
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) pred[j] = (j * 32 + lane < N) && (s.p[j] == -1);
+  } else {
+#pragma unroll
+    for (int j = 0; j < RPL; ++j)
+      pred[j] = (j * 32 + lane < N) && (s.p[j] == -1 || s.q[j] == -1 || s.oid[j] == -1 || s.tid[j] == -1 ||
+                                        s.ts[j] == -1 || s.tns[j] == -1);
+  }
+  int idx = first_index<RPL>(pred);
+  if (idx < 0) idx = N - 1;
+  int qn = qrem > 0 ? qrem : 0;
+#pragma unroll
+  for (int j = 0; j < RPL; ++j)
+    if (j * 32 + lane == idx) {
+      s.p[j] = m.price; s.q[j] = qn; s.oid[j] = m.oid; s.tid[j] = m.tid; s.ts[j] = m.ts; s.tns[j] = m.tns;
+    }
+  if (m.price == -1 || m.oid == -1 || m.tid == -1 || m.ts == -1 || m.tns == -1) s.simple = false;
+  wipe_after(s, idx, lane);
+  refresh_best<RPL, IS_BID>(s, N, lane);
+}
+
+// JOBA:93-138 (Q4, Q5)
+template <int RPL, bool IS_BID>
+__device__ __forceinline__ void cancel_order(Side<RPL>& s, const Msg& m, int init_id, int N, int lane) {
+  bool pred[RPL];
+#pragma unroll
+  for (int j = 0; j < RPL; ++j) pred[j] = (j * 32 + lane < N) && (s.oid[j] == m.oid);
+  int idx = first_index<RPL>(pred);
+  if (idx < 0) {
+#pragma unroll
+    for (int j = 0; j < RPL; ++j)
+      pred[j] = (j * 32 + lane < N) && (s.p[j] == m.price) && (s.oid[j] <= init_id) && (s.q[j] >= m.qty);
+    idx = first_index<RPL>(pred);
+  }
+  if (idx < 0) idx = N - 1;
+#pragma unroll
+  for (int j = 0; j < RPL; ++j)
+    if (j * 32 + lane == idx) s.q[j] = wsub(s.q[j], m.qty);
+  wipe_after(s, idx, lane);
+  refresh_best<RPL, IS_BID>(s, N, lane);
+}
+
+// JOBA:617-661
+template <int RPL>
+__device__ __forceinline__ void process_message(Side<RPL>& asks, Side<RPL>& bids, const Msg& m, int32_t* tr,
+                                                int N, int T, int init_id, int lane) {
+  const int s = m.side, t = m.type;
+  int idx = (((s == 1 && t == 1) || (s == -1 && t == 4)) ? 1 : 0) + ((s == -1 && (t == 2 || t == 3)) ? 2 : 0) +
+            ((s == 1 && (t == 2 || t == 3)) ? 3 : 0) + ((s == 0 && t == 0) ? 4 : 0);
+  if (idx == 0) {          // ask_lim :417-453 (also every (type, side) outside the table, Q8)
+    int q = match_against<RPL, true>(bids, m, tr, N, T, lane);
+    add_order<RPL, false>(asks, m, q, N, lane);
+  } else if (idx == 1) {   // bid_lim :356-391
+    int q = match_against<RPL, false>(asks, m, tr, N, T, lane);
+    add_order<RPL, true>(bids, m, q, N, lane);
+  } else if (idx == 2) {   // ask_cancel :455-478
+    cancel_order<RPL, false>(asks, m, init_id, N, lane);
+  } else if (idx == 3) {   // bid_cancel :392-415
+    cancel_order<RPL, true>(bids, m, init_id, N, lane);
+  }                        // 4: doNothing :334-355
+}
+
+// ---------------------------------------------------------------- staging <-> registers
+template <int RPL>
+__device__ __forceinline__ void regs_from_smem(Side<RPL>& s, const int32_t* sm, int N, int lane) {
+  bool simple = true, clean = true;
+#pragma unroll
+  for (int j = 0; j < RPL; ++j) {
+    int r = j * 32 + lane;
+    if (r < N) {
+      const int2* row = reinterpret_cast<const int2*>(sm + r * 6);
+      int2 a = row[0], b = row[1], c = row[2];
+      s.p[j] = a.x; s.q[j] = a.y; s.oid[j] = b.x; s.tid[j] = b.y; s.ts[j] = c.x; s.tns[j] = c.y;
+      bool any = a.x == -1 || a.y == -1 || b.x == -1 || b.y == -1 || c.x == -1 || c.y == -1;
+      bool all = a.x == -1 && a.y == -1 && b.x == -1 && b.y == -1 && c.x == -1 && c.y == -1;
+      if (any != (a.x == -1)) simple = false;
+      if (a.y <= 0 && !all) clean = false;
+    } else {
+      wipe_row(s, j);
+    }
+  }
+  s.simple = __all_sync(FULL, simple);
+  s.clean = __all_sync(FULL, clean);
+}
+
+template <int RPL>
+__device__ __forceinline__ void regs_to_smem(const Side<RPL>& s, int32_t* sm, int N, int lane) {
+#pragma unroll
+  for (int j = 0; j < RPL; ++j) {
+    int r = j * 32 + lane;
+    if (r < N) {
+      int2* row = reinterpret_cast<int2*>(sm + r * 6);
+      row[0] = make_int2(s.p[j], s.q[j]);
+      row[1] = make_int2(s.oid[j], s.tid[j]);
+      row[2] = make_int2(s.ts[j], s.tns[j]);
+    }
+  }
+}
+
+__device__ __forceinline__ void warp_copy_g2s(int32_t* dst, const int32_t* src, int n, int lane) {
+  for (int i = lane; i < n; i += 32) dst[i] = src[i];
+}
+__device__ __forceinline__ void warp_copy_s2g(int32_t* dst, const int32_t* src, int n, int lane) {
+  for (int i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+// ---------------------------------------------------------------- deterministic log1p
+// Same operation sequence as oracle/lob_oracle.{py,c}: IEEE double mul/add/div only
+// (__dmul_rn/__dadd_rn/__ddiv_rn are never contracted into FMAs).
+__device__ __forceinline__ float vm_log1p_f32(float x) {
+  const double LN2_HI = 0x1.62e42fee00000p-1, LN2_LO = 0x1.a39ef35793c76p-33, SQRT2 = 0x1.6a09e667f3bcdp+0;
+  const double C[13] = {1.0 / 3, 1.0 / 5, 1.0 / 7, 1.0 / 9, 1.0 / 11, 1.0 / 13, 1.0 / 15, 1.0 / 17,
+                        1.0 / 19, 1.0 / 21, 1.0 / 23, 1.0 / 25, 1.0 / 27};
+  double xd = (double)x;
+  if (xd != xd || xd < -1.0) return __int_as_float(0x7fc00000);
+  if (xd == -1.0) return __int_as_float(0xff800000);
+  if (xd > 1.7e308) return __int_as_float(0x7f800000);
+  double y = __dadd_rn(1.0, xd);
+  long long bits = __double_as_longlong(y);
+  int k = (int)((bits >> 52) & 0x7FF) - 1023;
+  bits = (bits & 0x000FFFFFFFFFFFFFll) | 0x3FF0000000000000ll;
+  double m = __longlong_as_double(bits);
+  if (m > SQRT2) { m = __dmul_rn(m, 0.5); k += 1; }
+  double f = __dadd_rn(m, -1.0);
+  double s = __ddiv_rn(f, __dadd_rn(2.0, f));
+  double z = __dmul_rn(s, s);
+  double p = C[12];
+#pragma unroll
+  for (int i = 11; i >= 0; --i) p = __dadd_rn(__dmul_rn(p, z), C[i]);
+  p = __dmul_rn(p, z);
+  double s2 = __dmul_rn(2.0, s);
+  double logm = __dadd_rn(s2, __dmul_rn(s2, p));
+  double kd = (double)k;
+  double r = __dadd_rn(__dmul_rn(kd, LN2_HI), __dadd_rn(__dmul_rn(kd, LN2_LO), logm));
+  return __double2float_rn(r);
+}
+
+__device__ __forceinline__ int bar_length(int vol, int W) {
+  unsigned u = (unsigned)(vol > 0 ? vol : 0) + 1u;
+  int e = 31 - __clz(u);
+  unsigned frac2 = ((u << (31 - e)) >> 29) & 3u;
+  int l4 = 4 * e + (int)frac2;
+  int len = (l4 * W) >> 6;
+  return len < W ? len : W;
+}
+
+// ---------------------------------------------------------------- stage 2 on a register-resident book
+// JOBA:1108-1140 (+ :1075-1106), vision_env.py:2804-2854, docs/RENDER_SPEC.md
+template <int RPL>
+__device__ __forceinline__ void render_env(const Side<RPL>& asks, const Side<RPL>& bids, const LobParams& P, int e,
+                                           bool have_mid, float mid, int32_t* scratch, int lane) {
+  const int N = P.N, n = P.n_levels;
+  if (P.raw || P.l2 || P.norm) {
+    int lp[2] = {-1, -1}, lv[2] = {0, 0};   // this lane's level: price / volume per channel
+    int cumv[2] = {0, 0};
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      const Side<RPL>& s = ch == 0 ? asks : bids;
+      bool have_prev = false;
+      int prev = 0;
+      int cum = 0;
+      for (int l = 0; l < n; ++l) {
+        int cur = MAXINT;
+        bool cand = false;
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+          int key = ch == 0 ? (s.p[j] == -1 ? MAXINT : s.p[j]) : (int)(0u - (unsigned)s.p[j]);
+          bool c = (j * 32 + lane < N) && (!have_prev || key > prev);
+          cand |= c;
+          if (c) cur = min(cur, key);
+        }
+        bool found = __any_sync(FULL, cand);
+        cur = __reduce_min_sync(FULL, cur);
+        int price;
+        if (found) { prev = cur; have_prev = true; price = ch == 0 ? (cur == MAXINT ? -1 : cur) : (int)(0u - (unsigned)cur); }
+        else { price = -1; prev = MAXINT; have_prev = true; }
+        int v = 0;
+#pragma unroll
+        for (int j = 0; j < RPL; ++j)
+          if (j * 32 + lane < N && s.p[j] == price) v = wadd(v, s.q[j]);
+        v = __reduce_add_sync(FULL, v);
+        if (v < 0) v = 0;
+        int clean = price != -1 ? v : 0;
+        cum = wadd(cum, clean);
+        if (lane == l) { lp[ch] = price; lv[ch] = v; cumv[ch] = price != -1 ? cum : 0; }
+      }
+    }
+    if (lane < n) {
+      if (P.raw) reinterpret_cast<int4*>(P.raw + (size_t)e * n * 4)[lane] = make_int4(lp[0], lp[1], lv[0], lv[1]);
+      if (P.l2) reinterpret_cast<int4*>(P.l2 + (size_t)e * n * 4)[lane] = make_int4(lp[0], lv[0], lp[1], lv[1]);
+      if (P.norm && have_mid) {
+        const float tick = (float)P.tick;
+        float ga = 0.f, gb = 0.f;
+        if (lp[0] != -1) ga = __fdiv_rn(__fsub_rn((float)lp[0], mid), tick);
+        if (lp[1] != -1) gb = __fdiv_rn(__fsub_rn(mid, (float)lp[1]), tick);
+        float va = vm_log1p_f32((float)(lp[0] != -1 ? lv[0] : 0));
+        float vb = vm_log1p_f32((float)(lp[1] != -1 ? lv[1] : 0));
+        float ca = vm_log1p_f32((float)cumv[0]);
+        float cb = vm_log1p_f32((float)cumv[1]);
+        float2* o = reinterpret_cast<float2*>(P.norm + (size_t)e * n * 6 + lane * 6);
+        o[0] = make_float2(ga, gb);
+        o[1] = make_float2(va, vb);
+        o[2] = make_float2(ca, cb);
+      }
+    }
+  }
+  if (P.image) {
+    const int H = P.H, W = P.W;
+    // per-row volume histogram (both channels) in shared scratch: [2][H]
+    for (int i = lane; i < 2 * H; i += 32) scratch[i] = 0;
+    __syncwarp();
+    const int ba = best_price_out<RPL, false>(asks), bb = best_price_out<RPL, true>(bids);
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) {
+      if (j * 32 + lane < N) {
+        if (ba != -1 && asks.p[j] != -1) {
+          long long d = (long long)asks.p[j] - ba;
+          if (d >= 0) { long long r = d / P.tick; if (r < H) atomicAdd(&scratch[(int)r], asks.q[j]); }
+        }
+        if (bb != -1 && bids.p[j] != -1) {
+          long long d = (long long)bb - bids.p[j];
+          if (d >= 0) { long long r = d / P.tick; if (r < H) atomicAdd(&scratch[H + (int)r], bids.q[j]); }
+        }
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < 2 * H; i += 32) scratch[i] = bar_length(scratch[i], W);
+    __syncwarp();
+    if (P.img_dtype == VITMARL_IMG_BF16) {
+      // 16 bytes = 4 pixels x 2 channels x bf16
+      uint4* img = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.image) + (size_t)e * H * W * 2);
+      const int chunks_per_row = W / 4, total = H * chunks_per_row;
+      for (int c = lane; c < total; c += 32) {
+        int r = c / chunks_per_row, x0 = (c - r * chunks_per_row) * 4;
+        int la = scratch[r], lb = scratch[H + r];
+        unsigned w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = ((x0 + k) < la ? 0x3F80u : 0u) | ((x0 + k) < lb ? 0x3F800000u : 0u);
+        img[c] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    } else {
+      // 16 bytes = 8 pixels x 2 channels x u8
+      uint4* img = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(P.image) + (size_t)e * H * W * 2);
+      const int chunks_per_row = W / 8, total = H * chunks_per_row;
+      for (int c = lane; c < total; c += 32) {
+        int r = c / chunks_per_row, x0 = (c - r * chunks_per_row) * 8;
+        int la = scratch[r], lb = scratch[H + r];
+        unsigned w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          int x = x0 + 2 * k;
+          w[k] = (x < la ? 1u : 0u) | (x < lb ? 0x100u : 0u) | ((x + 1) < la ? 0x10000u : 0u) | ((x + 1) < lb ? 0x1000000u : 0u);
+        }
+        img[c] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------- the kernel
+template <int RPL>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) lob_kernel(const LobParams P) {
+  extern __shared__ __align__(16) int32_t smem[];
+  __shared__ __align__(8) uint64_t bars[kWarpsPerCta];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * kWarpsPerCta + warp;
+  if (e >= P.E) return;   // whole warp exits; no block-wide barriers are used below
+
+  const int N = P.N, T = P.T, M = P.M;
+  const int side_words = N * 6, trade_words = P.do_step ? T * 8 : 0;
+  int32_t* sm_asks = smem + (size_t)warp * (2 * side_words + trade_words);
+  int32_t* sm_bids = sm_asks + side_words;
+  int32_t* sm_tr = sm_bids + side_words;
+  const uint32_t bar = smem_u32(&bars[warp]);
+
+  const int32_t* g_asks = P.asks_in + (size_t)e * side_words;
+  const int32_t* g_bids = P.bids_in + (size_t)e * side_words;
+
+  // ---- load: TMA 1-D bulk copies (one elected lane) --------------------------------------
+  if (P.bulk_ok) {
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    if (lane == 0) {
+      uint32_t bytes = 2u * side_words * 4u + ((P.do_step && P.trades_in) ? trade_words * 4u : 0u);
+      mbar_arrive_expect_tx(bar, bytes);
+      bulk_g2s(smem_u32(sm_asks), g_asks, side_words * 4, bar);
+      bulk_g2s(smem_u32(sm_bids), g_bids, side_words * 4, bar);
+      if (P.do_step && P.trades_in) bulk_g2s(smem_u32(sm_tr), P.trades_in + (size_t)e * trade_words, trade_words * 4, bar);
+    }
+  } else {
+    warp_copy_g2s(sm_asks, g_asks, side_words, lane);
+    warp_copy_g2s(sm_bids, g_bids, side_words, lane);
+    if (P.do_step && P.trades_in) warp_copy_g2s(sm_tr, P.trades_in + (size_t)e * trade_words, trade_words, lane);
+  }
+  // overlapped with the copies: fresh trades (marl_env.py:377) and the first message block
+  if (P.do_step && !P.trades_in) {
+    int4* t4 = reinterpret_cast<int4*>(sm_tr);
+    for (int i = lane; i < trade_words / 4; i += 32) t4[i] = make_int4(-1, -1, -1, -1);
+  }
+  const int4* g_msgs = reinterpret_cast<const int4*>(P.msgs + (size_t)e * M * 8);
+  int4 nm0 = make_int4(0, 0, 0, 0), nm1 = nm0;
+  if (P.do_step && lane < M) { nm0 = ld_nc_v4(g_msgs + 2 * lane); nm1 = ld_nc_v4(g_msgs + 2 * lane + 1); }
+
+  if (P.bulk_ok) mbar_wait(bar, 0);
+  __syncwarp();
+
+  Side<RPL> asks, bids;
+  regs_from_smem<RPL>(asks, sm_asks, N, lane);
+  regs_from_smem<RPL>(bids, sm_bids, N, lane);
+  refresh_best<RPL, false>(asks, N, lane);
+  refresh_best<RPL, true>(bids, N, lane);
+
+  float mid = 0.f;
+  bool have_mid = false;
+  if (P.do_step) {
+    // ---- message loop: blocks of 32 messages, one per lane, next block prefetched --------
+    const int keep0 = M - P.n_keep;   // first message index whose best bid/ask is reported
+    int carry_a = -1, carry_b = -1;   // ffill carries across blocks
+    int last_a = 0, last_b = 0;
+    for (int base = 0; base < M; base += 32) {
+      int4 m0 = nm0, m1 = nm1;
+      int nb = base + 32 + lane;
+      if (nb < M) { nm0 = ld_nc_v4(g_msgs + 2 * nb); nm1 = ld_nc_v4(g_msgs + 2 * nb + 1); }
+      int oa_p = -1, oa_v = 0, ob_p = -1, ob_v = 0;   // this lane's message outputs
+      const int cnt = min(32, M - base);
+      for (int i = 0; i < cnt; ++i) {
+        Msg m;
+        m.type = __shfl_sync(FULL, m0.x, i); m.side = __shfl_sync(FULL, m0.y, i);
+        m.qty = __shfl_sync(FULL, m0.z, i);  m.price = __shfl_sync(FULL, m0.w, i);
+        m.oid = __shfl_sync(FULL, m1.x, i);  m.tid = __shfl_sync(FULL, m1.y, i);
+        m.ts = __shfl_sync(FULL, m1.z, i);   m.tns = __shfl_sync(FULL, m1.w, i);
+        process_message<RPL>(asks, bids, m, sm_tr, N, T, P.init_id, lane);
+        if (lane == i) {
+          oa_p = best_price_out<RPL, false>(asks); oa_v = asks.vol;
+          ob_p = best_price_out<RPL, true>(bids);  ob_v = bids.vol;
+        }
+      }
+      const int gi = base + lane;   // global message index of this lane
+      if (P.do_ffill) {
+        // marl_env.py:685-711 on both tracks
+        if (gi == 0) {
+          if (oa_p == -1) { oa_p = P.last_ask_price[e]; oa_v = 0; }
+          if (ob_p == -1) { ob_p = P.last_bid_price[e]; ob_v = 0; }
+        }
+        if (oa_p == -1) oa_v = 0;
+        if (ob_p == -1) ob_v = 0;
+        unsigned lower = (lane == 31) ? FULL : ((2u << lane) - 1u);
+        unsigned va = __ballot_sync(FULL, lane < cnt && oa_p != -1) & lower;
+        unsigned vb = __ballot_sync(FULL, lane < cnt && ob_p != -1) & lower;
+        int sa = __shfl_sync(FULL, oa_p, va ? 31 - __clz(va) : 0);
+        int sb = __shfl_sync(FULL, ob_p, vb ? 31 - __clz(vb) : 0);
+        oa_p = va ? sa : carry_a;
+        ob_p = vb ? sb : carry_b;
+        carry_a = __shfl_sync(FULL, oa_p, cnt - 1);
+        carry_b = __shfl_sync(FULL, ob_p, cnt - 1);
+        last_a = carry_a; last_b = carry_b;
+      }
+      if (lane < cnt && gi >= keep0) {
+        if (P.best_asks) reinterpret_cast<int2*>(P.best_asks + (size_t)e * P.n_keep * 2)[gi - keep0] = make_int2(oa_p, oa_v);
+        if (P.best_bids) reinterpret_cast<int2*>(P.best_bids + (size_t)e * P.n_keep * 2)[gi - keep0] = make_int2(ob_p, ob_v);
+      }
+    }
+    if (P.do_ffill) {
+      mid = __fdiv_rn((float)wadd(last_b, last_a), 2.0f);   // marl_env.py:467 (int32 sum -> f32 -> /2)
+      have_mid = true;
+      if (lane == 0 && P.mid_out) P.mid_out[e] = mid;
+    }
+    // ---- store: registers -> shared (AoS) -> TMA bulk stores ------------------------------
+    regs_to_smem<RPL>(asks, sm_asks, N, lane);
+    regs_to_smem<RPL>(bids, sm_bids, N, lane);
+    if (P.bulk_ok) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        bulk_s2g(P.asks_out + (size_t)e * side_words, smem_u32(sm_asks), side_words * 4);
+        bulk_s2g(P.bids_out + (size_t)e * side_words, smem_u32(sm_bids), side_words * 4);
+        bulk_s2g(P.trades_out + (size_t)e * trade_words, smem_u32(sm_tr), trade_words * 4);
+        bulk_commit();
+      }
+    } else {
+      __syncwarp();
+      warp_copy_s2g(P.asks_out + (size_t)e * side_words, sm_asks, side_words, lane);
+      warp_copy_s2g(P.bids_out + (size_t)e * side_words, sm_bids, side_words, lane);
+      warp_copy_s2g(P.trades_out + (size_t)e * trade_words, sm_tr, trade_words, lane);
+    }
+  } else if (P.mid_in) {
+    mid = P.mid_in[e];
+    have_mid = true;
+  }
+
+  if (!P.do_step && (P.best_asks || P.best_bids)) {   // get_best_bid_and_ask_inclQuants
+    if (lane == 0) {
+      if (P.best_asks) reinterpret_cast<int2*>(P.best_asks)[e] = make_int2(best_price_out<RPL, false>(asks), asks.vol);
+      if (P.best_bids) reinterpret_cast<int2*>(P.best_bids)[e] = make_int2(best_price_out<RPL, true>(bids), bids.vol);
+    }
+  }
+
+  if (P.do_render) {
+    // scratch for the raster histogram: the trades slab is still being read by the bulk store,
+    // so the render-only kernel uses the (idle) book staging area and the fused kernel waits.
+    int32_t* scratch = sm_asks;
+    if (P.do_step && P.image) {
+      if (P.bulk_ok && lane == 0) bulk_wait_read0();
+      __syncwarp();
+    }
+    render_env<RPL>(asks, bids, P, e, have_mid, mid, scratch, lane);
+  }
+  if (P.do_step && P.bulk_ok && lane == 0) bulk_wait_read0();   // smem must outlive the bulk reads
+}
+
+// ---------------------------------------------------------------- host-side launch
+static int launch_lob(cudaStream_t stream, LobParams& P) {
+  if (P.E == 0) return VITMARL_OK;
+  if (P.E < 0 || P.N < 1 || P.N > 256 || !P.asks_in || !P.bids_in) return VITMARL_EINVAL;
+  if (P.do_step) {
+    if (P.T < 1 || P.T > 1024 || P.M < 0 || P.n_keep < 0 || !P.asks_out || !P.bids_out || !P.trades_out) return VITMARL_EINVAL;
+    if (P.M > 0 && !P.msgs) return VITMARL_EINVAL;
+    if (P.n_keep > P.M) P.n_keep = P.M;
+    if (P.do_ffill && (P.M < 1 || !P.last_ask_price || !P.last_bid_price || P.n_keep != P.M)) return VITMARL_EINVAL;
+    if (P.M > 0 && (reinterpret_cast<uintptr_t>(P.msgs) & 15)) return VITMARL_EINVAL;
+    if (P.n_keep > 0 && ((P.best_asks && (reinterpret_cast<uintptr_t>(P.best_asks) & 7)) ||
+                         (P.best_bids && (reinterpret_cast<uintptr_t>(P.best_bids) & 7)))) return VITMARL_EINVAL;
+  }
+  if (P.do_render) {
+    if (P.n_levels < 1 || P.n_levels > 32 || P.tick < 1) return VITMARL_EINVAL;
+    if ((P.raw && (reinterpret_cast<uintptr_t>(P.raw) & 15)) || (P.l2 && (reinterpret_cast<uintptr_t>(P.l2) & 15)) ||
+        (P.norm && (reinterpret_cast<uintptr_t>(P.norm) & 7))) return VITMARL_EINVAL;
+    if (P.image) {
+      if (P.img_dtype != VITMARL_IMG_U8 && P.img_dtype != VITMARL_IMG_BF16) return VITMARL_EINVAL;
+      if (P.H < 1 || P.W < 8 || (P.W % 8) || 2 * P.H > 12 * P.N) return VITMARL_EINVAL;
+      if (reinterpret_cast<uintptr_t>(P.image) & 15) return VITMARL_EINVAL;
+    }
+  }
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  P.bulk_ok = ((P.N * 24) % 16 == 0) && al16(P.asks_in) && al16(P.bids_in) &&
+              (!P.do_step || (al16(P.asks_out) && al16(P.bids_out) && al16(P.trades_out) && (!P.trades_in || al16(P.trades_in))));
+  const int rpl = (P.N + 31) / 32;
+  const size_t smem = (size_t)kWarpsPerCta * (2 * P.N * 6 + (P.do_step ? P.T * 8 : 0)) * sizeof(int32_t);
+  const dim3 grid((P.E + kWarpsPerCta - 1) / kWarpsPerCta), block(kWarpsPerCta * 32);
+  cudaError_t err = cudaSuccess;
+#define VM_LAUNCH(R)                                                                                      \
+  do {                                                                                                    \
+    if (smem > 48 * 1024) err = cudaFuncSetAttribute(lob_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (err == cudaSuccess) lob_kernel<R><<<grid, block, smem, stream>>>(P);                              \
+  } while (0)
+  if (rpl <= 1) VM_LAUNCH(1);
+  else if (rpl <= 2) VM_LAUNCH(2);
+  else if (rpl <= 4) VM_LAUNCH(4);
+  else VM_LAUNCH(8);
+#undef VM_LAUNCH
+  if (err == cudaSuccess) err = cudaGetLastError();
+  return check_cuda(err);
+}
+
+}  // namespace vitmarl
+
+using vitmarl::LobParams;
+
+extern "C" int vitmarl_lob_step(void* stream, int E, int N, int T, int M, int n_keep,
+                                const int32_t* asks_in, const int32_t* bids_in, const int32_t* trades_in,
+                                const int32_t* msgs, int32_t* asks_out, int32_t* bids_out, int32_t* trades_out,
+                                int32_t* best_asks, int32_t* best_bids, int cancel_mode, int32_t init_id) {
+  if (cancel_mode != 0 && cancel_mode != 1) return VITMARL_EUNSUPPORTED;   // JOBA:130-163 need jax.random
+  LobParams P{};
+  P.E = E; P.N = N; P.T = T; P.M = M; P.n_keep = n_keep; P.init_id = init_id;
+  P.asks_in = asks_in; P.bids_in = bids_in; P.trades_in = trades_in; P.msgs = msgs;
+  P.asks_out = asks_out; P.bids_out = bids_out; P.trades_out = trades_out;
+  P.best_asks = best_asks; P.best_bids = best_bids;
+  P.do_step = 1;
+  return vitmarl::launch_lob(static_cast<cudaStream_t>(stream), P);
+}
+
+extern "C" int vitmarl_lob_best_bid_ask(void* stream, int E, int N, const int32_t* asks, const int32_t* bids,
+                                        int32_t* best_ask, int32_t* best_bid) {
+  if (!best_ask || !best_bid) return VITMARL_EINVAL;
+  LobParams P{};
+  P.E = E; P.N = N; P.asks_in = asks; P.bids_in = bids; P.best_asks = best_ask; P.best_bids = best_bid;
+  return vitmarl::launch_lob(static_cast<cudaStream_t>(stream), P);
+}
+
+extern "C" int vitmarl_lob_render(void* stream, int E, int N, int n_levels, int tick_size,
+                                  const int32_t* asks, const int32_t* bids, const float* mid_price,
+                                  int32_t* raw, int32_t* l2, float* norm, void* image, int img_dtype, int H, int W) {
+  if (norm && !mid_price) return VITMARL_EINVAL;
+  LobParams P{};
+  P.E = E; P.N = N; P.asks_in = asks; P.bids_in = bids;
+  P.do_render = 1; P.n_levels = n_levels; P.tick = tick_size; P.mid_in = mid_price;
+  P.raw = raw; P.l2 = l2; P.norm = norm;
+  P.image = (img_dtype == VITMARL_IMG_NONE) ? nullptr : image; P.img_dtype = img_dtype; P.H = H; P.W = W;
+  return vitmarl::launch_lob(static_cast<cudaStream_t>(stream), P);
+}
+
+extern "C" int vitmarl_env_step(void* stream, int E, int N, int T, int M,
+                                const int32_t* asks_in, const int32_t* bids_in, const int32_t* msgs,
+                                const int32_t* last_ask_price, const int32_t* last_bid_price,
+                                int32_t* asks_out, int32_t* bids_out, int32_t* trades_out,
+                                int32_t* best_asks, int32_t* best_bids, float* mid_price,
+                                int n_levels, int tick_size, int32_t* raw, int32_t* l2, float* norm,
+                                void* image, int img_dtype, int H, int W, int cancel_mode, int32_t init_id) {
+  if (cancel_mode != 0 && cancel_mode != 1) return VITMARL_EUNSUPPORTED;
+  LobParams P{};
+  P.E = E; P.N = N; P.T = T; P.M = M; P.n_keep = M; P.init_id = init_id;
+  P.asks_in = asks_in; P.bids_in = bids_in; P.msgs = msgs;
+  P.asks_out = asks_out; P.bids_out = bids_out; P.trades_out = trades_out;
+  P.best_asks = best_asks; P.best_bids = best_bids;
+  P.do_step = 1; P.do_ffill = 1; P.last_ask_price = last_ask_price; P.last_bid_price = last_bid_price; P.mid_out = mid_price;
+  P.do_render = (raw || l2 || norm || (image && img_dtype != VITMARL_IMG_NONE)) ? 1 : 0;
+  P.n_levels = n_levels; P.tick = tick_size; P.raw = raw; P.l2 = l2; P.norm = norm;
+  P.image = (img_dtype == VITMARL_IMG_NONE) ? nullptr : image; P.img_dtype = img_dtype; P.H = H; P.W = W;
+  return vitmarl::launch_lob(static_cast<cudaStream_t>(stream), P);
+}

@@ -1,0 +1,77 @@
+"""Fused environment step: the book part of ``MARLEnv.step_env``
+(``gymnax_exchange/jaxen/marl_env.py:377-393, 466-467, 637-662``) as ONE kernel launch:
+order-book scan -> forward-filled best prices -> mid price -> vision observation
+(+ optional H x W raster feeding the ViT).  State stays resident in HBM between steps."""
+from __future__ import annotations
+
+import dataclasses
+from typing import Optional
+
+import torch
+
+from . import _capi
+from .config import World_EnvironmentConfig
+from .jaxob import _chk, _ptr, _stream, get_best_bid_and_ask_inclQuants
+
+__all__ = ["BookState", "StepOutput", "reset", "step"]
+
+
+@dataclasses.dataclass
+class BookState:
+    """The leaves of WorldState the hot path touches (StatesandParams.py:58-79)."""
+    ask_raw_orders: torch.Tensor      # int32 [E,N,6]
+    bid_raw_orders: torch.Tensor      # int32 [E,N,6]
+    trades: torch.Tensor              # int32 [E,T,8]
+    best_asks: torch.Tensor           # int32 [E,M,2]
+    best_bids: torch.Tensor           # int32 [E,M,2]
+    mid_price: torch.Tensor           # float32 [E]
+
+
+@dataclasses.dataclass
+class StepOutput:
+    vision_obs: Optional[torch.Tensor]     # float32 [E,n,3,2]
+    vision_raw: Optional[torch.Tensor]     # int32   [E,n,2,2]
+    image: Optional[torch.Tensor]          # [E,H,W,2] bf16/u8
+
+
+def reset(cfg: World_EnvironmentConfig, asks: torch.Tensor, bids: torch.Tensor, num_msgs_per_step: int) -> BookState:
+    """World part of MARLEnv.reset_env (marl_env.py:186-190): tile the initial best bid/ask,
+    mid = float32((best_bid + best_ask) / 2)."""
+    ba, bb = get_best_bid_and_ask_inclQuants(cfg, asks, bids)
+    E = asks.shape[0]
+    mid = ((bb[:, 0] + ba[:, 0]).to(torch.float32) / 2.0)
+    trades = torch.full((E, cfg.nTradesLogged, 8), -1, dtype=torch.int32, device=asks.device)
+    return BookState(asks, bids, trades, ba[:, None, :].repeat(1, num_msgs_per_step, 1).contiguous(),
+                     bb[:, None, :].repeat(1, num_msgs_per_step, 1).contiguous(), mid)
+
+
+def step(cfg: World_EnvironmentConfig, state: BookState, msgs: torch.Tensor, *, n_levels: int = 10,
+         want_obs: bool = True, want_raw: bool = False, image_hw=None, image_dtype=torch.bfloat16,
+         inplace: bool = True) -> tuple[BookState, StepOutput]:
+    """One fused env step for all E environments (msgs int32 [E,M,8])."""
+    asks, bids = _chk(state.ask_raw_orders, "asks", 6), _chk(state.bid_raw_orders, "bids", 6)
+    msgs = _chk(msgs, "msgs", 8)
+    E, N, _ = asks.shape
+    M, T = msgs.shape[1], cfg.nTradesLogged
+    dev = asks.device
+    last_a = state.best_asks[:, -1, 0].contiguous()
+    last_b = state.best_bids[:, -1, 0].contiguous()
+    a_out = asks if inplace else torch.empty_like(asks)
+    b_out = bids if inplace else torch.empty_like(bids)
+    t_out = state.trades if (inplace and state.trades.shape == (E, T, 8)) else torch.empty((E, T, 8), dtype=torch.int32, device=dev)
+    ba = torch.empty((E, M, 2), dtype=torch.int32, device=dev)
+    bb = torch.empty((E, M, 2), dtype=torch.int32, device=dev)
+    mid = torch.empty((E,), dtype=torch.float32, device=dev)
+    raw = torch.empty((E, n_levels, 2, 2), dtype=torch.int32, device=dev) if want_raw else None
+    norm = torch.empty((E, n_levels, 3, 2), dtype=torch.float32, device=dev) if want_obs else None
+    img, code, H, W = None, _capi.IMG_NONE, 0, 0
+    if image_hw is not None:
+        H, W = image_hw
+        code = {torch.bfloat16: _capi.IMG_BF16, torch.uint8: _capi.IMG_U8}[image_dtype]
+        img = torch.empty((E, H, W, 2), dtype=image_dtype, device=dev)
+    rc = _capi.lib().vitmarl_env_step(_stream(), E, N, T, M, _ptr(asks), _ptr(bids), _ptr(msgs), _ptr(last_a), _ptr(last_b),
+                                      _ptr(a_out), _ptr(b_out), _ptr(t_out), _ptr(ba), _ptr(bb), _ptr(mid),
+                                      n_levels, cfg.tick_size, _ptr(raw), None, _ptr(norm), _ptr(img), code, H, W,
+                                      int(cfg.cancel_mode), int(cfg.init_id))
+    _capi.check(rc)
+    return BookState(a_out, b_out, t_out, ba, bb, mid), StepOutput(norm, raw, img)
