@@ -111,6 +111,23 @@ int vitmarl_env_step(void* stream, int E, int N, int T, int M,
                      void* image, int img_dtype, int H, int W,
                      int cancel_mode, int32_t init_id);
 
+/* ---- stage 3: ViT encoder ---------------------------------------------------------- */
+
+#define VITMARL_EPI_STORE_BF16 0 /* C(bf16) = acc (+bias) (+pos[row % period]) (+residual)        */
+#define VITMARL_EPI_BIAS_GELU 1  /* C(bf16) = gelu_tanh(acc + bias)                              */
+#define VITMARL_EPI_STORE_F32 2  /* C(fp32) = acc (+bias)                                        */
+#define VITMARL_EPI_ATOMIC_F32 3 /* C(fp32) += out_scale * acc  (split-K, C pre-initialised)     */
+
+/* The tensor-core building block of the encoder (TMA -> tcgen05.mma -> TMEM epilogue):
+ *   C[M,N] = epi( A[M,K] . B[N,K]^T ),  A/B bf16, fp32 accumulate.
+ * Operand X is K-major when element (r,k) is X[r*ldx + k] (activations [tokens,features],
+ * flax Dense kernels stored [out,in]) and MN-major when it is X[k*ldx + r].
+ * Limits: N % 64 == 0, K % 8 == 0, lda/ldb % 8 == 0, 16-byte aligned bases. */
+int vitmarl_gemm_bf16(void* stream, int M, int N, int K,
+                      const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major,
+                      void* C, int ldc, int epi, const float* bias, const void* residual, int ldr,
+                      const float* pos, int pos_period, float out_scale);
+
 #ifdef __cplusplus
 }
 #endif

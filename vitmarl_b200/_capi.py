@@ -41,6 +41,7 @@ SIGNATURES = {
     "vitmarl_lob_step": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, ctypes.c_int32]),
     "vitmarl_lob_best_bid_ask": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "vitmarl_lob_render": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I]),
+    "vitmarl_gemm_bf16": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, ctypes.c_float]),
     "vitmarl_env_step": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                               _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, ctypes.c_int32]),
 }

@@ -1,0 +1,288 @@
+// bf16 GEMM on the 5th-gen tensor cores: TMA (128B swizzle) -> smem ring -> tcgen05.mma
+// (accumulators in TMEM, double buffered) -> tcgen05.ld epilogue with fused bias / GELU /
+// residual / positional-embedding add.  Persistent, warp specialised:
+//   warp 0   TMA producer (one elected lane)
+//   warp 1   TMEM allocator + MMA issuer (one elected lane)
+//   warps 2-5 epilogue, warp w owns TMEM lanes 32*(w%4) .. +31 (one output row per thread)
+//
+//   C[M,N] = epi( A[M,K] . B[N,K]^T )        A, B bf16; fp32 accumulate
+// A / B may each be "K-major" (contraction index contiguous: activations [tokens, features],
+// weights [out, in]) or "MN-major" (the operand is stored transposed, e.g. dW = dY^T X where
+// both operands have the token index as the slow dimension).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tc_common.cuh"
+#include "vit_kernels.h"
+#include "../../include/vitmarl_b200.h"
+
+namespace vitmarl {
+
+constexpr int BM = 128, BK = 64;
+constexpr int kGemmThreads = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = BN >= 192 ? 5 : (BN >= 128 ? 6 : 8);
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = BN * 2 <= 128 ? 128 : (BN * 2 <= 256 ? 256 : 512);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  int M, N, K;            // GEMM extents (K = contraction)
+  int kb_per_split;       // k-blocks per split-K slice
+  int splits;
+  int epi;                // GemmEpi
+  void* C; int ldc;       // bf16 or fp32 (atomic) output, row pitch in elements
+  const float* bias;      // [N] or null
+  const __nv_bfloat16* residual; int ldr;   // [M, N] bf16 or null
+  const float* pos; int pos_period;         // [pos_period, N] fp32 (row % pos_period) or null
+  float out_scale;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = p.N / BN;
+  const int KB = (p.K + BK - 1) / BK;
+  const int num_work = tiles_m * tiles_n * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int split = w % p.splits, tile = w / p.splits;
+        const int tn = tile % tiles_n, tm = tile / tiles_n;
+        const int kb0 = split * p.kb_per_split, kb1 = min(KB, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_arrive_expect_tx(full_bar(s), Cfg::kStageBytes);
+          const uint32_t sa = smem_base + s * Cfg::kStageBytes, sb = sa + Cfg::kABytes;
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, kb * BK, tm * BM, full_bar(s));
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * 8192, &tmA, tm * BM + i * 64, kb * BK, full_bar(s));
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, kb * BK, tn * BN, full_bar(s));
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * 8192, &tmB, tn * BN + i * 64, kb * BK, full_bar(s));
+          }
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      int s = 0; uint32_t ph = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+        const int split = w % p.splits;
+        const int kb0 = split * p.kb_per_split, kb1 = min(KB, kb0 + p.kb_per_split);
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * Cfg::kStageBytes, sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = A_MN ? umma_desc_sw128(sa + k * 2048, 8192, 1024) : umma_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_desc_sw128(sb + k * 2048, 8192, 1024) : umma_desc_sw128(sb + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));                     // frees the smem stage when these MMAs retire
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));                     // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int quad = warp & 3;
+    int it = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      const int tile = w / p.splits;
+      const int tn = tile % tiles_n, tm = tile / tiles_n;
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(tfull_bar(acc), acc_ph);
+      tc_fence_after();
+      const int row = tm * BM + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c, r);
+        tmem_ld_wait();
+        const int col = tn * BN + c;
+        if (p.epi == EPI_ATOMIC_F32) {
+          if (row_ok) {
+            float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]) * p.out_scale);
+          }
+        } else {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+          if (p.epi == EPI_BIAS_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+          }
+          if (row_ok) {
+            if (p.pos) {
+              const float* pp = p.pos + (size_t)(row % p.pos_period) * p.N + col;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(pp + j));
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+            if (p.residual) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + col);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 q = __ldg(rp + j);
+                v[8 * j + 0] += bf16_lo(q.x); v[8 * j + 1] += bf16_hi(q.x);
+                v[8 * j + 2] += bf16_lo(q.y); v[8 * j + 3] += bf16_hi(q.y);
+                v[8 * j + 4] += bf16_lo(q.z); v[8 * j + 5] += bf16_hi(q.z);
+                v[8 * j + 6] += bf16_lo(q.w); v[8 * j + 7] += bf16_hi(q.w);
+              }
+            }
+            if (p.epi == EPI_STORE_F32) {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                    pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------- host
+static int g_num_sms = 0;
+int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm_t(cudaStream_t stream, const GemmDesc& g) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  // K-major operand: tensor [rows = M or N, cols = K], box [BM or BN rows, 64 cols]
+  // MN-major operand: tensor [rows = K, cols = M or N], box [64 rows, 64 cols]
+  if (!A_MN) rc = make_tmap_2d_bf16(&tmA, g.A, g.M, g.K, (uint64_t)g.lda * 2, BM, BK);
+  else rc = make_tmap_2d_bf16(&tmA, g.A, g.K, g.M, (uint64_t)g.lda * 2, BK, 64);
+  if (rc) return rc;
+  if (!B_MN) rc = make_tmap_2d_bf16(&tmB, g.B, g.N, g.K, (uint64_t)g.ldb * 2, BN, BK);
+  else rc = make_tmap_2d_bf16(&tmB, g.B, g.K, g.N, (uint64_t)g.ldb * 2, BK, 64);
+  if (rc) return rc;
+  GemmParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  const int KB = (g.K + BK - 1) / BK;
+  const int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
+  int splits = 1;
+  if (g.epi == EPI_ATOMIC_F32) {
+    splits = max(1, min(KB, (2 * num_sms() + tiles - 1) / tiles));
+  }
+  p.kb_per_split = (KB + splits - 1) / splits;
+  p.splits = (KB + p.kb_per_split - 1) / p.kb_per_split;
+  p.epi = g.epi; p.C = g.C; p.ldc = g.ldc; p.bias = g.bias; p.residual = g.residual; p.ldr = g.ldr;
+  p.pos = g.pos; p.pos_period = g.pos_period > 0 ? g.pos_period : 1; p.out_scale = g.out_scale;
+  auto kern = gemm_kernel<BN, A_MN, B_MN>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  if (err != cudaSuccess) return check_cuda(err);
+  const int work = tiles * p.splits;
+  const int grid = min(work, num_sms());
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  return check_cuda(cudaGetLastError());
+}
+
+template <int BN>
+static int launch_gemm_bn(cudaStream_t stream, const GemmDesc& g) {
+  if (!g.a_mn_major && !g.b_mn_major) return launch_gemm_t<BN, false, false>(stream, g);
+  if (g.a_mn_major && g.b_mn_major) return launch_gemm_t<BN, true, true>(stream, g);
+  if (!g.a_mn_major && g.b_mn_major) return launch_gemm_t<BN, false, true>(stream, g);
+  return launch_gemm_t<BN, true, false>(stream, g);
+}
+
+int launch_gemm(cudaStream_t stream, const GemmDesc& g) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0 || !g.A || !g.B || !g.C) { set_last_error("gemm: bad arguments"); return VITMARL_EINVAL; }
+  if (g.N % 64 || g.K % 8 || g.lda % 8 || g.ldb % 8 || (g.a_mn_major && g.M % 64)) { set_last_error("gemm: unsupported shape"); return VITMARL_EINVAL; }
+  if (g.N % 192 == 0) return launch_gemm_bn<192>(stream, g);
+  if (g.N % 128 == 0) return launch_gemm_bn<128>(stream, g);
+  return launch_gemm_bn<64>(stream, g);
+}
+
+}  // namespace vitmarl

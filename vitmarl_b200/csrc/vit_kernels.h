@@ -1,0 +1,62 @@
+// Internal launch API shared by the ViT translation units (not part of the C ABI).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vitmarl {
+
+enum GemmEpi {
+  EPI_STORE_BF16 = 0,   // C(bf16) = acc (+bias) (+pos) (+residual)
+  EPI_BIAS_GELU = 1,    // C(bf16) = gelu_tanh(acc + bias)
+  EPI_STORE_F32 = 2,    // C(fp32) = acc (+bias)
+  EPI_ATOMIC_F32 = 3,   // C(fp32) += out_scale * acc   (split-K over the contraction, red.add)
+};
+
+// C[M,N] = epi(A . B^T).  K-major operand X: element (row r, k) at X[r*ldx + k].
+// MN-major operand X: element (row r, k) at X[k*ldx + r]  (i.e. stored as [K, rows]).
+struct GemmDesc {
+  int M = 0, N = 0, K = 0;
+  const __nv_bfloat16* A = nullptr; int lda = 0; bool a_mn_major = false;
+  const __nv_bfloat16* B = nullptr; int ldb = 0; bool b_mn_major = false;
+  void* C = nullptr; int ldc = 0;
+  int epi = EPI_STORE_BF16;
+  const float* bias = nullptr;
+  const __nv_bfloat16* residual = nullptr; int ldr = 0;
+  const float* pos = nullptr; int pos_period = 0;
+  float out_scale = 1.0f;
+};
+
+int num_sms();
+int launch_gemm(cudaStream_t stream, const GemmDesc& g);
+
+// x[B,H,W,C] bf16 -> patches [B*T, P*P*C] bf16, token t = py*(W/P)+px, feature (ph, pw, c)
+int launch_patchify(cudaStream_t s, const __nv_bfloat16* x, __nv_bfloat16* out, int B, int H, int W, int C, int P);
+// d(patches) -> d(x) (exact inverse scatter; every pixel belongs to one patch)
+int launch_unpatchify(cudaStream_t s, const __nv_bfloat16* dpatches, __nv_bfloat16* dx, int B, int H, int W, int C, int P);
+
+// y = LN(x) * gamma + beta over the last dim D (bf16 in/out, fp32 statistics); stats[M,2] = (mean, rstd) or null
+int launch_layernorm(cudaStream_t s, const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* y,
+                     float* stats, int M, int D, float eps);
+// LN backward: dx (+)= dLN(dy); dgamma/dbeta accumulated with atomics (fp32, pre-zeroed)
+int launch_layernorm_bwd(cudaStream_t s, const __nv_bfloat16* x, const float* gamma, const float* stats, const __nv_bfloat16* dy,
+                         const __nv_bfloat16* dx_add, __nv_bfloat16* dx, float* dgamma, float* dbeta, int M, int D);
+
+// multi-head self-attention over T = 64 tokens, head dim 64: qkv [B*64, 3*D] (q | k | v, head-major) -> out [B*64, D]
+int launch_attention(cudaStream_t s, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int heads);
+int launch_attention_bwd(cudaStream_t s, const __nv_bfloat16* qkv, const __nv_bfloat16* dout, __nv_bfloat16* dqkv, int B, int heads);
+
+// y[B,D] (fp32) = mean_t LN(x[B*T,D]); saves stats[M,2]
+int launch_final_ln_pool(cudaStream_t s, const __nv_bfloat16* x, const float* gamma, const float* beta, float* y, float* stats,
+                         int B, int T, int D, float eps);
+// dx[B*T,D] (bf16) from dy[B,D]; dgamma/dbeta atomics
+int launch_final_ln_pool_bwd(cudaStream_t s, const __nv_bfloat16* x, const float* gamma, const float* stats, const float* dy,
+                             __nv_bfloat16* dx, float* dgamma, float* dbeta, int B, int T, int D);
+
+// elementwise helpers
+int launch_gelu_bwd(cudaStream_t s, const __nv_bfloat16* pre, const __nv_bfloat16* dy, __nv_bfloat16* dx, size_t n);   // dx = dy * gelu'(pre)
+int launch_colsum(cudaStream_t s, const __nv_bfloat16* x, float* out, int M, int N);                                  // out[N] += sum_m x[m,n]
+int launch_cast_f32_to_bf16(cudaStream_t s, const float* src, __nv_bfloat16* dst, size_t n);
+int launch_transpose_f32_to_bf16(cudaStream_t s, const float* src, __nv_bfloat16* dst, int rows, int cols);            // dst[cols, rows] = src[rows, cols]^T
+
+}  // namespace vitmarl
