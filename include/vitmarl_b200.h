@@ -117,6 +117,7 @@ int vitmarl_env_step(void* stream, int E, int N, int T, int M,
 #define VITMARL_EPI_BIAS_GELU 1  /* C(bf16) = gelu_tanh(acc + bias)                              */
 #define VITMARL_EPI_STORE_F32 2  /* C(fp32) = acc (+bias)                                        */
 #define VITMARL_EPI_ATOMIC_F32 3 /* C(fp32) += out_scale * acc  (split-K, C pre-initialised)     */
+#define VITMARL_EPI_MUL_GELU_GRAD 4 /* C(bf16) = acc * gelu_tanh'(residual[row,col])             */
 
 /* The tensor-core building block of the encoder (TMA -> tcgen05.mma -> TMEM epilogue):
  *   C[M,N] = epi( A[M,K] . B[N,K]^T ),  A/B bf16, fp32 accumulate.
@@ -127,6 +128,45 @@ int vitmarl_gemm_bf16(void* stream, int M, int N, int K,
                       const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major,
                       void* C, int ldc, int epi, const float* bias, const void* residual, int ldr,
                       const float* pos, int pos_period, float out_scale);
+
+/* Shape of the encoder (docs/VIT_SPEC.md): pre-LN ViT, learned position embedding, no class
+ * token, final LayerNorm then mean pool -> [B, dim].  Requires (H/P)*(W/P) == 64 tokens and
+ * head dim 64 (ViT-Tiny/8 @ 64x64: dim 192, heads 3; ViT-S/16 @ 128x128: dim 384, heads 6). */
+typedef struct VitmarlVitShape {
+  int batch;      /* B images                                      */
+  int img_h;      /* H                                             */
+  int img_w;      /* W                                             */
+  int channels;   /* C (2: ask, bid)                               */
+  int patch;      /* P                                             */
+  int dim;        /* D                                             */
+  int depth;      /* L                                             */
+  int heads;      /* h = D / 64                                    */
+  int mlp_dim;    /* 4 * D                                         */
+  float ln_eps;   /* 1e-6 (flax LayerNorm default)                 */
+} VitmarlVitShape;
+
+/* Packed parameter table: 5 + 12*depth device pointers, order (docs/VIT_SPEC.md):
+ *   0 patch_embed.kernel bf16 [D, P*P*C]   1 patch_embed.bias f32 [D]   2 pos_embed f32 [T, D]
+ *   per block l at 3 + 12*l: ln1.scale, ln1.bias (f32 [D]); qkv.kernel bf16 [3D, D]; qkv.bias f32 [3D];
+ *     out.kernel bf16 [D, D]; out.bias f32 [D]; ln2.scale, ln2.bias; fc1.kernel bf16 [mlp, D];
+ *     fc1.bias f32 [mlp]; fc2.kernel bf16 [D, mlp]; fc2.bias f32 [D]
+ *   last two: encoder_norm.scale, encoder_norm.bias (f32 [D])
+ * Matrices are stored [out, in] (the transpose of the flax Dense kernel).  The gradient table of
+ * vitmarl_vit_bwd has the same order and shapes, all fp32. */
+int vitmarl_vit_num_params(const VitmarlVitShape* s);
+long long vitmarl_vit_param_elems(const VitmarlVitShape* s, int index, int* is_bf16_matrix);
+/* Bytes of caller-owned activation workspace for fwd (save_for_bwd = 0) or fwd+bwd (1). */
+size_t vitmarl_vit_workspace_bytes(const VitmarlVitShape* s, int save_for_bwd);
+
+/* y[B,D] (fp32) = ViT(x[B,H,W,C] bf16).  Replaces `module.apply({'params': p}, x)`. */
+int vitmarl_vit_fwd(void* stream, const VitmarlVitShape* s, const void* const* params,
+                    const void* x, float* y, void* workspace, size_t workspace_bytes, int save_for_bwd);
+
+/* VJP: gradients of <y, dy> w.r.t. every packed parameter (fp32, zeroed here) and, if dx != NULL,
+ * w.r.t. the input (bf16 [B,H,W,C]).  `workspace` is the one filled by vitmarl_vit_fwd(..., 1). */
+int vitmarl_vit_bwd(void* stream, const VitmarlVitShape* s, const void* const* params,
+                    void* workspace, size_t workspace_bytes, const float* dy,
+                    void* const* dparams, void* dx);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,6 @@ extern "C" int vitmarl_gemm_bf16(void* stream, int M, int N, int K, const void* 
   g.C = C; g.ldc = ldc; g.epi = epi; g.bias = bias;
   g.residual = static_cast<const __nv_bfloat16*>(residual); g.ldr = ldr; g.pos = pos; g.pos_period = pos_period;
   g.out_scale = out_scale;
-  if (epi < 0 || epi > 3) return VITMARL_EINVAL;
+  if (epi < 0 || epi > 4) return VITMARL_EINVAL;
   return vitmarl::launch_gemm(static_cast<cudaStream_t>(stream), g);
 }

@@ -39,6 +39,7 @@ struct GemmParams {
   int splits;
   int epi;                // GemmEpi
   void* C; int ldc;       // bf16 or fp32 (atomic) output, row pitch in elements
+  void* C2;               // EPI_BIAS_GELU: optional bf16 copy of the pre-activation (saved for backward)
   const float* bias;      // [N] or null
   const __nv_bfloat16* residual; int ldr;   // [M, N] bf16 or null
   const float* pos; int pos_period;         // [pos_period, N] fp32 (row % pos_period) or null
@@ -173,6 +174,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           if (p.epi == EPI_BIAS_GELU) {
+            if (p.C2 && row_ok) {
+              uint4* dst2 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C2) + (size_t)row * p.ldc + col);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                dst2[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                     pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+            }
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
           }
@@ -187,13 +195,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             if (p.residual) {
               const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + col);
+              float a[32];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 uint4 q = __ldg(rp + j);
-                v[8 * j + 0] += bf16_lo(q.x); v[8 * j + 1] += bf16_hi(q.x);
-                v[8 * j + 2] += bf16_lo(q.y); v[8 * j + 3] += bf16_hi(q.y);
-                v[8 * j + 4] += bf16_lo(q.z); v[8 * j + 5] += bf16_hi(q.z);
-                v[8 * j + 6] += bf16_lo(q.w); v[8 * j + 7] += bf16_hi(q.w);
+                a[8 * j + 0] = bf16_lo(q.x); a[8 * j + 1] = bf16_hi(q.x);
+                a[8 * j + 2] = bf16_lo(q.y); a[8 * j + 3] = bf16_hi(q.y);
+                a[8 * j + 4] = bf16_lo(q.z); a[8 * j + 5] = bf16_hi(q.z);
+                a[8 * j + 6] = bf16_lo(q.w); a[8 * j + 7] = bf16_hi(q.w);
+              }
+              if (p.epi == EPI_MUL_GELU_GRAD) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= gelu_tanh_grad(a[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += a[j];
               }
             }
             if (p.epi == EPI_STORE_F32) {
@@ -258,7 +274,7 @@ static int launch_gemm_t(cudaStream_t stream, const GemmDesc& g) {
   }
   p.kb_per_split = (KB + splits - 1) / splits;
   p.splits = (KB + p.kb_per_split - 1) / p.kb_per_split;
-  p.epi = g.epi; p.C = g.C; p.ldc = g.ldc; p.bias = g.bias; p.residual = g.residual; p.ldr = g.ldr;
+  p.epi = g.epi; p.C = g.C; p.C2 = g.C2; p.ldc = g.ldc; p.bias = g.bias; p.residual = g.residual; p.ldr = g.ldr;
   p.pos = g.pos; p.pos_period = g.pos_period > 0 ? g.pos_period : 1; p.out_scale = g.out_scale;
   auto kern = gemm_kernel<BN, A_MN, B_MN>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);

@@ -1,0 +1,283 @@
+// ViT encoder forward / backward orchestration (docs/VIT_SPEC.md) behind the C ABI.
+// Drop-in for the flax `module.apply({'params': p}, x[B,H,W,C]) -> [B,D]` convention of the
+// reference's vision encoder slot (gymnax_exchange/networks/vision_agent.py:16-24; the
+// reference ships no ViT) and for its VJP inside the PPO loss
+// (gymnax_exchange/jaxrl/MARL/ippo_rnn_JAXMARL.py:423-475).
+//
+// Every matrix product runs on the tcgen05 GEMM (gemm.cu): forward projections with fused
+// bias / GELU / residual / pos-embed epilogues, dX products with the SAME weight buffer read
+// as an MN-major operand (no transposed copies), dW products as MN-major x MN-major split-K
+// GEMMs over the token dimension with fp32 red.add epilogues.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "vit_kernels.h"
+#include "../../include/vitmarl_b200.h"
+
+namespace vitmarl {
+
+typedef __nv_bfloat16 bf16;
+
+struct Dims {
+  int B, H, W, C, P, D, L, heads, mlp, T, M, Kp;
+  float eps;
+};
+
+static int get_dims(const VitmarlVitShape* s, Dims& d) {
+  if (!s) return VITMARL_EINVAL;
+  d.B = s->batch; d.H = s->img_h; d.W = s->img_w; d.C = s->channels; d.P = s->patch; d.D = s->dim; d.L = s->depth;
+  d.heads = s->heads; d.mlp = s->mlp_dim; d.eps = s->ln_eps;
+  if (d.B < 0 || d.P <= 0 || d.H % d.P || d.W % d.P || d.L < 0) { set_last_error("vit: bad shape"); return VITMARL_EINVAL; }
+  d.T = (d.H / d.P) * (d.W / d.P);
+  d.M = d.B * d.T;
+  d.Kp = d.P * d.P * d.C;
+  if (d.T != 64) { set_last_error("vit: (H/P)*(W/P) must be 64 tokens (attention kernel tile)"); return VITMARL_EINVAL; }
+  if (d.D != d.heads * 64) { set_last_error("vit: head dim must be 64"); return VITMARL_EINVAL; }
+  if (d.D % 64 || d.mlp % 64 || d.Kp % 64 || (d.P * d.C) % 8) { set_last_error("vit: D, mlp, P*P*C must be multiples of 64"); return VITMARL_EINVAL; }
+  return VITMARL_OK;
+}
+
+// ---- packed parameter table (docs/VIT_SPEC.md "packed layout") ----------------------------------
+enum { P_PE_W = 0, P_PE_B = 1, P_POS = 2, P_LAYER0 = 3, P_PER_LAYER = 12 };
+enum { L_LN1_G = 0, L_LN1_B, L_QKV_W, L_QKV_B, L_OUT_W, L_OUT_B, L_LN2_G, L_LN2_B, L_FC1_W, L_FC1_B, L_FC2_W, L_FC2_B };
+static inline int p_layer(int l, int k) { return P_LAYER0 + l * P_PER_LAYER + k; }
+static inline int p_lnf_g(const Dims& d) { return P_LAYER0 + d.L * P_PER_LAYER; }
+static inline int num_params(const Dims& d) { return p_lnf_g(d) + 2; }
+
+static size_t param_elems(const Dims& d, int idx, bool* is_matrix) {
+  *is_matrix = false;
+  if (idx == P_PE_W) { *is_matrix = true; return (size_t)d.D * d.Kp; }
+  if (idx == P_PE_B) return d.D;
+  if (idx == P_POS) return (size_t)d.T * d.D;
+  if (idx >= p_lnf_g(d)) return d.D;
+  const int k = (idx - P_LAYER0) % P_PER_LAYER;
+  switch (k) {
+    case L_QKV_W: *is_matrix = true; return (size_t)3 * d.D * d.D;
+    case L_QKV_B: return (size_t)3 * d.D;
+    case L_OUT_W: *is_matrix = true; return (size_t)d.D * d.D;
+    case L_FC1_W: *is_matrix = true; return (size_t)d.mlp * d.D;
+    case L_FC1_B: return d.mlp;
+    case L_FC2_W: *is_matrix = true; return (size_t)d.D * d.mlp;
+    default: return d.D;
+  }
+}
+
+// ---- workspace layout -------------------------------------------------------------------------
+struct Ws {
+  size_t patches, x, xm, ln1, ln2, qkv, att, hpre, hact, st1, st2, stf, dA, dB, dC, dH, dQKV, total;
+  size_t sz_md, sz_mh, sz_mq, sz_st;   // per-layer strides (bytes)
+};
+static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+static Ws layout(const Dims& d, bool save) {
+  Ws w{};
+  const size_t M = (size_t)d.M;
+  w.sz_md = al(M * d.D * 2); w.sz_mh = al(M * d.mlp * 2); w.sz_mq = al(M * 3 * d.D * 2); w.sz_st = al(M * 2 * 4);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
+  const int nl = save ? d.L : 1;
+  w.patches = take(M * d.Kp * 2);
+  w.x = take(w.sz_md * (save ? d.L + 1 : 1));
+  w.xm = save ? take(w.sz_md * nl) : w.x;          // inference: residual stream updated in place
+  w.ln1 = take(w.sz_md * nl);
+  w.ln2 = save ? take(w.sz_md * nl) : w.ln1;
+  w.qkv = take(w.sz_mq * nl);
+  w.att = take(w.sz_md * nl);
+  w.hact = take(w.sz_mh * nl);
+  w.hpre = save ? take(w.sz_mh * nl) : 0;
+  w.st1 = save ? take(w.sz_st * nl) : 0;
+  w.st2 = save ? take(w.sz_st * nl) : 0;
+  w.stf = save ? take(w.sz_st) : 0;
+  if (save) {
+    w.dA = take(w.sz_md); w.dB = take(w.sz_md); w.dC = take(w.sz_md);
+    w.dH = take(w.sz_mh); w.dQKV = take(w.sz_mq);
+  }
+  w.total = off;
+  return w;
+}
+
+#define VM_TRY(x)            \
+  do {                       \
+    int rc__ = (x);          \
+    if (rc__) return rc__;   \
+  } while (0)
+
+static GemmDesc gd(int M, int N, int K, const bf16* A, int lda, bool amn, const bf16* B, int ldb, bool bmn, void* C, int ldc, int epi) {
+  GemmDesc g;
+  g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.a_mn_major = amn; g.B = B; g.ldb = ldb; g.b_mn_major = bmn;
+  g.C = C; g.ldc = ldc; g.epi = epi;
+  return g;
+}
+
+static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, const bf16* x, float* y, uint8_t* ws, bool save) {
+  const Ws w = layout(d, save);
+  const int M = d.M, D = d.D;
+  auto PB = [&](int i) { return static_cast<const bf16*>(prm[i]); };
+  auto PF = [&](int i) { return static_cast<const float*>(prm[i]); };
+  bf16* patches = reinterpret_cast<bf16*>(ws + w.patches);
+  auto X = [&](int l) { return reinterpret_cast<bf16*>(ws + w.x + (save ? (size_t)l * w.sz_md : 0)); };
+  auto XM = [&](int l) { return reinterpret_cast<bf16*>(ws + w.xm + (save ? (size_t)l * w.sz_md : 0)); };
+  auto LN1 = [&](int l) { return reinterpret_cast<bf16*>(ws + w.ln1 + (save ? (size_t)l * w.sz_md : 0)); };
+  auto LN2 = [&](int l) { return reinterpret_cast<bf16*>(ws + w.ln2 + (save ? (size_t)l * w.sz_md : 0)); };
+  auto QKV = [&](int l) { return reinterpret_cast<bf16*>(ws + w.qkv + (save ? (size_t)l * w.sz_mq : 0)); };
+  auto ATT = [&](int l) { return reinterpret_cast<bf16*>(ws + w.att + (save ? (size_t)l * w.sz_md : 0)); };
+  auto HACT = [&](int l) { return reinterpret_cast<bf16*>(ws + w.hact + (save ? (size_t)l * w.sz_mh : 0)); };
+  auto HPRE = [&](int l) { return save ? reinterpret_cast<bf16*>(ws + w.hpre + (size_t)l * w.sz_mh) : nullptr; };
+  auto ST1 = [&](int l) { return save ? reinterpret_cast<float*>(ws + w.st1 + (size_t)l * w.sz_st) : nullptr; };
+  auto ST2 = [&](int l) { return save ? reinterpret_cast<float*>(ws + w.st2 + (size_t)l * w.sz_st) : nullptr; };
+
+  // patch embedding: tokens = patches . Wpe^T + b + pos
+  VM_TRY(launch_patchify(st, x, patches, d.B, d.H, d.W, d.C, d.P));
+  {
+    GemmDesc g = gd(M, D, d.Kp, patches, d.Kp, false, PB(P_PE_W), d.Kp, false, X(0), D, EPI_STORE_BF16);
+    g.bias = PF(P_PE_B); g.pos = PF(P_POS); g.pos_period = d.T;
+    VM_TRY(launch_gemm(st, g));
+  }
+  for (int l = 0; l < d.L; ++l) {
+    VM_TRY(launch_layernorm(st, X(l), PF(p_layer(l, L_LN1_G)), PF(p_layer(l, L_LN1_B)), LN1(l), ST1(l), M, D, d.eps));
+    {
+      GemmDesc g = gd(M, 3 * D, D, LN1(l), D, false, PB(p_layer(l, L_QKV_W)), D, false, QKV(l), 3 * D, EPI_STORE_BF16);
+      g.bias = PF(p_layer(l, L_QKV_B));
+      VM_TRY(launch_gemm(st, g));
+    }
+    VM_TRY(launch_attention(st, QKV(l), ATT(l), d.B, d.heads));
+    {
+      GemmDesc g = gd(M, D, D, ATT(l), D, false, PB(p_layer(l, L_OUT_W)), D, false, XM(l), D, EPI_STORE_BF16);
+      g.bias = PF(p_layer(l, L_OUT_B)); g.residual = X(l); g.ldr = D;
+      VM_TRY(launch_gemm(st, g));
+    }
+    VM_TRY(launch_layernorm(st, XM(l), PF(p_layer(l, L_LN2_G)), PF(p_layer(l, L_LN2_B)), LN2(l), ST2(l), M, D, d.eps));
+    {
+      GemmDesc g = gd(M, d.mlp, D, LN2(l), D, false, PB(p_layer(l, L_FC1_W)), D, false, HACT(l), d.mlp, EPI_BIAS_GELU);
+      g.bias = PF(p_layer(l, L_FC1_B)); g.C2 = HPRE(l);
+      VM_TRY(launch_gemm(st, g));
+    }
+    {
+      GemmDesc g = gd(M, D, d.mlp, HACT(l), d.mlp, false, PB(p_layer(l, L_FC2_W)), d.mlp, false, X(l + 1), D, EPI_STORE_BF16);
+      g.bias = PF(p_layer(l, L_FC2_B)); g.residual = XM(l); g.ldr = D;
+      VM_TRY(launch_gemm(st, g));
+    }
+  }
+  float* stf = save ? reinterpret_cast<float*>(ws + w.stf) : nullptr;
+  VM_TRY(launch_final_ln_pool(st, X(d.L), PF(p_lnf_g(d)), PF(p_lnf_g(d) + 1), y, stf, d.B, d.T, D, d.eps));
+  return VITMARL_OK;
+}
+
+static int vit_backward(cudaStream_t st, const Dims& d, const void* const* prm, uint8_t* ws, const float* dy, void* const* dprm, bf16* dx) {
+  const Ws w = layout(d, true);
+  const int M = d.M, D = d.D, H = d.mlp;
+  auto PB = [&](int i) { return static_cast<const bf16*>(prm[i]); };
+  auto PF = [&](int i) { return static_cast<const float*>(prm[i]); };
+  auto G = [&](int i) { return static_cast<float*>(dprm[i]); };
+  bf16* patches = reinterpret_cast<bf16*>(ws + w.patches);
+  auto X = [&](int l) { return reinterpret_cast<bf16*>(ws + w.x + (size_t)l * w.sz_md); };
+  auto XM = [&](int l) { return reinterpret_cast<bf16*>(ws + w.xm + (size_t)l * w.sz_md); };
+  auto LN1 = [&](int l) { return reinterpret_cast<bf16*>(ws + w.ln1 + (size_t)l * w.sz_md); };
+  auto LN2 = [&](int l) { return reinterpret_cast<bf16*>(ws + w.ln2 + (size_t)l * w.sz_md); };
+  auto QKV = [&](int l) { return reinterpret_cast<bf16*>(ws + w.qkv + (size_t)l * w.sz_mq); };
+  auto ATT = [&](int l) { return reinterpret_cast<bf16*>(ws + w.att + (size_t)l * w.sz_md); };
+  auto HACT = [&](int l) { return reinterpret_cast<bf16*>(ws + w.hact + (size_t)l * w.sz_mh); };
+  auto HPRE = [&](int l) { return reinterpret_cast<bf16*>(ws + w.hpre + (size_t)l * w.sz_mh); };
+  auto ST1 = [&](int l) { return reinterpret_cast<float*>(ws + w.st1 + (size_t)l * w.sz_st); };
+  auto ST2 = [&](int l) { return reinterpret_cast<float*>(ws + w.st2 + (size_t)l * w.sz_st); };
+  float* stf = reinterpret_cast<float*>(ws + w.stf);
+  bf16* dA = reinterpret_cast<bf16*>(ws + w.dA);
+  bf16* dB = reinterpret_cast<bf16*>(ws + w.dB);
+  bf16* dC = reinterpret_cast<bf16*>(ws + w.dC);
+  bf16* dH = reinterpret_cast<bf16*>(ws + w.dH);
+  bf16* dQKV = reinterpret_cast<bf16*>(ws + w.dQKV);
+
+  for (int i = 0; i < num_params(d); ++i) {
+    bool mat;
+    size_t n = param_elems(d, i, &mat);
+    cudaError_t e = cudaMemsetAsync(dprm[i], 0, n * sizeof(float), st);
+    if (e != cudaSuccess) return check_cuda(e);
+  }
+  // dW[out,in] += dY^T . Xin   (both operands MN-major over the token dimension; split-K red.add)
+  auto dW = [&](float* dw, const bf16* dY, int n_out, const bf16* Xin, int n_in) {
+    GemmDesc g = gd(n_out, n_in, M, dY, n_out, true, Xin, n_in, true, dw, n_in, EPI_ATOMIC_F32);
+    return launch_gemm(st, g);
+  };
+  // dXin[M,n_in] = dY[M,n_out] . W[n_out,n_in]   (W read as the MN-major B operand)
+  auto dXg = [&](bf16* dXin, const bf16* dY, int n_out, const bf16* W, int n_in, int epi, const bf16* aux) {
+    GemmDesc g = gd(M, n_in, n_out, dY, n_out, false, W, n_in, true, dXin, n_in, epi);
+    g.residual = aux; g.ldr = n_in;
+    return launch_gemm(st, g);
+  };
+
+  VM_TRY(launch_final_ln_pool_bwd(st, X(d.L), PF(p_lnf_g(d)), stf, dy, dA, G(p_lnf_g(d)), G(p_lnf_g(d) + 1), d.B, d.T, D));
+  for (int l = d.L - 1; l >= 0; --l) {
+    // ---- MLP branch: x_{l+1} = xm + fc2(gelu(fc1(ln2(xm))))
+    VM_TRY(launch_colsum(st, dA, G(p_layer(l, L_FC2_B)), M, D));
+    VM_TRY(dW(G(p_layer(l, L_FC2_W)), dA, D, HACT(l), H));
+    VM_TRY(dXg(dH, dA, D, PB(p_layer(l, L_FC2_W)), H, EPI_MUL_GELU_GRAD, HPRE(l)));
+    VM_TRY(launch_colsum(st, dH, G(p_layer(l, L_FC1_B)), M, H));
+    VM_TRY(dW(G(p_layer(l, L_FC1_W)), dH, H, LN2(l), D));
+    VM_TRY(dXg(dC, dH, H, PB(p_layer(l, L_FC1_W)), D, EPI_STORE_BF16, nullptr));
+    VM_TRY(launch_layernorm_bwd(st, XM(l), PF(p_layer(l, L_LN2_G)), ST2(l), dC, dA, dB, G(p_layer(l, L_LN2_G)), G(p_layer(l, L_LN2_B)), M, D));
+    // ---- attention branch: xm = x_l + out(attn(qkv(ln1(x_l))))
+    VM_TRY(launch_colsum(st, dB, G(p_layer(l, L_OUT_B)), M, D));
+    VM_TRY(dW(G(p_layer(l, L_OUT_W)), dB, D, ATT(l), D));
+    VM_TRY(dXg(dC, dB, D, PB(p_layer(l, L_OUT_W)), D, EPI_STORE_BF16, nullptr));
+    VM_TRY(launch_attention_bwd(st, QKV(l), dC, dQKV, d.B, d.heads));
+    VM_TRY(launch_colsum(st, dQKV, G(p_layer(l, L_QKV_B)), M, 3 * D));
+    VM_TRY(dW(G(p_layer(l, L_QKV_W)), dQKV, 3 * D, LN1(l), D));
+    VM_TRY(dXg(dC, dQKV, 3 * D, PB(p_layer(l, L_QKV_W)), D, EPI_STORE_BF16, nullptr));
+    VM_TRY(launch_layernorm_bwd(st, X(l), PF(p_layer(l, L_LN1_G)), ST1(l), dC, dB, dA, G(p_layer(l, L_LN1_G)), G(p_layer(l, L_LN1_B)), M, D));
+  }
+  // ---- patch embedding
+  VM_TRY(launch_colsum(st, dA, G(P_POS), d.B, d.T * D));     // dpos[t,:] = sum over images
+  VM_TRY(launch_colsum(st, dA, G(P_PE_B), M, D));
+  VM_TRY(dW(G(P_PE_W), dA, D, patches, d.Kp));
+  if (dx) {
+    VM_TRY(dXg(patches, dA, D, PB(P_PE_W), d.Kp, EPI_STORE_BF16, nullptr));   // reuse the patches buffer for d(patches)
+    VM_TRY(launch_unpatchify(st, patches, dx, d.B, d.H, d.W, d.C, d.P));
+  }
+  return VITMARL_OK;
+}
+
+}  // namespace vitmarl
+
+using namespace vitmarl;
+
+extern "C" int vitmarl_vit_num_params(const VitmarlVitShape* s) {
+  Dims d;
+  if (get_dims(s, d)) return VITMARL_EINVAL;
+  return num_params(d);
+}
+
+extern "C" long long vitmarl_vit_param_elems(const VitmarlVitShape* s, int index, int* is_bf16_matrix) {
+  Dims d;
+  if (get_dims(s, d) || index < 0 || index >= num_params(d)) return VITMARL_EINVAL;
+  bool mat;
+  size_t n = param_elems(d, index, &mat);
+  if (is_bf16_matrix) *is_bf16_matrix = mat ? 1 : 0;
+  return (long long)n;
+}
+
+extern "C" size_t vitmarl_vit_workspace_bytes(const VitmarlVitShape* s, int save_for_bwd) {
+  Dims d;
+  if (get_dims(s, d)) return 0;
+  return layout(d, save_for_bwd != 0).total;
+}
+
+extern "C" int vitmarl_vit_fwd(void* stream, const VitmarlVitShape* s, const void* const* params, const void* x, float* y,
+                               void* workspace, size_t workspace_bytes, int save_for_bwd) {
+  Dims d;
+  VM_TRY(get_dims(s, d));
+  if (d.B == 0) return VITMARL_OK;
+  if (!params || !x || !y || !workspace) return VITMARL_EINVAL;
+  if (workspace_bytes < layout(d, save_for_bwd != 0).total) { set_last_error("vit_fwd: workspace too small"); return VITMARL_EINVAL; }
+  return vit_forward(static_cast<cudaStream_t>(stream), d, params, static_cast<const bf16*>(x), y, static_cast<uint8_t*>(workspace), save_for_bwd != 0);
+}
+
+extern "C" int vitmarl_vit_bwd(void* stream, const VitmarlVitShape* s, const void* const* params, void* workspace,
+                               size_t workspace_bytes, const float* dy, void* const* dparams, void* dx) {
+  Dims d;
+  VM_TRY(get_dims(s, d));
+  if (d.B == 0) return VITMARL_OK;
+  if (!params || !workspace || !dy || !dparams) return VITMARL_EINVAL;
+  if (workspace_bytes < layout(d, true).total) { set_last_error("vit_bwd: workspace too small"); return VITMARL_EINVAL; }
+  return vit_backward(static_cast<cudaStream_t>(stream), d, params, static_cast<uint8_t*>(workspace), dy, dparams, static_cast<bf16*>(dx));
+}

@@ -11,6 +11,7 @@ enum GemmEpi {
   EPI_BIAS_GELU = 1,    // C(bf16) = gelu_tanh(acc + bias)
   EPI_STORE_F32 = 2,    // C(fp32) = acc (+bias)
   EPI_ATOMIC_F32 = 3,   // C(fp32) += out_scale * acc   (split-K over the contraction, red.add)
+  EPI_MUL_GELU_GRAD = 4,// C(bf16) = acc * gelu_tanh'(aux[row,col]),  aux passed as `residual`
 };
 
 // C[M,N] = epi(A . B^T).  K-major operand X: element (row r, k) at X[r*ldx + k].
@@ -20,6 +21,7 @@ struct GemmDesc {
   const __nv_bfloat16* A = nullptr; int lda = 0; bool a_mn_major = false;
   const __nv_bfloat16* B = nullptr; int ldb = 0; bool b_mn_major = false;
   void* C = nullptr; int ldc = 0;
+  void* C2 = nullptr;   // EPI_BIAS_GELU: also store the pre-activation (bf16) here
   int epi = EPI_STORE_BF16;
   const float* bias = nullptr;
   const __nv_bfloat16* residual = nullptr; int ldr = 0;
