@@ -168,6 +168,12 @@ int vitmarl_vit_bwd(void* stream, const VitmarlVitShape* s, const void* const* p
                     void* workspace, size_t workspace_bytes, const float* dy,
                     void* const* dparams, void* dx);
 
+/* Measurement hook: CUDA-event timing (on the launch stream) of every tensor-core GEMM launch
+ * issued by vitmarl_vit_fwd / vitmarl_vit_bwd.  enable(1) resets the log; read() synchronises on
+ * the last logged launch and returns total milliseconds, launch count and algorithmic FLOPs. */
+int vitmarl_vit_gemm_timing_enable(int enable);
+int vitmarl_vit_gemm_timing_read(double* total_ms, long long* launches, double* flops);
+
 #ifdef __cplusplus
 }
 #endif

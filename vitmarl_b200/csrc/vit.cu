@@ -97,6 +97,30 @@ static Ws layout(const Dims& d, bool save) {
   return w;
 }
 
+// ---- optional per-launch GEMM timing (CUDA events on the launch stream; used by bench.py) --------
+struct GemmTiming {
+  bool enabled = false;
+  static constexpr int kMax = 16384;
+  cudaEvent_t ev[2 * kMax];
+  bool created = false;
+  int n = 0;
+  double flops = 0.0;
+};
+static GemmTiming g_timing;
+
+static int timed_gemm(cudaStream_t st, const GemmDesc& g) {
+  GemmTiming& t = g_timing;
+  const bool on = t.enabled && t.n < GemmTiming::kMax;
+  if (on) cudaEventRecord(t.ev[2 * t.n], st);
+  int rc = launch_gemm(st, g);
+  if (on) {
+    cudaEventRecord(t.ev[2 * t.n + 1], st);
+    t.flops += 2.0 * g.M * g.N * g.K;
+    ++t.n;
+  }
+  return rc;
+}
+
 #define VM_TRY(x)            \
   do {                       \
     int rc__ = (x);          \
@@ -132,31 +156,31 @@ static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, c
   {
     GemmDesc g = gd(M, D, d.Kp, patches, d.Kp, false, PB(P_PE_W), d.Kp, false, X(0), D, EPI_STORE_BF16);
     g.bias = PF(P_PE_B); g.pos = PF(P_POS); g.pos_period = d.T;
-    VM_TRY(launch_gemm(st, g));
+    VM_TRY(timed_gemm(st, g));
   }
   for (int l = 0; l < d.L; ++l) {
     VM_TRY(launch_layernorm(st, X(l), PF(p_layer(l, L_LN1_G)), PF(p_layer(l, L_LN1_B)), LN1(l), ST1(l), M, D, d.eps));
     {
       GemmDesc g = gd(M, 3 * D, D, LN1(l), D, false, PB(p_layer(l, L_QKV_W)), D, false, QKV(l), 3 * D, EPI_STORE_BF16);
       g.bias = PF(p_layer(l, L_QKV_B));
-      VM_TRY(launch_gemm(st, g));
+      VM_TRY(timed_gemm(st, g));
     }
     VM_TRY(launch_attention(st, QKV(l), ATT(l), d.B, d.heads));
     {
       GemmDesc g = gd(M, D, D, ATT(l), D, false, PB(p_layer(l, L_OUT_W)), D, false, XM(l), D, EPI_STORE_BF16);
       g.bias = PF(p_layer(l, L_OUT_B)); g.residual = X(l); g.ldr = D;
-      VM_TRY(launch_gemm(st, g));
+      VM_TRY(timed_gemm(st, g));
     }
     VM_TRY(launch_layernorm(st, XM(l), PF(p_layer(l, L_LN2_G)), PF(p_layer(l, L_LN2_B)), LN2(l), ST2(l), M, D, d.eps));
     {
       GemmDesc g = gd(M, d.mlp, D, LN2(l), D, false, PB(p_layer(l, L_FC1_W)), D, false, HACT(l), d.mlp, EPI_BIAS_GELU);
       g.bias = PF(p_layer(l, L_FC1_B)); g.C2 = HPRE(l);
-      VM_TRY(launch_gemm(st, g));
+      VM_TRY(timed_gemm(st, g));
     }
     {
       GemmDesc g = gd(M, D, d.mlp, HACT(l), d.mlp, false, PB(p_layer(l, L_FC2_W)), d.mlp, false, X(l + 1), D, EPI_STORE_BF16);
       g.bias = PF(p_layer(l, L_FC2_B)); g.residual = XM(l); g.ldr = D;
-      VM_TRY(launch_gemm(st, g));
+      VM_TRY(timed_gemm(st, g));
     }
   }
   float* stf = save ? reinterpret_cast<float*>(ws + w.stf) : nullptr;
@@ -197,13 +221,13 @@ static int vit_backward(cudaStream_t st, const Dims& d, const void* const* prm, 
   // dW[out,in] += dY^T . Xin   (both operands MN-major over the token dimension; split-K red.add)
   auto dW = [&](float* dw, const bf16* dY, int n_out, const bf16* Xin, int n_in) {
     GemmDesc g = gd(n_out, n_in, M, dY, n_out, true, Xin, n_in, true, dw, n_in, EPI_ATOMIC_F32);
-    return launch_gemm(st, g);
+    return timed_gemm(st, g);
   };
   // dXin[M,n_in] = dY[M,n_out] . W[n_out,n_in]   (W read as the MN-major B operand)
   auto dXg = [&](bf16* dXin, const bf16* dY, int n_out, const bf16* W, int n_in, int epi, const bf16* aux) {
     GemmDesc g = gd(M, n_in, n_out, dY, n_out, false, W, n_in, true, dXin, n_in, epi);
     g.residual = aux; g.ldr = n_in;
-    return launch_gemm(st, g);
+    return timed_gemm(st, g);
   };
 
   VM_TRY(launch_final_ln_pool_bwd(st, X(d.L), PF(p_lnf_g(d)), stf, dy, dA, G(p_lnf_g(d)), G(p_lnf_g(d) + 1), d.B, d.T, D));
@@ -280,4 +304,36 @@ extern "C" int vitmarl_vit_bwd(void* stream, const VitmarlVitShape* s, const voi
   if (!params || !workspace || !dy || !dparams) return VITMARL_EINVAL;
   if (workspace_bytes < layout(d, true).total) { set_last_error("vit_bwd: workspace too small"); return VITMARL_EINVAL; }
   return vit_backward(static_cast<cudaStream_t>(stream), d, params, static_cast<uint8_t*>(workspace), dy, dparams, static_cast<bf16*>(dx));
+}
+
+// Enable / disable CUDA-event timing of every GEMM launch issued by vit_fwd / vit_bwd (resets the log).
+extern "C" int vitmarl_vit_gemm_timing_enable(int enable) {
+  GemmTiming& t = g_timing;
+  if (enable && !t.created) {
+    for (int i = 0; i < 2 * GemmTiming::kMax; ++i)
+      if (cudaEventCreate(&t.ev[i]) != cudaSuccess) return check_cuda(cudaGetLastError());
+    t.created = true;
+  }
+  t.enabled = enable != 0;
+  t.n = 0;
+  t.flops = 0.0;
+  return VITMARL_OK;
+}
+
+// Sum of the logged launches (synchronises on the last event): total ms, launches, algorithmic FLOPs.
+extern "C" int vitmarl_vit_gemm_timing_read(double* total_ms, long long* launches, double* flops) {
+  GemmTiming& t = g_timing;
+  double ms = 0.0;
+  if (t.n > 0) {
+    cudaError_t e = cudaEventSynchronize(t.ev[2 * t.n - 1]);
+    if (e != cudaSuccess) return check_cuda(e);
+    for (int i = 0; i < t.n; ++i) {
+      float x = 0.f;
+      if (cudaEventElapsedTime(&x, t.ev[2 * i], t.ev[2 * i + 1]) == cudaSuccess) ms += x;
+    }
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = t.n;
+  if (flops) *flops = t.flops;
+  return VITMARL_OK;
 }

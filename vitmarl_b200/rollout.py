@@ -1,0 +1,69 @@
+"""Batched rollout-and-encode step: the public call a user of this framework makes.
+
+    engine = RolloutEncoder(cfg, vit_cfg, params, E, M)
+    engine.reset(asks, bids)                       # device-resident book state
+    feats = engine.step(msgs_device)               # [E, D] fp32 ViT encoding of the new LOB image
+    feats_host = engine.step_host(msgs_pinned)     # same with host buffers (H2D / D2H inside)
+
+One step = fused order-book kernel (scan + forward fill + mid price + vision tensor + raster,
+``marl_env.py:377-393,466-467,637-662``) followed by the ViT encoder forward on the rendered
+images.  Environments are independent, so multi-GPU runs shard ``E`` across ranks with no
+collective on this path (``ippo_rnn_JAXMARL_pmap.py:290-330``)."""
+from __future__ import annotations
+
+import torch
+
+from . import env as venv
+from . import vit as vvit
+from .config import World_EnvironmentConfig
+
+__all__ = ["RolloutEncoder", "kernels_per_step"]
+
+
+def kernels_per_step(vit_cfg: vvit.ViTConfig) -> int:
+    """Launches of this library's kernels in one step: 1 env-step + patchify + (1 + 4 L) GEMMs + 2 L LayerNorm
+    + L attention + final LN/pool."""
+    L = vit_cfg.depth
+    return 1 + 1 + (1 + 4 * L) + 2 * L + L + 1
+
+
+class RolloutEncoder:
+    def __init__(self, cfg: World_EnvironmentConfig, vit_cfg: vvit.ViTConfig, params, E: int, M: int,
+                 n_levels: int = 10, device="cuda"):
+        self.cfg, self.vit_cfg, self.E, self.M, self.n_levels = cfg, vit_cfg, E, M, n_levels
+        self.device = torch.device(device)
+        self.encoder = vvit.ViTEncoder(vit_cfg)
+        self.packed = vvit.pack_params(vit_cfg, params)
+        self.state = None
+        self.last = None
+        # staging for the host-buffer path
+        self._msgs_dev = torch.empty((E, M, 8), dtype=torch.int32, device=self.device)
+        self._feat_host = torch.empty((E, vit_cfg.dim), dtype=torch.float32).pin_memory() if torch.cuda.is_available() else None
+        self._obs_host = torch.empty((E, n_levels, 3, 2), dtype=torch.float32).pin_memory() if torch.cuda.is_available() else None
+
+    def reset(self, asks: torch.Tensor, bids: torch.Tensor):
+        self.state = venv.reset(self.cfg, asks, bids, self.M)
+        return self.state
+
+    def step(self, msgs: torch.Tensor) -> torch.Tensor:
+        c = self.vit_cfg
+        self.state, out = venv.step(self.cfg, self.state, msgs, n_levels=self.n_levels, want_obs=True,
+                                    image_hw=(c.img_h, c.img_w), image_dtype=torch.bfloat16, inplace=True)
+        self.last = out
+        return self.encoder.apply_packed(self.packed, out.image)
+
+    def step_host(self, msgs_pinned: torch.Tensor):
+        """Host-buffer entry: H2D of the step's messages, the step, D2H of the encoding and the vision tensor."""
+        self._msgs_dev.copy_(msgs_pinned, non_blocking=True)
+        feats = self.step(self._msgs_dev)
+        self._feat_host.copy_(feats, non_blocking=True)
+        self._obs_host.copy_(self.last.vision_obs, non_blocking=True)
+        return self._feat_host, self._obs_host
+
+    @property
+    def h2d_bytes_per_step(self) -> int:
+        return self.E * self.M * 8 * 4
+
+    @property
+    def d2h_bytes_per_step(self) -> int:
+        return self.E * self.vit_cfg.dim * 4 + self.E * self.n_levels * 6 * 4
