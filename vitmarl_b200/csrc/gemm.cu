@@ -3,7 +3,9 @@
 // residual / positional-embedding add.  Persistent, warp specialised:
 //   warp 0   TMA producer (one elected lane)
 //   warp 1   TMEM allocator + MMA issuer (one elected lane)
-//   warps 2-5 epilogue, warp w owns TMEM lanes 32*(w%4) .. +31 (one output row per thread)
+//   warps 2-9 epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 (one output row per thread) and half of
+//             the tile's columns (the epilogue -- TMEM loads, bias/GELU math, stores -- is the per-SM
+//             issue bottleneck for these skinny-K products, so it gets 8 of the 10 warps)
 //
 //   C[M,N] = epi( A[M,K] . B[N,K]^T )        A, B bf16; fp32 accumulate
 // A / B may each be "K-major" (contraction index contiguous: activations [tokens, features],
@@ -21,7 +23,8 @@
 namespace vitmarl {
 
 constexpr int BM = 128, BK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;                       // 2 warps per TMEM lane quadrant, each owns half of the tile's columns
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 
 template <int BN>
 struct GemmCfg {
@@ -68,7 +71,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -137,8 +140,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    // ================= epilogue (warps 2..5) =================
+    // ================= epilogue (warps 2..9) =================
     const int quad = warp & 3;
+    const int chalf = (warp - 2) >> 2;           // which half of the columns
+    constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
     int it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
       const int tile = w / p.splits;
@@ -151,7 +156,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = chalf * kColsPerWarp; c < (chalf + 1) * kColsPerWarp; c += 32) {
         uint32_t r[32];
         tmem_ld_32x32(taddr + c, r);
         tmem_ld_wait();

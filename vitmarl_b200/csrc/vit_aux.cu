@@ -198,10 +198,8 @@ template <int NP>
 __global__ void __launch_bounds__(256) final_ln_pool_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float* __restrict__ y,
                                                              float* __restrict__ stats, int T, int D, float eps) {
-  extern __shared__ float red[];   // [D]
+  extern __shared__ float red[];   // [warps][D]: per-warp partial sums, combined in a fixed order (bitwise deterministic)
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < D; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
   float acc[2 * NP];
 #pragma unroll
   for (int i = 0; i < 2 * NP; ++i) acc[i] = 0.f;
@@ -216,12 +214,14 @@ __global__ void __launch_bounds__(256) final_ln_pool_kernel(const __nv_bfloat16*
     if (stats && lane == 0) reinterpret_cast<float2*>(stats)[row] = make_float2(mean, rstd);
   }
 #pragma unroll
-  for (int i = 0; i < NP; ++i) {
-    atomicAdd(&red[2 * (lane + 32 * i)], acc[2 * i]);
-    atomicAdd(&red[2 * (lane + 32 * i) + 1], acc[2 * i + 1]);
-  }
+  for (int i = 0; i < NP; ++i)
+    reinterpret_cast<float2*>(red + warp * D)[lane + 32 * i] = make_float2(acc[2 * i], acc[2 * i + 1]);
   __syncthreads();
-  for (int i = threadIdx.x; i < D; i += blockDim.x) y[(size_t)b * D + i] = red[i] / T * __ldg(gamma + i) + __ldg(beta + i);
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += red[w * D + i];
+    y[(size_t)b * D + i] = s / T * __ldg(gamma + i) + __ldg(beta + i);
+  }
 }
 
 // dx[t,:] = LN_bwd(dy[b,:] / T);  dgamma += sum_t dy/T * xhat,  dbeta += dy   (dbeta: sum over tokens of dy/T = dy)
@@ -281,7 +281,7 @@ int launch_final_ln_pool(cudaStream_t s, const __nv_bfloat16* x, const float* ga
                          int B, int T, int D, float eps) {
   if (B <= 0) return VITMARL_OK;
   if (D % 64) return VITMARL_EINVAL;
-  VM_DISPATCH_NP(D, (final_ln_pool_kernel<NP><<<B, 256, D * sizeof(float), s>>>(x, gamma, beta, y, stats, T, D, eps)));
+  VM_DISPATCH_NP(D, (final_ln_pool_kernel<NP><<<B, 256, 8 * D * sizeof(float), s>>>(x, gamma, beta, y, stats, T, D, eps)));
   return check_cuda(cudaGetLastError());
 }
 int launch_final_ln_pool_bwd(cudaStream_t s, const __nv_bfloat16* x, const float* gamma, const float* stats, const float* dy,
