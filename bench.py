@@ -216,6 +216,8 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms, n, fl = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
     lib.vitmarl_vit_gemm_timing_read(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl))
+    cat_ms, cat_n = (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
+    lib.vitmarl_vit_timing_read_categories(cat_ms, cat_n)
     lib.vitmarl_vit_gemm_timing_enable(0)
     feats_dev = eng.step(msgs_dev[-1]).clone()
     # ---- end-to-end run through the host-buffer API (pinned H2D of the messages, D2H of the encoding) -------
@@ -231,7 +233,10 @@ def run_ours(args):
     gemm_ms_total, gemm_launches, gemm_flops = ms.value, n.value, fl.value
     gemm_ms_per_launch = gemm_ms_total / max(gemm_launches, 1)
     achieved_tf = gemm_flops / max(gemm_ms_total * 1e-3, 1e-12) / 1e12
-    steps_logged = gemm_launches / (1 + 4 * vcfg.depth)
+    steps_logged = W + K                      # the log covers warm-up + timed steps of the device-resident run
+    names = ["gemm", "fused_mlp", "fused_attn_block", "attention", "layernorm", "other"]
+    breakdown = {nm: {"ms_per_step": cat_ms[i] / steps_logged, "launches_per_step": cat_n[i] / steps_logged}
+                 for i, nm in enumerate(names) if cat_n[i]}
     value = world * E * K / t_dev
     e2e = world * E * K / t_e2e
     # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
@@ -252,7 +257,8 @@ def run_ours(args):
                    "parallelism": f"env-sharded x{world}, no data-path collective"},
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved_tf / peaks["bf16_tflops_sustained"], "traffic": None,
-                     "kernel": "vitmarl::gemm_kernel (tcgen05, all forward GEMM launches of the step)",
+                     "kernel": "tcgen05 kernels of the step (vitmarl::gemm_kernel + fused block kernels), CUDA events per launch",
+                     "per_step_ms_by_kernel_class": breakdown,
                      "launches_timed": gemm_launches, "avg_launch_us": gemm_ms_per_launch * 1e3,
                      "flops_per_step": gemm_flops / max(steps_logged, 1), "gemm_share_of_step": (gemm_ms_total / max(steps_logged, 1)) / (t_dev / K * 1e3),
                      "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)"},

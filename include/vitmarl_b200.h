@@ -168,11 +168,21 @@ int vitmarl_vit_bwd(void* stream, const VitmarlVitShape* s, const void* const* p
                     void* workspace, size_t workspace_bytes, const float* dy,
                     void* const* dparams, void* dx);
 
+/* Inference forward: use the fused per-block kernels (1, default) or the unfused kernel sequence (0). */
+int vitmarl_vit_set_fused(int enable);
+
+/* Debug hook: device buffer (>= 256 int64) that receives clock64() phase stamps of the fused MLP kernel
+ * (CTA 0, second tile); NULL switches it off. */
+int vitmarl_debug_fused_mlp_timeline(long long* device_buf);
+
 /* Measurement hook: CUDA-event timing (on the launch stream) of every tensor-core GEMM launch
- * issued by vitmarl_vit_fwd / vitmarl_vit_bwd.  enable(1) resets the log; read() synchronises on
- * the last logged launch and returns total milliseconds, launch count and algorithmic FLOPs. */
+ * (plain GEMMs and fused block kernels) issued by vitmarl_vit_fwd / vitmarl_vit_bwd.  enable(1) resets the log;
+ * read() synchronises on the last logged launch and returns total ms, launch count and algorithmic FLOPs. */
 int vitmarl_vit_gemm_timing_enable(int enable);
 int vitmarl_vit_gemm_timing_read(double* total_ms, long long* launches, double* flops);
+/* Per-category totals over the same log; arrays of 8: 0 gemm, 1 fused MLP block, 2 fused attention block,
+ * 3 attention, 4 layernorm, 5 other. */
+int vitmarl_vit_timing_read_categories(double* ms8, long long* n8);
 
 #ifdef __cplusplus
 }

@@ -49,7 +49,14 @@ def test_forward_matches_fp32_oracle(cfg, B):
     ref = VO.vit_forward(cfg, params, x)
     assert y.shape == (B, cfg.dim) and y.dtype == torch.float32
     assert _rel(y, ref) <= ACT_TOL, _rel(y, ref)
-    assert torch.equal(y, y_train)            # saving activations must not change the result
+    # the inference path runs the fused block kernels, the training path the unfused sequence: same maths
+    assert _rel(y, y_train) <= 1e-2, _rel(y, y_train)
+    lib = _capi.lib()
+    lib.vitmarl_vit_set_fused(0)
+    y_unfused = enc.apply({"params": params}, x)
+    lib.vitmarl_vit_set_fused(1)
+    assert torch.equal(y_unfused, y_train)    # saving activations must not change the result
+    assert torch.equal(y, enc.apply({"params": params}, x))   # forward is bitwise deterministic
 
 
 @pytest.mark.parametrize("cfg,B", [(vit.ViTConfig(64, 64, 2, 8, 192, 0, 3, 768), 6),

@@ -47,8 +47,11 @@ SIGNATURES = {
     "vitmarl_vit_workspace_bytes": (_SZ, [_P, _I]),
     "vitmarl_vit_fwd": (_I, [_P, _P, _P, _P, _P, _P, _SZ, _I]),
     "vitmarl_vit_bwd": (_I, [_P, _P, _P, _P, _SZ, _P, _P, _P]),
+    "vitmarl_vit_set_fused": (_I, [_I]),
+    "vitmarl_debug_fused_mlp_timeline": (_I, [_P]),
     "vitmarl_vit_gemm_timing_enable": (_I, [_I]),
     "vitmarl_vit_gemm_timing_read": (_I, [_P, _P, _P]),
+    "vitmarl_vit_timing_read_categories": (_I, [_P, _P]),
     "vitmarl_env_step": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                               _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, ctypes.c_int32]),
 }

@@ -115,6 +115,21 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// gelu_tanh on a packed bf16x2 pair: 5 packed FP ops + 1 packed MUFU for two elements
+// (x^2, fma, mul, tanh.approx.bf16x2, mul, fma) -- the epilogue of the fused MLP is issue-bound on the CUDA cores.
+__device__ __forceinline__ uint32_t gelu_tanh_bf16x2(uint32_t x) {
+  const uint32_t C0 = 0x3F4C3F4Cu;   // bf16(0.7978845608) x2
+  const uint32_t C1 = 0x3D123D12u;   // bf16(0.7978845608 * 0.044715 = 0.0356774) x2
+  const uint32_t HALF = 0x3F003F00u; // bf16(0.5) x2
+  uint32_t x2, p, u, t, hx, y;
+  asm("mul.rn.bf16x2 %0, %1, %1;" : "=r"(x2) : "r"(x));
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(p) : "r"(x2), "r"(C1), "r"(C0));
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(u) : "r"(p), "r"(x));
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t) : "r"(u));
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(hx) : "r"(x), "r"(HALF));
+  asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(y) : "r"(hx), "r"(t));
+  return y;
+}
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 #endif  // __CUDACC__

@@ -97,28 +97,37 @@ static Ws layout(const Dims& d, bool save) {
   return w;
 }
 
-// ---- optional per-launch GEMM timing (CUDA events on the launch stream; used by bench.py) --------
-struct GemmTiming {
+// ---- optional per-launch timing (CUDA events on the launch stream; used by bench.py) ---------------
+enum { CAT_GEMM = 0, CAT_FUSED_MLP = 1, CAT_FUSED_ATTN = 2, CAT_ATTENTION = 3, CAT_LAYERNORM = 4, CAT_OTHER = 5, CAT_COUNT = 8 };
+struct OpTiming {
   bool enabled = false;
   static constexpr int kMax = 16384;
   cudaEvent_t ev[2 * kMax];
+  unsigned char cat[kMax];
   bool created = false;
   int n = 0;
-  double flops = 0.0;
+  double flops = 0.0;     // algorithmic FLOPs of the tensor-core launches (categories 0-2)
 };
-static GemmTiming g_timing;
+static OpTiming g_timing;
+static bool g_use_fused = true;   // fused block kernels on the inference path (vitmarl_vit_set_fused)
 
-static int timed_gemm(cudaStream_t st, const GemmDesc& g) {
-  GemmTiming& t = g_timing;
-  const bool on = t.enabled && t.n < GemmTiming::kMax;
+template <typename F>
+static int timed(cudaStream_t st, int cat, double flops, F&& launch) {
+  OpTiming& t = g_timing;
+  const bool on = t.enabled && t.n < OpTiming::kMax;
   if (on) cudaEventRecord(t.ev[2 * t.n], st);
-  int rc = launch_gemm(st, g);
+  int rc = launch();
   if (on) {
     cudaEventRecord(t.ev[2 * t.n + 1], st);
-    t.flops += 2.0 * g.M * g.N * g.K;
+    t.cat[t.n] = (unsigned char)cat;
+    t.flops += flops;
     ++t.n;
   }
   return rc;
+}
+
+static int timed_gemm(cudaStream_t st, const GemmDesc& g) {
+  return timed(st, CAT_GEMM, 2.0 * g.M * g.N * g.K, [&] { return launch_gemm(st, g); });
 }
 
 #define VM_TRY(x)            \
@@ -152,26 +161,34 @@ static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, c
   auto ST2 = [&](int l) { return save ? reinterpret_cast<float*>(ws + w.st2 + (size_t)l * w.sz_st) : nullptr; };
 
   // patch embedding: tokens = patches . Wpe^T + b + pos
-  VM_TRY(launch_patchify(st, x, patches, d.B, d.H, d.W, d.C, d.P));
+  VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_patchify(st, x, patches, d.B, d.H, d.W, d.C, d.P); }));
   {
     GemmDesc g = gd(M, D, d.Kp, patches, d.Kp, false, PB(P_PE_W), d.Kp, false, X(0), D, EPI_STORE_BF16);
     g.bias = PF(P_PE_B); g.pos = PF(P_POS); g.pos_period = d.T;
     VM_TRY(timed_gemm(st, g));
   }
   for (int l = 0; l < d.L; ++l) {
-    VM_TRY(launch_layernorm(st, X(l), PF(p_layer(l, L_LN1_G)), PF(p_layer(l, L_LN1_B)), LN1(l), ST1(l), M, D, d.eps));
+    VM_TRY(timed(st, CAT_LAYERNORM, 0, [&] { return launch_layernorm(st, X(l), PF(p_layer(l, L_LN1_G)), PF(p_layer(l, L_LN1_B)), LN1(l), ST1(l), M, D, d.eps); }));
     {
       GemmDesc g = gd(M, 3 * D, D, LN1(l), D, false, PB(p_layer(l, L_QKV_W)), D, false, QKV(l), 3 * D, EPI_STORE_BF16);
       g.bias = PF(p_layer(l, L_QKV_B));
       VM_TRY(timed_gemm(st, g));
     }
-    VM_TRY(launch_attention(st, QKV(l), ATT(l), d.B, d.heads));
+    VM_TRY(timed(st, CAT_ATTENTION, 0, [&] { return launch_attention(st, QKV(l), ATT(l), d.B, d.heads); }));
     {
       GemmDesc g = gd(M, D, D, ATT(l), D, false, PB(p_layer(l, L_OUT_W)), D, false, XM(l), D, EPI_STORE_BF16);
       g.bias = PF(p_layer(l, L_OUT_B)); g.residual = X(l); g.ldr = D;
       VM_TRY(timed_gemm(st, g));
     }
-    VM_TRY(launch_layernorm(st, XM(l), PF(p_layer(l, L_LN2_G)), PF(p_layer(l, L_LN2_B)), LN2(l), ST2(l), M, D, d.eps));
+    if (!save && g_use_fused && fused_mlp_supported(D, d.mlp)) {
+      // inference: LN2 + FC1 + GELU + FC2 + residual in one kernel (hidden activations stay on chip)
+      VM_TRY(timed(st, CAT_FUSED_MLP, 4.0 * M * D * d.mlp, [&] {
+        return launch_fused_mlp(st, XM(l), X(l + 1), PF(p_layer(l, L_LN2_G)), PF(p_layer(l, L_LN2_B)), PB(p_layer(l, L_FC1_W)),
+                                PF(p_layer(l, L_FC1_B)), PB(p_layer(l, L_FC2_W)), PF(p_layer(l, L_FC2_B)), M, D, d.mlp, d.eps);
+      }));
+      continue;
+    }
+    VM_TRY(timed(st, CAT_LAYERNORM, 0, [&] { return launch_layernorm(st, XM(l), PF(p_layer(l, L_LN2_G)), PF(p_layer(l, L_LN2_B)), LN2(l), ST2(l), M, D, d.eps); }));
     {
       GemmDesc g = gd(M, d.mlp, D, LN2(l), D, false, PB(p_layer(l, L_FC1_W)), D, false, HACT(l), d.mlp, EPI_BIAS_GELU);
       g.bias = PF(p_layer(l, L_FC1_B)); g.C2 = HPRE(l);
@@ -184,7 +201,7 @@ static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, c
     }
   }
   float* stf = save ? reinterpret_cast<float*>(ws + w.stf) : nullptr;
-  VM_TRY(launch_final_ln_pool(st, X(d.L), PF(p_lnf_g(d)), PF(p_lnf_g(d) + 1), y, stf, d.B, d.T, D, d.eps));
+  VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_final_ln_pool(st, X(d.L), PF(p_lnf_g(d)), PF(p_lnf_g(d) + 1), y, stf, d.B, d.T, D, d.eps); }));
   return VITMARL_OK;
 }
 
@@ -306,11 +323,11 @@ extern "C" int vitmarl_vit_bwd(void* stream, const VitmarlVitShape* s, const voi
   return vit_backward(static_cast<cudaStream_t>(stream), d, params, static_cast<uint8_t*>(workspace), dy, dparams, static_cast<bf16*>(dx));
 }
 
-// Enable / disable CUDA-event timing of every GEMM launch issued by vit_fwd / vit_bwd (resets the log).
+// Enable / disable CUDA-event timing of the launches issued by vit_fwd / vit_bwd (resets the log).
 extern "C" int vitmarl_vit_gemm_timing_enable(int enable) {
-  GemmTiming& t = g_timing;
+  OpTiming& t = g_timing;
   if (enable && !t.created) {
-    for (int i = 0; i < 2 * GemmTiming::kMax; ++i)
+    for (int i = 0; i < 2 * OpTiming::kMax; ++i)
       if (cudaEventCreate(&t.ev[i]) != cudaSuccess) return check_cuda(cudaGetLastError());
     t.created = true;
   }
@@ -320,20 +337,43 @@ extern "C" int vitmarl_vit_gemm_timing_enable(int enable) {
   return VITMARL_OK;
 }
 
-// Sum of the logged launches (synchronises on the last event): total ms, launches, algorithmic FLOPs.
-extern "C" int vitmarl_vit_gemm_timing_read(double* total_ms, long long* launches, double* flops) {
-  GemmTiming& t = g_timing;
-  double ms = 0.0;
+// Per-category totals: ms8 / n8 are arrays of 8 (0 gemm, 1 fused mlp, 2 fused attention block, 3 attention,
+// 4 layernorm, 5 other).  Synchronises on the last logged launch.
+extern "C" int vitmarl_vit_timing_read_categories(double* ms8, long long* n8) {
+  OpTiming& t = g_timing;
+  for (int i = 0; i < CAT_COUNT; ++i) { if (ms8) ms8[i] = 0.0; if (n8) n8[i] = 0; }
   if (t.n > 0) {
     cudaError_t e = cudaEventSynchronize(t.ev[2 * t.n - 1]);
     if (e != cudaSuccess) return check_cuda(e);
     for (int i = 0; i < t.n; ++i) {
       float x = 0.f;
-      if (cudaEventElapsedTime(&x, t.ev[2 * i], t.ev[2 * i + 1]) == cudaSuccess) ms += x;
+      if (cudaEventElapsedTime(&x, t.ev[2 * i], t.ev[2 * i + 1]) == cudaSuccess && ms8) ms8[t.cat[i]] += x;
+      if (n8) n8[t.cat[i]] += 1;
     }
   }
-  if (total_ms) *total_ms = ms;
-  if (launches) *launches = t.n;
-  if (flops) *flops = t.flops;
+  return VITMARL_OK;
+}
+
+// Tensor-core launches only (GEMM + fused block kernels): total ms, launches, algorithmic FLOPs.
+extern "C" int vitmarl_vit_gemm_timing_read(double* total_ms, long long* launches, double* flops) {
+  double ms8[CAT_COUNT];
+  long long n8[CAT_COUNT];
+  int rc = vitmarl_vit_timing_read_categories(ms8, n8);
+  if (rc) return rc;
+  if (total_ms) *total_ms = ms8[CAT_GEMM] + ms8[CAT_FUSED_MLP] + ms8[CAT_FUSED_ATTN];
+  if (launches) *launches = n8[CAT_GEMM] + n8[CAT_FUSED_MLP] + n8[CAT_FUSED_ATTN];
+  if (flops) *flops = g_timing.flops;
+  return VITMARL_OK;
+}
+
+// Select the fused block kernels (1, default) or the unfused v0 kernel sequence (0) for the inference forward.
+extern "C" int vitmarl_vit_set_fused(int enable) {
+  g_use_fused = enable != 0;
+  return VITMARL_OK;
+}
+
+// Debug: device buffer (>= 256 int64) receiving clock64() phase stamps of the fused MLP kernel (CTA 0, 2nd tile).
+extern "C" int vitmarl_debug_fused_mlp_timeline(long long* device_buf) {
+  fused_mlp_set_debug(device_buf);
   return VITMARL_OK;
 }

@@ -55,6 +55,12 @@ int launch_final_ln_pool(cudaStream_t s, const __nv_bfloat16* x, const float* ga
 int launch_final_ln_pool_bwd(cudaStream_t s, const __nv_bfloat16* x, const float* gamma, const float* stats, const float* dy,
                              __nv_bfloat16* dx, float* dgamma, float* dbeta, int B, int T, int D);
 
+// Fused MLP block (inference, D = 192): out = x + fc2(gelu(fc1(LN(x))));  `out` may alias `x`
+int launch_fused_mlp(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16* out, const float* gamma, const float* beta,
+                     const __nv_bfloat16* w1, const float* b1, const __nv_bfloat16* w2, const float* b2, int M, int D, int hidden, float eps);
+bool fused_mlp_supported(int D, int hidden);
+void fused_mlp_set_debug(long long* buf);   // device buffer of >= 256 int64 for clock64 phase stamps (null = off)
+
 // elementwise helpers
 int launch_gelu_bwd(cudaStream_t s, const __nv_bfloat16* pre, const __nv_bfloat16* dy, __nv_bfloat16* dx, size_t n);   // dx = dy * gelu'(pre)
 int launch_colsum(cudaStream_t s, const __nv_bfloat16* x, float* out, int M, int N);                                  // out[N] += sum_m x[m,n]
