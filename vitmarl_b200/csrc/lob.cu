@@ -63,9 +63,13 @@ struct Side {
   int p[RPL], q[RPL], oid[RPL], tid[RPL], ts[RPL], tns[RPL];
   int best;      // bids: max(price) | asks: min(price, -1 -> MAXINT)   (over existing rows)
   int vol;       // volume at the reported best price (Q10 semantics)
-  bool simple;   // every row: (price == -1) <=> (any field == -1)      -> fast empty-row search
-  bool clean;    // every row: qty > 0 or row is all -1                 -> touched-row wipe
+  bool tidy;     // every row is either all -1 or has no -1 field and qty > 0.  While this holds (the normal
+                 // state) an empty row <=> price == -1, only the touched row can need wiping and the cached
+                 // best price / volume can be updated incrementally; otherwise the literal full-array forms run.
 };
+
+// rows r = j*32 + lane exist for r < N; RPL = ceil(N/32), so only the last j can hold phantom rows
+#define VM_EX(j) ((j) < RPL - 1 || (j) * 32 + lane < N)
 
 template <int RPL>
 __device__ __forceinline__ void wipe_row(Side<RPL>& s, int j) {
@@ -78,13 +82,12 @@ __device__ __forceinline__ void wipe_all(Side<RPL>& s) {
 #pragma unroll
   for (int j = 0; j < RPL; ++j)
     if (s.q[j] <= 0) wipe_row(s, j);
-  s.clean = true;
 }
 
 // After modifying row `idx`: JOBA:85-90.  Fast path touches only that row.
 template <int RPL>
 __device__ __forceinline__ void wipe_after(Side<RPL>& s, int idx, int lane) {
-  if (!s.clean) { wipe_all(s); return; }
+  if (!s.tidy) { wipe_all(s); return; }
 #pragma unroll
   for (int j = 0; j < RPL; ++j)
     if (j * 32 + lane == idx && s.q[j] <= 0) wipe_row(s, j);
@@ -108,9 +111,8 @@ __device__ __forceinline__ void refresh_best(Side<RPL>& s, int N, int lane) {
   int m = IS_BID ? (int)0x80000000 : MAXINT;
 #pragma unroll
   for (int j = 0; j < RPL; ++j) {
-    bool ex = j * 32 + lane < N;
-    if (IS_BID) { if (ex) m = max(m, s.p[j]); }
-    else        { if (ex) m = min(m, s.p[j] == -1 ? MAXINT : s.p[j]); }
+    if (IS_BID) { if (VM_EX(j)) m = max(m, s.p[j]); }
+    else        { m = min(m, s.p[j] == -1 ? MAXINT : s.p[j]); }   // phantom rows hold -1 -> MAXINT: neutral
   }
   m = IS_BID ? __reduce_max_sync(FULL, m) : __reduce_min_sync(FULL, m);
   s.best = m;
@@ -118,7 +120,7 @@ __device__ __forceinline__ void refresh_best(Side<RPL>& s, int N, int lane) {
   int v = 0;
 #pragma unroll
   for (int j = 0; j < RPL; ++j)
-    if (j * 32 + lane < N && s.p[j] == bp) v = wadd(v, s.q[j]);
+    if (VM_EX(j) && s.p[j] == bp) v = wadd(v, s.q[j]);
   s.vol = __reduce_add_sync(FULL, v);
 }
 
@@ -135,7 +137,7 @@ __device__ __forceinline__ int top_index(const Side<RPL>& s, int N, int lane) {
   int ms = MAXINT;
 #pragma unroll
   for (int j = 0; j < RPL; ++j) {
-    bool ex = j * 32 + lane < N;
+    bool ex = VM_EX(j);
     t[j] = (s.p[j] == best) ? s.ts[j] : MAXINT;
     if (ex) ms = min(ms, t[j]);
   }
@@ -143,14 +145,14 @@ __device__ __forceinline__ int top_index(const Side<RPL>& s, int N, int lane) {
   int mn = MAXINT;
 #pragma unroll
   for (int j = 0; j < RPL; ++j) {
-    bool ex = j * 32 + lane < N;
+    bool ex = VM_EX(j);
     t[j] = (t[j] == ms) ? s.tns[j] : MAXINT;
     if (ex) mn = min(mn, t[j]);
   }
   mn = __reduce_min_sync(FULL, mn);
   bool pred[RPL];
 #pragma unroll
-  for (int j = 0; j < RPL; ++j) pred[j] = (j * 32 + lane < N) && (t[j] == mn);
+  for (int j = 0; j < RPL; ++j) pred[j] = VM_EX(j) && (t[j] == mn);
   int idx = first_index<RPL>(pred);
   return idx < 0 ? N - 1 : idx;
 }
@@ -218,26 +220,48 @@ __device__ __forceinline__ int match_against(Side<RPL>& book, const Msg& m, int3
 // JOBA:62-83 (Q1, Q2, Q3)
 template <int RPL, bool IS_BID>
 __device__ __forceinline__ void add_order(Side<RPL>& s, const Msg& m, int qrem, int N, int lane) {
+  const int qn = qrem > 0 ? qrem : 0;
+  const bool msg_clean = !(m.price == -1 || m.oid == -1 || m.tid == -1 || m.ts == -1 || m.tns == -1);
   bool pred[RPL];
-  if (s.simple) {
+  if (s.tidy) {
+    // ---- fast path: empty row <=> price == -1 (phantom rows r >= N also hold -1: caught by idx >= N) ----
 #pragma unroll
-    for (int j = 0; j < RPL; ++j) pred[j] = (j * 32 + lane < N) && (s.p[j] == -1);
-  } else {
+    for (int j = 0; j < RPL; ++j) pred[j] = s.p[j] == -1;
+    int idx = first_index<RPL>(pred);
+    const bool found = idx >= 0 && idx < N;
+    if (!found) idx = N - 1;                                   // Q2: full side -> last row overwritten
+    const bool alive = qn > 0;                                 // write + wipe merged: a zero-quantity row ends up all -1
+    const int wp = alive ? m.price : -1, wq = alive ? qn : -1, wo = alive ? m.oid : -1, wt = alive ? m.tid : -1,
+              ws = alive ? m.ts : -1, wn = alive ? m.tns : -1;
 #pragma unroll
     for (int j = 0; j < RPL; ++j)
-      pred[j] = (j * 32 + lane < N) && (s.p[j] == -1 || s.q[j] == -1 || s.oid[j] == -1 || s.tid[j] == -1 ||
-                                        s.ts[j] == -1 || s.tns[j] == -1);
+      if (j * 32 + lane == idx) { s.p[j] = wp; s.q[j] = wq; s.oid[j] = wo; s.tid[j] = wt; s.ts[j] = ws; s.tns[j] = wn; }
+    if (alive && !msg_clean) s.tidy = false;                   // a resting row with a -1 field
+    // cached best: the overwritten row was empty, so nothing changes unless the new order rests at / inside the best
+    const bool side_nonempty = IS_BID ? (s.best != -1) : (s.best != MAXINT);
+    if (found && msg_clean && side_nonempty) {
+      if (alive) {
+        const bool better = IS_BID ? (m.price > s.best) : (m.price < s.best);
+        if (better) { s.best = m.price; s.vol = qn; }
+        else if (m.price == s.best) s.vol = wadd(s.vol, qn);
+      }
+      return;
+    }
+    refresh_best<RPL, IS_BID>(s, N, lane);
+    return;
   }
+  // ---- literal path ----
+#pragma unroll
+  for (int j = 0; j < RPL; ++j)
+    pred[j] = VM_EX(j) && (s.p[j] == -1 || s.q[j] == -1 || s.oid[j] == -1 || s.tid[j] == -1 || s.ts[j] == -1 || s.tns[j] == -1);
   int idx = first_index<RPL>(pred);
   if (idx < 0) idx = N - 1;
-  int qn = qrem > 0 ? qrem : 0;
 #pragma unroll
   for (int j = 0; j < RPL; ++j)
     if (j * 32 + lane == idx) {
       s.p[j] = m.price; s.q[j] = qn; s.oid[j] = m.oid; s.tid[j] = m.tid; s.ts[j] = m.ts; s.tns[j] = m.tns;
     }
-  if (m.price == -1 || m.oid == -1 || m.tid == -1 || m.ts == -1 || m.tns == -1) s.simple = false;
-  wipe_after(s, idx, lane);
+  wipe_all(s);
   refresh_best<RPL, IS_BID>(s, N, lane);
 }
 
@@ -246,20 +270,30 @@ template <int RPL, bool IS_BID>
 __device__ __forceinline__ void cancel_order(Side<RPL>& s, const Msg& m, int init_id, int N, int lane) {
   bool pred[RPL];
 #pragma unroll
-  for (int j = 0; j < RPL; ++j) pred[j] = (j * 32 + lane < N) && (s.oid[j] == m.oid);
+  for (int j = 0; j < RPL; ++j) pred[j] = s.oid[j] == m.oid;       // phantom rows (oid -1) sit above every real row
   int idx = first_index<RPL>(pred);
-  if (idx < 0) {
+  if (idx < 0 || idx >= N) {
 #pragma unroll
-    for (int j = 0; j < RPL; ++j)
-      pred[j] = (j * 32 + lane < N) && (s.p[j] == m.price) && (s.oid[j] <= init_id) && (s.q[j] >= m.qty);
+    for (int j = 0; j < RPL; ++j) pred[j] = (s.p[j] == m.price) && (s.oid[j] <= init_id) && (s.q[j] >= m.qty);
     idx = first_index<RPL>(pred);
   }
-  if (idx < 0) idx = N - 1;
+  if (idx < 0 || idx >= N) idx = N - 1;                               // Q5
+  int rp = 0;                                                          // price of the touched row (before the update)
+  bool odd = false;
 #pragma unroll
   for (int j = 0; j < RPL; ++j)
-    if (j * 32 + lane == idx) s.q[j] = wsub(s.q[j], m.qty);
-  wipe_after(s, idx, lane);
-  refresh_best<RPL, IS_BID>(s, N, lane);
+    if (j * 32 + lane == idx) {
+      rp = s.p[j];
+      s.q[j] = wsub(s.q[j], m.qty);
+      if (s.p[j] == -1 && s.q[j] > 0) odd = true;                     // an empty row that acquired a positive quantity
+      if (s.tidy && s.q[j] <= 0) wipe_row(s, j);
+    }
+  if (!s.tidy) wipe_all(s);
+  else if (m.qty < 0 && __any_sync(FULL, odd)) s.tidy = false;
+  rp = __shfl_sync(FULL, rp, idx & 31);
+  // the cached best only changes when the touched row sat at the best price (or the side had no best)
+  const int bp = best_price_out<RPL, IS_BID>(s);
+  if (!s.tidy || rp == bp || bp == -1 || m.qty < 0) refresh_best<RPL, IS_BID>(s, N, lane);
 }
 
 // JOBA:617-661
@@ -285,24 +319,22 @@ __device__ __forceinline__ void process_message(Side<RPL>& asks, Side<RPL>& bids
 // ---------------------------------------------------------------- staging <-> registers
 template <int RPL>
 __device__ __forceinline__ void regs_from_smem(Side<RPL>& s, const int32_t* sm, int N, int lane) {
-  bool simple = true, clean = true;
+  bool tidy = true;
 #pragma unroll
   for (int j = 0; j < RPL; ++j) {
     int r = j * 32 + lane;
-    if (r < N) {
+    if (VM_EX(j)) {
       const int2* row = reinterpret_cast<const int2*>(sm + r * 6);
       int2 a = row[0], b = row[1], c = row[2];
       s.p[j] = a.x; s.q[j] = a.y; s.oid[j] = b.x; s.tid[j] = b.y; s.ts[j] = c.x; s.tns[j] = c.y;
-      bool any = a.x == -1 || a.y == -1 || b.x == -1 || b.y == -1 || c.x == -1 || c.y == -1;
-      bool all = a.x == -1 && a.y == -1 && b.x == -1 && b.y == -1 && c.x == -1 && c.y == -1;
-      if (any != (a.x == -1)) simple = false;
-      if (a.y <= 0 && !all) clean = false;
+      const bool all = (a.x & a.y & b.x & b.y & c.x & c.y) == -1;
+      const bool none = a.x != -1 && a.y != -1 && b.x != -1 && b.y != -1 && c.x != -1 && c.y != -1;
+      if (!(all || (none && a.y > 0))) tidy = false;
     } else {
       wipe_row(s, j);
     }
   }
-  s.simple = __all_sync(FULL, simple);
-  s.clean = __all_sync(FULL, clean);
+  s.tidy = __all_sync(FULL, tidy);
 }
 
 template <int RPL>
@@ -310,7 +342,7 @@ __device__ __forceinline__ void regs_to_smem(const Side<RPL>& s, int32_t* sm, in
 #pragma unroll
   for (int j = 0; j < RPL; ++j) {
     int r = j * 32 + lane;
-    if (r < N) {
+    if (VM_EX(j)) {
       int2* row = reinterpret_cast<int2*>(sm + r * 6);
       row[0] = make_int2(s.p[j], s.q[j]);
       row[1] = make_int2(s.oid[j], s.tid[j]);
@@ -387,7 +419,7 @@ __device__ __forceinline__ void render_env(const Side<RPL>& asks, const Side<RPL
 #pragma unroll
         for (int j = 0; j < RPL; ++j) {
           int key = ch == 0 ? (s.p[j] == -1 ? MAXINT : s.p[j]) : (int)(0u - (unsigned)s.p[j]);
-          bool c = (j * 32 + lane < N) && (!have_prev || key > prev);
+          bool c = VM_EX(j) && (!have_prev || key > prev);
           cand |= c;
           if (c) cur = min(cur, key);
         }
@@ -399,7 +431,7 @@ __device__ __forceinline__ void render_env(const Side<RPL>& asks, const Side<RPL
         int v = 0;
 #pragma unroll
         for (int j = 0; j < RPL; ++j)
-          if (j * 32 + lane < N && s.p[j] == price) v = wadd(v, s.q[j]);
+          if (VM_EX(j) && s.p[j] == price) v = wadd(v, s.q[j]);
         v = __reduce_add_sync(FULL, v);
         if (v < 0) v = 0;
         int clean = price != -1 ? v : 0;
@@ -434,7 +466,7 @@ __device__ __forceinline__ void render_env(const Side<RPL>& asks, const Side<RPL
     const int ba = best_price_out<RPL, false>(asks), bb = best_price_out<RPL, true>(bids);
 #pragma unroll
     for (int j = 0; j < RPL; ++j) {
-      if (j * 32 + lane < N) {
+      if (VM_EX(j)) {
         if (ba != -1 && asks.p[j] != -1) {
           long long d = (long long)asks.p[j] - ba;
           if (d >= 0) { long long r = d / P.tick; if (r < H) atomicAdd(&scratch[(int)r], asks.q[j]); }
@@ -482,7 +514,7 @@ __device__ __forceinline__ void render_env(const Side<RPL>& asks, const Side<RPL
 
 // ---------------------------------------------------------------- the kernel
 template <int RPL>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) lob_kernel(const LobParams P) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, RPL <= 4 ? 5 : (RPL <= 6 ? 3 : 2)) lob_kernel(const LobParams P) {
   extern __shared__ __align__(16) int32_t smem[];
   __shared__ __align__(8) uint64_t bars[kWarpsPerCta];
 
@@ -668,12 +700,19 @@ static int launch_lob(cudaStream_t stream, LobParams& P) {
 #define VM_LAUNCH(R)                                                                                      \
   do {                                                                                                    \
     if (smem > 48 * 1024) err = cudaFuncSetAttribute(lob_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(lob_kernel<R>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);  \
     if (err == cudaSuccess) lob_kernel<R><<<grid, block, smem, stream>>>(P);                              \
   } while (0)
-  if (rpl <= 1) VM_LAUNCH(1);
-  else if (rpl <= 2) VM_LAUNCH(2);
-  else if (rpl <= 4) VM_LAUNCH(4);
-  else VM_LAUNCH(8);
+  switch (rpl) {
+    case 1: VM_LAUNCH(1); break;
+    case 2: VM_LAUNCH(2); break;
+    case 3: VM_LAUNCH(3); break;
+    case 4: VM_LAUNCH(4); break;
+    case 5: VM_LAUNCH(5); break;
+    case 6: VM_LAUNCH(6); break;
+    case 7: VM_LAUNCH(7); break;
+    default: VM_LAUNCH(8); break;
+  }
 #undef VM_LAUNCH
   if (err == cudaSuccess) err = cudaGetLastError();
   return check_cuda(err);
