@@ -168,6 +168,14 @@ static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, c
     VM_TRY(timed_gemm(st, g));
   }
   for (int l = 0; l < d.L; ++l) {
+    const bool fuse_attn = !save && g_use_fused && fused_attn_supported(D, d.heads, d.T);
+    if (fuse_attn) {
+      // inference: LN1 + QKV + softmax(QK^T)V + out-projection + residual in one kernel
+      VM_TRY(timed(st, CAT_FUSED_ATTN, 8.0 * M * D * D + 4.0 * M * d.T * D, [&] {
+        return launch_fused_attn(st, X(l), XM(l), PF(p_layer(l, L_LN1_G)), PF(p_layer(l, L_LN1_B)), PB(p_layer(l, L_QKV_W)),
+                                 PF(p_layer(l, L_QKV_B)), PB(p_layer(l, L_OUT_W)), PF(p_layer(l, L_OUT_B)), M, D, d.heads, d.eps);
+      }));
+    } else {
     VM_TRY(timed(st, CAT_LAYERNORM, 0, [&] { return launch_layernorm(st, X(l), PF(p_layer(l, L_LN1_G)), PF(p_layer(l, L_LN1_B)), LN1(l), ST1(l), M, D, d.eps); }));
     {
       GemmDesc g = gd(M, 3 * D, D, LN1(l), D, false, PB(p_layer(l, L_QKV_W)), D, false, QKV(l), 3 * D, EPI_STORE_BF16);
@@ -179,6 +187,7 @@ static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, c
       GemmDesc g = gd(M, D, D, ATT(l), D, false, PB(p_layer(l, L_OUT_W)), D, false, XM(l), D, EPI_STORE_BF16);
       g.bias = PF(p_layer(l, L_OUT_B)); g.residual = X(l); g.ldr = D;
       VM_TRY(timed_gemm(st, g));
+    }
     }
     if (!save && g_use_fused && fused_mlp_supported(D, d.mlp)) {
       // inference: LN2 + FC1 + GELU + FC2 + residual in one kernel (hidden activations stay on chip)

@@ -61,6 +61,11 @@ int launch_fused_mlp(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16*
 bool fused_mlp_supported(int D, int hidden);
 void fused_mlp_set_debug(long long* buf);   // device buffer of >= 256 int64 for clock64 phase stamps (null = off)
 
+// Fused attention block (inference, D = 192, 3 heads, 64 tokens): out = x + Wo.attn(LN(x)) + bo; `out` may alias `x`
+int launch_fused_attn(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16* out, const float* gamma, const float* beta,
+                      const __nv_bfloat16* wqkv, const float* bqkv, const __nv_bfloat16* wo, const float* bo, int M, int D, int heads, float eps);
+bool fused_attn_supported(int D, int heads, int tokens);
+
 // elementwise helpers
 int launch_gelu_bwd(cudaStream_t s, const __nv_bfloat16* pre, const __nv_bfloat16* dy, __nv_bfloat16* dx, size_t n);   // dx = dy * gelu'(pre)
 int launch_colsum(cudaStream_t s, const __nv_bfloat16* x, float* out, int M, int N);                                  // out[N] += sum_m x[m,n]
