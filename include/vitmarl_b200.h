@@ -171,8 +171,8 @@ int vitmarl_vit_bwd(void* stream, const VitmarlVitShape* s, const void* const* p
 /* Inference forward: use the fused per-block kernels (1, default) or the unfused kernel sequence (0). */
 int vitmarl_vit_set_fused(int enable);
 
-/* Debug hook: device buffer (>= 256 int64) that receives clock64() phase stamps of the fused MLP kernel
- * (CTA 0, second tile); NULL switches it off. */
+/* Debug hook: device buffer (>= 512 int64) that receives clock64() phase stamps of the fused block kernels
+ * (CTA 0, second tile; [0,256) MLP block, [256,512) attention block); NULL switches it off. */
 int vitmarl_debug_fused_mlp_timeline(long long* device_buf);
 
 /* Measurement hook: CUDA-event timing (on the launch stream) of every tensor-core GEMM launch

@@ -31,6 +31,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
       : "memory");
 }
 
+// 2-D tile store smem -> global (bulk async group); rows beyond the tensor extent are clipped by the TMA unit
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m), "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // ---- UMMA descriptors -------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_128B, tile rows are 128 bytes (64 bf16), 8-row atoms of 1024 B.
 //   K-major  (rows = M/N index, 128 B of K per row):  LBO unused (=1), SBO = 1024 B between 8-row groups.

@@ -381,8 +381,10 @@ extern "C" int vitmarl_vit_set_fused(int enable) {
   return VITMARL_OK;
 }
 
-// Debug: device buffer (>= 256 int64) receiving clock64() phase stamps of the fused MLP kernel (CTA 0, 2nd tile).
+// Debug: device buffer (>= 512 int64) receiving clock64() phase stamps of the fused block kernels (CTA 0, 2nd tile):
+// [0,256) fused MLP, [256,512) fused attention block.
 extern "C" int vitmarl_debug_fused_mlp_timeline(long long* device_buf) {
   fused_mlp_set_debug(device_buf);
+  fused_attn_set_debug(device_buf ? device_buf + 256 : nullptr);
   return VITMARL_OK;
 }

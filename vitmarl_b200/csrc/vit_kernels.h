@@ -65,6 +65,7 @@ void fused_mlp_set_debug(long long* buf);   // device buffer of >= 256 int64 for
 int launch_fused_attn(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16* out, const float* gamma, const float* beta,
                       const __nv_bfloat16* wqkv, const float* bqkv, const __nv_bfloat16* wo, const float* bo, int M, int D, int heads, float eps);
 bool fused_attn_supported(int D, int heads, int tokens);
+void fused_attn_set_debug(long long* buf);
 
 // elementwise helpers
 int launch_gelu_bwd(cudaStream_t s, const __nv_bfloat16* pre, const __nv_bfloat16* dy, __nv_bfloat16* dx, size_t n);   // dx = dy * gelu'(pre)
