@@ -50,7 +50,7 @@ constexpr int ACC2_COL = 256;
 // barrier slots (8 bytes each)
 enum { B_XFULL = 0, B_XEMPTY, B_XNREADY, B_ACC2FULL, B_ACC2EMPTY, B_ACC1FULL = 5, B_ACC1EMPTY = B_ACC1FULL + NB,
        B_HREADY = B_ACC1EMPTY + NB, B_HEMPTY = B_HREADY + NB, B_W1FULL = B_HEMPTY + NB, B_W1EMPTY = B_W1FULL + NS1,
-       B_W2FULL = B_W1EMPTY + NS1, B_W2EMPTY = B_W2FULL + NS2, B_TMEMSLOT = B_W2EMPTY + NS2, B_COUNT };
+       B_W2FULL = B_W1EMPTY + NS1, B_W2EMPTY = B_W2FULL + NS2, B_RESFULL = B_W2EMPTY + NS2, B_RESREAD, B_TMEMSLOT, B_COUNT };
 static_assert(B_COUNT * 8 <= 512, "barrier area");
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 }  // namespace fmlp
@@ -69,7 +69,7 @@ struct FusedMlpParams {
 
 __global__ void __launch_bounds__(fmlp::THREADS, 1)
 fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-                 const __grid_constant__ CUtensorMap tmW2, const FusedMlpParams p) {
+                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut, const FusedMlpParams p) {
   using namespace fmlp;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -85,9 +85,9 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const int num_tiles = (p.M + TM - 1) / TM;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmOut);
     mbar_init(bar(B_XFULL), 1); mbar_init(bar(B_XEMPTY), 1); mbar_init(bar(B_XNREADY), 8);
-    mbar_init(bar(B_ACC2FULL), 1); mbar_init(bar(B_ACC2EMPTY), 8);
+    mbar_init(bar(B_ACC2FULL), 1); mbar_init(bar(B_ACC2EMPTY), 8); mbar_init(bar(B_RESFULL), 1); mbar_init(bar(B_RESREAD), 8);
     for (int i = 0; i < NB; ++i) {
       mbar_init(bar(B_ACC1FULL + i), 1); mbar_init(bar(B_ACC1EMPTY + i), 8);
       mbar_init(bar(B_HREADY + i), 8); mbar_init(bar(B_HEMPTY + i), 1);
@@ -111,7 +111,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       int s1 = 0; uint32_t ph1 = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        mbar_wait(bar(B_XEMPTY), (it & 1) ^ 1);
+        mbar_wait(bar(B_RESREAD), (it & 1) ^ 1);            // previous tile's epilogue has read its residual out of the x buffer
         mbar_arrive_expect_tx(bar(B_XFULL), XN_BYTES);
         for (int kb = 0; kb < KB_X; ++kb) tma_load_2d(sbase + OFF_XN + kb * TM * 128, &tmX, kb * 64, tile * TM, bar(B_XFULL));
         for (int c = 0; c < NCHUNK; ++c)
@@ -121,6 +121,10 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             tma_load_2d(sbase + OFF_W1 + s1 * S1_BYTES, &tmW1, kb * 64, c * HC, bar(B_W1FULL + s1));
             if (++s1 == NS1) { s1 = 0; ph1 ^= 1; }
           }
+        // residual: when the last FC1 has retired (XEMPTY) LN(x) is dead -> reload the raw x tile into the same buffer
+        mbar_wait(bar(B_XEMPTY), it & 1);
+        mbar_arrive_expect_tx(bar(B_RESFULL), XN_BYTES);
+        for (int kb = 0; kb < KB_X; ++kb) tma_load_2d(sbase + OFF_XN + kb * TM * 128, &tmX, kb * 64, tile * TM, bar(B_RESFULL));
       }
     }
   } else if (warp == 2) {
@@ -210,9 +214,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     uint32_t gc = 0;                           // global chunk counter
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int grow = tile * TM + row;
       const bool stamp = (warp == 3 && lane == 0);
-      if (stamp) FMLP_STAMP(0);
+      if (stamp) { bulk_wait_read0(); FMLP_STAMP(0); }      // previous tile's TMA store has finished reading the staging smem
       // ---- LayerNorm in place: thread (row, hf) owns columns [hf*96, hf*96+96) = 12 chunks of 8 bf16 ----
       mbar_wait(bar(B_XFULL), it & 1);
       if (stamp) FMLP_STAMP(1);
@@ -275,11 +278,6 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           pk[16 + 2 * j] = gelu_tanh_bf16x2(pack_bf16(__uint_as_float(r1[4 * j]) + bw.x, __uint_as_float(r1[4 * j + 1]) + bw.y));
           pk[16 + 2 * j + 1] = gelu_tanh_bf16x2(pack_bf16(__uint_as_float(r1[4 * j + 2]) + bw.z, __uint_as_float(r1[4 * j + 3]) + bw.w));
         }
-        if (c == NCHUNK - 2 && grow < p.M) {                        // prefetch the residual row segment for the final epilogue
-          const uint4* rp = reinterpret_cast<const uint4*>(p.x + (size_t)grow * D + hf * 96);
-#pragma unroll
-          for (int i = 0; i < 12; ++i) v[i] = __ldg(rp + i);
-        }
         if (stamp) FMLP_STAMP(11 + 4 * c);
         mbar_wait(bar(B_HEMPTY + b), (use & 1) ^ 1);                // FC2 of the previous user has finished reading this H buffer
         if (stamp) FMLP_STAMP(12 + 4 * c);
@@ -292,8 +290,9 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (lane == 0) mbar_arrive(bar(B_HREADY + b));
         if (stamp) FMLP_STAMP(13 + 4 * c);
       }
-      // ---- final epilogue: out = acc2 + b2 + x ----
+      // ---- final epilogue: out = acc2 + b2 + x  (residual tile in smem, result staged in the H buffers, TMA store) ----
       mbar_wait(bar(B_ACC2FULL), it & 1);
+      mbar_wait(bar(B_RESFULL), it & 1);
       tc_fence_after();
       if (stamp) FMLP_STAMP(60);
 #pragma unroll
@@ -302,28 +301,36 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + tm_lane + ACC2_COL + col, r);
         tmem_ld_wait();
-        if (grow < p.M) {
-          uint4* op = reinterpret_cast<uint4*>(p.out + (size_t)grow * D + col);
+        const int kb = col >> 6, ch0 = (col & 63) >> 3;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 xr = v[cc * 4 + j];
-            const uint32_t* xw = &xr.x;
-            uint32_t ow[4];
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t off = (uint32_t)(kb * TM * 128 + row * 128) + ((((uint32_t)(ch0 + j)) ^ sw) << 4);
+          const uint4 xr = *reinterpret_cast<const uint4*>(sptr + OFF_XN + off);
+          const uint32_t* xw = &xr.x;
+          uint32_t ow[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int e = 8 * j + 2 * k;
-              ow[k] = pack_bf16(__uint_as_float(r[e]) + s_b2[col + e] + bf16_lo(xw[k]), __uint_as_float(r[e + 1]) + s_b2[col + e + 1] + bf16_hi(xw[k]));
-            }
-            op[j] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          for (int k = 0; k < 4; ++k) {
+            const int e = 8 * j + 2 * k;
+            ow[k] = pack_bf16(__uint_as_float(r[e]) + s_b2[col + e] + bf16_lo(xw[k]), __uint_as_float(r[e + 1]) + s_b2[col + e + 1] + bf16_hi(xw[k]));
           }
+          *reinterpret_cast<uint4*>(sptr + OFF_H + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
       }
       tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_RESREAD));
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (stamp) {
+        for (int kb = 0; kb < KB_X; ++kb) tma_store_2d(&tmOut, sbase + OFF_H + kb * TM * 128, kb * 64, tile * TM);
+        bulk_commit();
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_ACC2EMPTY));
       if (stamp) FMLP_STAMP(61);
     }
   }
+  if (warp == 3 && lane == 0) bulk_wait0();                  // outstanding TMA stores complete before the CTA exits
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -342,16 +349,17 @@ int launch_fused_mlp(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16*
   using namespace fmlp;
   if (D != fmlp::D || hidden != HID) { set_last_error("fused_mlp: only D=192, hidden=768"); return VITMARL_EINVAL; }
   if (M <= 0) return VITMARL_OK;
-  CUtensorMap tmX, tmW1, tmW2;
+  CUtensorMap tmX, tmW1, tmW2, tmOut;
   int rc;
   if ((rc = make_tmap_2d_bf16(&tmX, x, M, D, (uint64_t)D * 2, TM, 64))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmOut, out, M, D, (uint64_t)D * 2, TM, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmW1, w1, HID, D, (uint64_t)D * 2, HC, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmW2, w2, fmlp::D, HID, (uint64_t)HID * 2, fmlp::D, 64))) return rc;
   FusedMlpParams p{M, x, out, gamma, beta, b1, b2, eps, g_fmlp_dbg};
   cudaError_t e = cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return check_cuda(e);
   const int tiles = (M + TM - 1) / TM;
-  fused_mlp_kernel<<<min(tiles, num_sms()), THREADS, SMEM_BYTES, stream>>>(tmX, tmW1, tmW2, p);
+  fused_mlp_kernel<<<min(tiles, num_sms()), THREADS, SMEM_BYTES, stream>>>(tmX, tmW1, tmW2, tmOut, p);
   return check_cuda(cudaGetLastError());
 }
 
