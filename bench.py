@@ -253,10 +253,13 @@ def run_ours(args):
         "config": {"workload": "configs[1]: 2-agent MAPPO step shape (MM+EXE), 4096 envs/GPU, M=13 msgs/step, N=T=100, "
                                "64x64x2 LOB raster, ViT-Tiny/8 (D192 L12 h3) forward",
                    "envs_per_gpu": E, "msgs_per_step": M, "image": "64x64x2 bf16", "vit": "tiny/8 D192 L12",
-                   "l2": "per-step working set ~1.1 GB (activations) > 126 MB L2; no flush needed",
+                   "l2": "per-step working set ~300 MB (residual stream 100 MB + patches 67 MB + raster 67 MB + books/trades 35 MB + weights) > 126 MB L2; no flush needed",
                    "parallelism": f"env-sharded x{world}, no data-path collective"},
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved_tf / peaks["bf16_tflops_sustained"], "traffic": None,
+                     "frac": achieved_tf / peaks["bf16_tflops_sustained"],
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused block kernels at this shape,
+                     # from the ncu --set full capture profiles/r01_fused_blocks_ncu_full_v2.md (algorithmic: 100.7 MB in + 100.7 MB out)
+                     "traffic": 143.0e6,
                      "kernel": "tcgen05 kernels of the step (vitmarl::gemm_kernel + fused block kernels), CUDA events per launch",
                      "per_step_ms_by_kernel_class": breakdown,
                      "launches_timed": gemm_launches, "avg_launch_us": gemm_ms_per_launch * 1e3,
