@@ -111,6 +111,30 @@ int vitmarl_env_step(void* stream, int E, int N, int T, int M,
                      void* image, int img_dtype, int H, int W,
                      int cancel_mode, int32_t init_id);
 
+/* ---- callers either side of the order-book step --------------------- */
+
+/* Replaces job.getCancelMsgs under vmap (JaxOrderBookArrays.py:756-782): for each env the first `size` rows
+ * (ascending) of `bookside` [E,N,6] whose trader id equals agent_id become cancel messages
+ * [2, side, qty, price, oid, tid, t_s, t_ns]; missing ones are [2, side, 0, 0, 0, 0, t_s, t_ns].
+ *   cancel_time [E,2], out [E,size,8] */
+int vitmarl_get_cancel_msgs(void* stream, int E, int N, int size, const int32_t* bookside, int agent_id, int side,
+                            const int32_t* cancel_time, int32_t* out);
+
+/* Replaces job.get_agent_trades under vmap (JaxOrderBookArrays.py:824-831): rows of trades [E,T,8] that are executed
+ * (price >= 0) and involve agent_id as passive or aggressive trader are kept, all others zeroed. */
+int vitmarl_get_agent_trades(void* stream, int E, int T, const int32_t* trades, int agent_id, int32_t* out);
+
+/* Message assembly of MARLEnv.step_env (marl_env.py:272-344): combined[e] = [cancel_msgs[e]; action_msgs[e] with
+ * order ids renumbered to order_id_counter[e] - arange(Ma) and rows permuted by perm[e] (jax.random.permutation
+ * indices computed by the caller; NULL = no shuffle); data messages] where the data messages are
+ * lax.dynamic_slice(message_data [n_total,8], start_index[e] + n_data*step_counter[e], n_data) (start clamped,
+ * base_env.py:341-371) with the first six fields zeroed when time_s >= end_time_s[e] (fixed_time episodes; NULL =
+ * fixed_steps).  combined [E, Mc+Ma+n_data, 8]; new_order_id_counter [E] = counter - Ma (nullable). */
+int vitmarl_build_step_msgs(void* stream, int E, int n_total, int n_data, int Mc, int Ma, const int32_t* message_data,
+                            const int32_t* start_index, const int32_t* step_counter, const int32_t* end_time_s,
+                            const int32_t* cancel_msgs, const int32_t* action_msgs, const int32_t* perm,
+                            const int32_t* order_id_counter, int32_t* combined, int32_t* new_order_id_counter);
+
 /* ---- stage 3: ViT encoder ---------------------------------------------------------- */
 
 #define VITMARL_EPI_STORE_BF16 0 /* C(bf16) = acc (+bias) (+pos[row % period]) (+residual)        */
@@ -181,7 +205,7 @@ int vitmarl_debug_fused_mlp_timeline(long long* device_buf);
 int vitmarl_vit_gemm_timing_enable(int enable);
 int vitmarl_vit_gemm_timing_read(double* total_ms, long long* launches, double* flops);
 /* Per-category totals over the same log; arrays of 8: 0 gemm, 1 fused MLP block, 2 fused attention block,
- * 3 attention, 4 layernorm, 5 other. */
+ * 3 attention, 4 layernorm, 5 other (patchify, pool, bias column sums), 6 dW GEMMs, 7 dX GEMMs. */
 int vitmarl_vit_timing_read_categories(double* ms8, long long* n8);
 
 #ifdef __cplusplus

@@ -382,3 +382,56 @@ def render_image(asks, bids, height: int, width: int, tick_size: int = 100) -> n
             v = _w32(int(vol[r]))
             img[r, :bar_length(v, width), ch] = 1
     return img
+
+
+# ----------------------------------------------------------------------------- callers either side of the book step
+def getCancelMsgs(bookside, agentID, size, side, cancel_time, cancel_time_ns) -> np.ndarray:
+    """JOBA:756-782: cancel messages for the first `size` orders of a trader; fill -> the appended zero row."""
+    book = np.concatenate([np.asarray(bookside, dtype=np.int32), np.zeros((1, 6), dtype=np.int32)], axis=0)
+    idx = np.flatnonzero(book[:, 3] == agentID)[:size]
+    idx = np.concatenate([idx, np.full((size - idx.size,), -1, dtype=np.int64)])
+    out = np.zeros((size, 8), dtype=np.int32)
+    out[:, 0] = 2
+    out[:, 1] = side
+    out[:, 2] = book[idx, 1]
+    out[:, 3] = book[idx, 0]
+    out[:, 4] = book[idx, 2]
+    out[:, 5] = book[idx, 3]
+    out[:, 6] = cancel_time
+    out[:, 7] = cancel_time_ns
+    return out
+
+
+def get_agent_trades(trades, agent_id) -> np.ndarray:
+    """JOBA:824-831"""
+    trades = np.asarray(trades, dtype=np.int32)
+    executed = np.where((trades[:, 0] >= 0)[:, None], trades, 0)
+    mask2 = (agent_id == executed[:, 6]) | (agent_id == executed[:, 7])
+    return np.where(mask2[:, None], executed, 0).astype(np.int32)
+
+
+def get_data_messages(message_data, start, step_counter, n_data_msg_per_step, end_time_s=None) -> np.ndarray:
+    """base_env.py:341-371 (`_get_data_messages`); lax.dynamic_slice_in_dim clamps the start index.
+    end_time_s is given for ep_type == 'fixed_time' only."""
+    message_data = np.asarray(message_data, dtype=np.int32)
+    off = int(start) + n_data_msg_per_step * int(step_counter)
+    off = max(0, min(off, message_data.shape[0] - n_data_msg_per_step))
+    msgs = message_data[off:off + n_data_msg_per_step].copy()
+    if end_time_s is not None:
+        late = msgs[:, -2] >= end_time_s
+        msgs[late, :-2] = 0
+    return msgs
+
+
+def build_step_msgs(message_data, start, step_counter, n_data, cancel_msgs, action_msgs, order_id_counter, perm=None,
+                    end_time_s=None):
+    """marl_env.py:272-344: data messages, order-id renumbering of the action messages (:314-319), shuffle (:322-324,
+    with the permutation indices supplied by the caller's jax.random.permutation), concatenation (:344)."""
+    action = np.array(action_msgs, dtype=np.int32, copy=True)
+    Ma = action.shape[0]
+    action[:, 4] = np.array([_w32(int(order_id_counter) - k) for k in range(Ma)], dtype=np.int32)
+    if perm is not None:
+        action = action[np.asarray(perm)]
+    data = get_data_messages(message_data, start, step_counter, n_data, end_time_s)
+    combined = np.concatenate([np.asarray(cancel_msgs, dtype=np.int32).reshape(-1, 8), action, data], axis=0)
+    return combined, _w32(int(order_id_counter) - Ma)

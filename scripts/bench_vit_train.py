@@ -51,6 +51,10 @@ e1.record(); sync()
 ms = e0.elapsed_time(e1) / a.steps
 gm, gn, gf = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
 lib.vitmarl_vit_gemm_timing_read(ctypes.byref(gm), ctypes.byref(gn), ctypes.byref(gf))
+cat_ms, cat_n = (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
+lib.vitmarl_vit_timing_read_categories(cat_ms, cat_n)
+names = ["gemm_fwd", "fused_mlp", "fused_attn", "attention", "layernorm", "other", "gemm_dW", "gemm_dX"]
+breakdown = {nm: round(cat_ms[i] / a.steps, 3) for i, nm in enumerate(names) if cat_n[i]}
 if world > 1:
     t = torch.tensor([ms], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t)
 T, D, L, P, C = cfg.tokens, cfg.dim, cfg.depth, cfg.patch, cfg.channels
@@ -60,5 +64,5 @@ if rank == 0:
                       "alg_tflop_per_step": 3 * F * B / 1e12, "achieved_tflops_per_gpu": 3 * F * B / (ms * 1e-3) / 1e12,
                       "gemm_ms_per_step": gm.value / a.steps, "gemm_tflops": gf.value / (gm.value * 1e-3) / 1e12,
                       "grad_bytes_allreduced": red.flat.numel() * 4 if world > 1 else 0,
-                      "workspace_GB": enc._ws.numel() / 1e9}))
+                      "workspace_GB": enc._ws.numel() / 1e9, "ms_by_kernel_class": breakdown}))
 if world > 1: dist.destroy_process_group()

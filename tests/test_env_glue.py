@@ -1,0 +1,84 @@
+"""Callers either side of the book step: oracle known answers on CPU, CUDA parity on GPU."""
+import numpy as np
+import pytest
+
+from oracle import lob_oracle as O
+
+
+def _book(rng, N=12):
+    b = np.full((N, 6), -1, np.int32)
+    live = rng.random(N) < 0.7
+    b[live] = np.stack([rng.integers(100, 110, N), rng.integers(1, 50, N), rng.integers(1, 99, N), rng.integers(-3, 2, N),
+                        rng.integers(0, 5, N), rng.integers(0, 5, N)], axis=1)[live]
+    return b
+
+
+def test_get_cancel_msgs_known_answer():
+    b = np.full((5, 6), -1, np.int32)
+    b[1] = [101, 7, 11, -100, 3, 4]
+    b[3] = [102, 9, 12, -100, 3, 5]
+    b[4] = [103, 1, 13, -101, 3, 6]
+    out = O.getCancelMsgs(b, -100, 3, 1, 77, 88)
+    assert out.tolist() == [[2, 1, 7, 101, 11, -100, 77, 88], [2, 1, 9, 102, 12, -100, 77, 88], [2, 1, 0, 0, 0, 0, 77, 88]]
+    assert O.getCancelMsgs(b, -100, 1, -1, 1, 2).tolist() == [[2, -1, 7, 101, 11, -100, 1, 2]]
+
+
+def test_get_agent_trades_known_answer():
+    t = np.full((4, 8), -1, np.int32)
+    t[0] = [100, 5, 1, 2, 3, 4, -100, 9]
+    t[1] = [100, -5, 1, 2, 3, 4, 8, -100]
+    t[2] = [100, 5, 1, 2, 3, 4, 8, 9]
+    out = O.get_agent_trades(t, -100)
+    assert out[0].tolist() == t[0].tolist() and out[1].tolist() == t[1].tolist() and (out[2:] == 0).all()
+    assert (O.get_agent_trades(t, -1) == 0).all()      # empty rows (price -1) never count, even for id -1
+
+
+def test_build_step_msgs_known_answer():
+    md = np.arange(10 * 8, dtype=np.int32).reshape(10, 8)
+    md[:, 6] = np.arange(10) + 100
+    cancel = np.full((2, 8), 7, np.int32)
+    action = np.stack([np.full(8, 10 + k, np.int32) for k in range(3)])
+    comb, newc = O.build_step_msgs(md, 2, 1, 2, cancel, action, -200, perm=[2, 0, 1], end_time_s=105)
+    assert comb.shape == (7, 8) and newc == -203
+    assert comb[2:5, 4].tolist() == [-202, -200, -201] and comb[2:5, 0].tolist() == [12, 10, 11]
+    assert np.array_equal(comb[5], md[4])                       # time 104 < 105 kept
+    assert comb[6, :6].tolist() == [0] * 6 and comb[6, 6:].tolist() == md[5, 6:].tolist()   # time 105 >= end -> zeroed
+    # dynamic_slice clamps the start so that the slice fits
+    assert np.array_equal(O.get_data_messages(md, 9, 5, 3), md[7:10])
+
+
+@pytest.mark.gpu
+def test_env_glue_cuda_parity():
+    import torch
+    from vitmarl_b200 import env as venv, jaxob
+    rng = np.random.default_rng(3)
+    E, N, T = 70, 37, 20
+    books = np.stack([_book(rng, N) for _ in range(E)])
+    ct = rng.integers(0, 1000, (E, 2)).astype(np.int32)
+    for agent, size, side in ((-3, 4, 1), (0, 40, -1), (1, 1, 1)):
+        got = jaxob.getCancelMsgs(torch.from_numpy(books).cuda(), agent, size, side, torch.from_numpy(ct).cuda()).cpu().numpy()
+        want = np.stack([O.getCancelMsgs(books[e], agent, size, side, ct[e, 0], ct[e, 1]) for e in range(E)])
+        assert np.array_equal(got, want)
+    trades = rng.integers(-3, 4, (E, T, 8)).astype(np.int32)
+    for agent in (-1, 0, 2):
+        got = jaxob.get_agent_trades(torch.from_numpy(trades).cuda(), agent).cpu().numpy()
+        want = np.stack([O.get_agent_trades(trades[e], agent) for e in range(E)])
+        assert np.array_equal(got, want)
+    n_total, n_data, Mc, Ma = 500, 7, 5, 12
+    md = rng.integers(-5, 50000, (n_total, 8)).astype(np.int32)
+    md[:, 6] = np.sort(rng.integers(34200, 34300, n_total))
+    start = rng.integers(-3, n_total + 5, E).astype(np.int32)
+    stepc = rng.integers(0, 20, E).astype(np.int32)
+    cancel = rng.integers(-9, 9, (E, Mc, 8)).astype(np.int32)
+    action = rng.integers(-9, 9, (E, Ma, 8)).astype(np.int32)
+    counter = rng.integers(-5000, -200, E).astype(np.int32)
+    perm = np.stack([rng.permutation(Ma) for _ in range(E)]).astype(np.int32)
+    endt = rng.integers(34200, 34300, E).astype(np.int32)
+    dev = lambda a: torch.from_numpy(a).cuda()
+    for use_perm, use_end in ((True, True), (False, False)):
+        got, newc = venv.build_step_msgs(dev(md), dev(start), dev(stepc), n_data, dev(cancel), dev(action), dev(counter),
+                                         dev(perm) if use_perm else None, dev(endt) if use_end else None)
+        for e in range(E):
+            w, wc = O.build_step_msgs(md, start[e], stepc[e], n_data, cancel[e], action[e], counter[e],
+                                      perm[e] if use_perm else None, endt[e] if use_end else None)
+            assert np.array_equal(got[e].cpu().numpy(), w) and int(newc[e]) == wc

@@ -1,0 +1,133 @@
+// Callers on either side of the order-book kernel: integer gather / select glue
+// of MARLEnv.step_env that touches the books, trades and the shared message array.  HBM-bound byte work: one thread
+// per 32-byte message row (2 x 16-byte accesses), grids sized from the SM count.
+//   vitmarl_get_cancel_msgs   job.getCancelMsgs                         JaxOrderBookArrays.py:756-782
+//   vitmarl_get_agent_trades  job.get_agent_trades                      JaxOrderBookArrays.py:824-831
+//   vitmarl_build_step_msgs   BaseLOBEnv._get_data_messages + order-id renumbering + (given) shuffle + concatenate
+//                             base_env.py:341-371, marl_env.py:272-344
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "vit_kernels.h"
+#include "../../include/vitmarl_b200.h"
+
+namespace vitmarl {
+
+// one warp per environment: the first `size` rows (ascending) whose trader id equals agent_id
+__global__ void __launch_bounds__(128) cancel_msgs_kernel(int E, int N, int size, const int32_t* __restrict__ book, int agent_id, int side,
+                                                           const int32_t* __restrict__ cancel_time, int32_t* __restrict__ out) {
+  const int e = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (e >= E) return;
+  const int32_t* b = book + (size_t)e * N * 6;
+  const int t_s = cancel_time[2 * e], t_ns = cancel_time[2 * e + 1];
+  int found = 0;
+  for (int base = 0; base < N && found < size; base += 32) {
+    const int r = base + lane;
+    const bool hit = r < N && b[r * 6 + 3] == agent_id;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    const int pos = found + __popc(m & ((1u << lane) - 1u));
+    if (hit && pos < size) {
+      int4* o = reinterpret_cast<int4*>(out + ((size_t)e * size + pos) * 8);
+      o[0] = make_int4(2, side, b[r * 6 + 1], b[r * 6 + 0]);
+      o[1] = make_int4(b[r * 6 + 2], b[r * 6 + 3], t_s, t_ns);
+    }
+    found += __popc(m);
+  }
+  // fill_value=-1 indexes the appended all-zero row (JOBA:770-771)
+  for (int pos = min(found, size) + lane; pos < size; pos += 32) {
+    int4* o = reinterpret_cast<int4*>(out + ((size_t)e * size + pos) * 8);
+    o[0] = make_int4(2, side, 0, 0);
+    o[1] = make_int4(0, 0, t_s, t_ns);
+  }
+}
+
+__global__ void agent_trades_kernel(size_t rows, const int4* __restrict__ trades, int agent_id, int4* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < rows; i += (size_t)gridDim.x * blockDim.x) {
+    int4 a = __ldg(trades + 2 * i), b = __ldg(trades + 2 * i + 1);
+    const bool executed = a.x >= 0;                            // JOBA:827
+    if (!executed) { a = make_int4(0, 0, 0, 0); b = a; }
+    const bool mine = (agent_id == b.z) || (agent_id == b.w);   // columns 6, 7 (JOBA:829)
+    if (!mine) { a = make_int4(0, 0, 0, 0); b = a; }
+    out[2 * i] = a;
+    out[2 * i + 1] = b;
+  }
+}
+
+struct StepMsgParams {
+  int E, n_total, n_data, Mc, Ma;
+  const int32_t* message_data; const int32_t* start_index; const int32_t* step_counter; const int32_t* end_time_s;
+  const int32_t* cancel_msgs; const int32_t* action_msgs; const int32_t* perm; const int32_t* order_id_counter;
+  int32_t* combined; int32_t* new_counter;
+};
+
+__global__ void step_msgs_kernel(const StepMsgParams p) {
+  const int M = p.Mc + p.Ma + p.n_data;
+  const size_t total = (size_t)p.E * M;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(i / M), j = (int)(i % M);
+    int4 a, b;
+    if (j < p.Mc) {                                            // cancel messages first (marl_env.py:344)
+      const int4* s = reinterpret_cast<const int4*>(p.cancel_msgs + ((size_t)e * p.Mc + j) * 8);
+      a = __ldg(s); b = __ldg(s + 1);
+    } else if (j < p.Mc + p.Ma) {                              // action messages: renumber, then shuffle (marl_env.py:314-324)
+      const int k = j - p.Mc;
+      const int src = p.perm ? p.perm[(size_t)e * p.Ma + k] : k;
+      const int4* s = reinterpret_cast<const int4*>(p.action_msgs + ((size_t)e * p.Ma + src) * 8);
+      a = __ldg(s); b = __ldg(s + 1);
+      b.x = wsub(p.order_id_counter[e], src);                  // new_order_ids = counter - arange(Ma), applied before the shuffle
+    } else {                                                   // data messages (base_env.py:341-371)
+      const int k = j - p.Mc - p.Ma;
+      long long off = (long long)p.start_index[e] + (long long)p.n_data * p.step_counter[e];
+      const long long hi = (long long)p.n_total - p.n_data;    // lax.dynamic_slice clamps the start index
+      off = off < 0 ? 0 : (off > hi ? hi : off);
+      const int4* s = reinterpret_cast<const int4*>(p.message_data + ((size_t)off + k) * 8);
+      a = __ldg(s); b = __ldg(s + 1);
+      if (p.end_time_s && b.z >= p.end_time_s[e]) { a = make_int4(0, 0, 0, 0); b.x = 0; b.y = 0; }   // fixed_time: zero all but the time
+    }
+    int4* d = reinterpret_cast<int4*>(p.combined + i * 8);
+    d[0] = a; d[1] = b;
+    if (j == 0 && p.new_counter) p.new_counter[e] = wsub(p.order_id_counter[e], p.Ma);
+  }
+}
+
+}  // namespace vitmarl
+
+using namespace vitmarl;
+
+extern "C" int vitmarl_get_cancel_msgs(void* stream, int E, int N, int size, const int32_t* bookside, int agent_id, int side,
+                                       const int32_t* cancel_time, int32_t* out) {
+  if (E == 0 || size == 0) return VITMARL_OK;
+  if (E < 0 || N < 1 || size < 0 || !bookside || !cancel_time || !out || (reinterpret_cast<uintptr_t>(out) & 15)) return VITMARL_EINVAL;
+  cancel_msgs_kernel<<<(E + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(E, N, size, bookside, agent_id, side, cancel_time, out);
+  return check_cuda(cudaGetLastError());
+}
+
+extern "C" int vitmarl_get_agent_trades(void* stream, int E, int T, const int32_t* trades, int agent_id, int32_t* out) {
+  const size_t rows = (size_t)E * T;
+  if (rows == 0) return VITMARL_OK;
+  if (E < 0 || T < 0 || !trades || !out || ((reinterpret_cast<uintptr_t>(trades) | reinterpret_cast<uintptr_t>(out)) & 15)) return VITMARL_EINVAL;
+  const int grid = (int)((rows + 255) / 256 < (size_t)num_sms() * 8 ? (rows + 255) / 256 : (size_t)num_sms() * 8);
+  agent_trades_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, reinterpret_cast<const int4*>(trades), agent_id,
+                                                                           reinterpret_cast<int4*>(out));
+  return check_cuda(cudaGetLastError());
+}
+
+extern "C" int vitmarl_build_step_msgs(void* stream, int E, int n_total, int n_data, int Mc, int Ma, const int32_t* message_data,
+                                       const int32_t* start_index, const int32_t* step_counter, const int32_t* end_time_s,
+                                       const int32_t* cancel_msgs, const int32_t* action_msgs, const int32_t* perm,
+                                       const int32_t* order_id_counter, int32_t* combined, int32_t* new_order_id_counter) {
+  if (E == 0) return VITMARL_OK;
+  if (E < 0 || n_data < 0 || Mc < 0 || Ma < 0 || n_total < n_data || !combined) return VITMARL_EINVAL;
+  if ((n_data > 0 && (!message_data || !start_index || !step_counter)) || (Mc > 0 && !cancel_msgs) || (Ma > 0 && (!action_msgs || !order_id_counter)))
+    return VITMARL_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(combined) | reinterpret_cast<uintptr_t>(message_data) | reinterpret_cast<uintptr_t>(cancel_msgs) |
+       reinterpret_cast<uintptr_t>(action_msgs)) & 15) return VITMARL_EINVAL;
+  if (Mc + Ma + n_data == 0) return VITMARL_OK;
+  StepMsgParams p{E, n_total, n_data, Mc, Ma, message_data, start_index, step_counter, end_time_s, cancel_msgs, action_msgs, perm,
+                  order_id_counter, combined, new_order_id_counter};
+  const size_t total = (size_t)E * (Mc + Ma + n_data);
+  const int grid = (int)((total + 255) / 256 < (size_t)num_sms() * 8 ? (total + 255) / 256 : (size_t)num_sms() * 8);
+  step_msgs_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_cuda(cudaGetLastError());
+}

@@ -98,7 +98,7 @@ static Ws layout(const Dims& d, bool save) {
 }
 
 // ---- optional per-launch timing (CUDA events on the launch stream; used by bench.py) ---------------
-enum { CAT_GEMM = 0, CAT_FUSED_MLP = 1, CAT_FUSED_ATTN = 2, CAT_ATTENTION = 3, CAT_LAYERNORM = 4, CAT_OTHER = 5, CAT_COUNT = 8 };
+enum { CAT_GEMM = 0, CAT_FUSED_MLP = 1, CAT_FUSED_ATTN = 2, CAT_ATTENTION = 3, CAT_LAYERNORM = 4, CAT_OTHER = 5, CAT_GEMM_DW = 6, CAT_GEMM_DX = 7, CAT_COUNT = 8 };
 struct OpTiming {
   bool enabled = false;
   static constexpr int kMax = 16384;
@@ -247,42 +247,42 @@ static int vit_backward(cudaStream_t st, const Dims& d, const void* const* prm, 
   // dW[out,in] += dY^T . Xin   (both operands MN-major over the token dimension; split-K red.add)
   auto dW = [&](float* dw, const bf16* dY, int n_out, const bf16* Xin, int n_in) {
     GemmDesc g = gd(n_out, n_in, M, dY, n_out, true, Xin, n_in, true, dw, n_in, EPI_ATOMIC_F32);
-    return timed_gemm(st, g);
+    return timed(st, CAT_GEMM_DW, 2.0 * g.M * g.N * g.K, [&] { return launch_gemm(st, g); });
   };
   // dXin[M,n_in] = dY[M,n_out] . W[n_out,n_in]   (W read as the MN-major B operand)
   auto dXg = [&](bf16* dXin, const bf16* dY, int n_out, const bf16* W, int n_in, int epi, const bf16* aux) {
     GemmDesc g = gd(M, n_in, n_out, dY, n_out, false, W, n_in, true, dXin, n_in, epi);
     g.residual = aux; g.ldr = n_in;
-    return timed_gemm(st, g);
+    return timed(st, CAT_GEMM_DX, 2.0 * g.M * g.N * g.K, [&] { return launch_gemm(st, g); });
   };
 
-  VM_TRY(launch_final_ln_pool_bwd(st, X(d.L), PF(p_lnf_g(d)), stf, dy, dA, G(p_lnf_g(d)), G(p_lnf_g(d) + 1), d.B, d.T, D));
+  VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_final_ln_pool_bwd(st, X(d.L), PF(p_lnf_g(d)), stf, dy, dA, G(p_lnf_g(d)), G(p_lnf_g(d) + 1), d.B, d.T, D); }));
   for (int l = d.L - 1; l >= 0; --l) {
     // ---- MLP branch: x_{l+1} = xm + fc2(gelu(fc1(ln2(xm))))
-    VM_TRY(launch_colsum(st, dA, G(p_layer(l, L_FC2_B)), M, D));
+    VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_colsum(st, dA, G(p_layer(l, L_FC2_B)), M, D); }));
     VM_TRY(dW(G(p_layer(l, L_FC2_W)), dA, D, HACT(l), H));
     VM_TRY(dXg(dH, dA, D, PB(p_layer(l, L_FC2_W)), H, EPI_MUL_GELU_GRAD, HPRE(l)));
-    VM_TRY(launch_colsum(st, dH, G(p_layer(l, L_FC1_B)), M, H));
+    VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_colsum(st, dH, G(p_layer(l, L_FC1_B)), M, H); }));
     VM_TRY(dW(G(p_layer(l, L_FC1_W)), dH, H, LN2(l), D));
     VM_TRY(dXg(dC, dH, H, PB(p_layer(l, L_FC1_W)), D, EPI_STORE_BF16, nullptr));
-    VM_TRY(launch_layernorm_bwd(st, XM(l), PF(p_layer(l, L_LN2_G)), ST2(l), dC, dA, dB, G(p_layer(l, L_LN2_G)), G(p_layer(l, L_LN2_B)), M, D));
+    VM_TRY(timed(st, CAT_LAYERNORM, 0, [&] { return launch_layernorm_bwd(st, XM(l), PF(p_layer(l, L_LN2_G)), ST2(l), dC, dA, dB, G(p_layer(l, L_LN2_G)), G(p_layer(l, L_LN2_B)), M, D); }));
     // ---- attention branch: xm = x_l + out(attn(qkv(ln1(x_l))))
-    VM_TRY(launch_colsum(st, dB, G(p_layer(l, L_OUT_B)), M, D));
+    VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_colsum(st, dB, G(p_layer(l, L_OUT_B)), M, D); }));
     VM_TRY(dW(G(p_layer(l, L_OUT_W)), dB, D, ATT(l), D));
     VM_TRY(dXg(dC, dB, D, PB(p_layer(l, L_OUT_W)), D, EPI_STORE_BF16, nullptr));
-    VM_TRY(launch_attention_bwd(st, QKV(l), dC, dQKV, d.B, d.heads));
-    VM_TRY(launch_colsum(st, dQKV, G(p_layer(l, L_QKV_B)), M, 3 * D));
+    VM_TRY(timed(st, CAT_ATTENTION, 0, [&] { return launch_attention_bwd(st, QKV(l), dC, dQKV, d.B, d.heads); }));
+    VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_colsum(st, dQKV, G(p_layer(l, L_QKV_B)), M, 3 * D); }));
     VM_TRY(dW(G(p_layer(l, L_QKV_W)), dQKV, 3 * D, LN1(l), D));
     VM_TRY(dXg(dC, dQKV, 3 * D, PB(p_layer(l, L_QKV_W)), D, EPI_STORE_BF16, nullptr));
-    VM_TRY(launch_layernorm_bwd(st, X(l), PF(p_layer(l, L_LN1_G)), ST1(l), dC, dB, dA, G(p_layer(l, L_LN1_G)), G(p_layer(l, L_LN1_B)), M, D));
+    VM_TRY(timed(st, CAT_LAYERNORM, 0, [&] { return launch_layernorm_bwd(st, X(l), PF(p_layer(l, L_LN1_G)), ST1(l), dC, dB, dA, G(p_layer(l, L_LN1_G)), G(p_layer(l, L_LN1_B)), M, D); }));
   }
   // ---- patch embedding
-  VM_TRY(launch_colsum(st, dA, G(P_POS), d.B, d.T * D));     // dpos[t,:] = sum over images
-  VM_TRY(launch_colsum(st, dA, G(P_PE_B), M, D));
+  VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_colsum(st, dA, G(P_POS), d.B, d.T * D); }));     // dpos[t,:] = sum over images
+  VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_colsum(st, dA, G(P_PE_B), M, D); }));
   VM_TRY(dW(G(P_PE_W), dA, D, patches, d.Kp));
   if (dx) {
     VM_TRY(dXg(patches, dA, D, PB(P_PE_W), d.Kp, EPI_STORE_BF16, nullptr));   // reuse the patches buffer for d(patches)
-    VM_TRY(launch_unpatchify(st, patches, dx, d.B, d.H, d.W, d.C, d.P));
+    VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_unpatchify(st, patches, dx, d.B, d.H, d.W, d.C, d.P); }));
   }
   return VITMARL_OK;
 }
@@ -347,7 +347,7 @@ extern "C" int vitmarl_vit_gemm_timing_enable(int enable) {
 }
 
 // Per-category totals: ms8 / n8 are arrays of 8 (0 gemm, 1 fused mlp, 2 fused attention block, 3 attention,
-// 4 layernorm, 5 other).  Synchronises on the last logged launch.
+// 4 layernorm, 5 other, 6 dW gemm, 7 dX gemm).  Synchronises on the last logged launch.
 extern "C" int vitmarl_vit_timing_read_categories(double* ms8, long long* n8) {
   OpTiming& t = g_timing;
   for (int i = 0; i < CAT_COUNT; ++i) { if (ms8) ms8[i] = 0.0; if (n8) n8[i] = 0; }
@@ -369,8 +369,8 @@ extern "C" int vitmarl_vit_gemm_timing_read(double* total_ms, long long* launche
   long long n8[CAT_COUNT];
   int rc = vitmarl_vit_timing_read_categories(ms8, n8);
   if (rc) return rc;
-  if (total_ms) *total_ms = ms8[CAT_GEMM] + ms8[CAT_FUSED_MLP] + ms8[CAT_FUSED_ATTN];
-  if (launches) *launches = n8[CAT_GEMM] + n8[CAT_FUSED_MLP] + n8[CAT_FUSED_ATTN];
+  if (total_ms) *total_ms = ms8[CAT_GEMM] + ms8[CAT_FUSED_MLP] + ms8[CAT_FUSED_ATTN] + ms8[CAT_GEMM_DW] + ms8[CAT_GEMM_DX];
+  if (launches) *launches = n8[CAT_GEMM] + n8[CAT_FUSED_MLP] + n8[CAT_FUSED_ATTN] + n8[CAT_GEMM_DW] + n8[CAT_GEMM_DX];
   if (flops) *flops = g_timing.flops;
   return VITMARL_OK;
 }

@@ -13,7 +13,7 @@ from . import _capi
 from .config import World_EnvironmentConfig
 from .jaxob import _chk, _ptr, _stream, get_best_bid_and_ask_inclQuants
 
-__all__ = ["BookState", "StepOutput", "reset", "step"]
+__all__ = ["BookState", "StepOutput", "reset", "step", "build_step_msgs"]
 
 
 @dataclasses.dataclass
@@ -75,3 +75,23 @@ def step(cfg: World_EnvironmentConfig, state: BookState, msgs: torch.Tensor, *, 
                                       int(cfg.cancel_mode), int(cfg.init_id))
     _capi.check(rc)
     return BookState(a_out, b_out, t_out, ba, bb, mid), StepOutput(norm, raw, img)
+
+
+def build_step_msgs(message_data: torch.Tensor, start_index: torch.Tensor, step_counter: torch.Tensor, n_data: int,
+                    cancel_msgs: torch.Tensor, action_msgs: torch.Tensor, order_id_counter: torch.Tensor,
+                    perm: Optional[torch.Tensor] = None, end_time_s: Optional[torch.Tensor] = None):
+    """Message assembly of ``MARLEnv.step_env`` (``marl_env.py:272-344``, ``base_env.py:341-371``) for all envs:
+    -> (combined int32 [E, Mc+Ma+n_data, 8], new_order_id_counter int32 [E]).  ``perm`` [E,Ma] are the indices of the
+    caller's ``jax.random.permutation`` (None = no shuffle); ``end_time_s`` only for fixed_time episodes."""
+    md = message_data.to(torch.int32).contiguous()
+    E = start_index.shape[0]
+    cm, am = _chk(cancel_msgs, "cancel_msgs", 8), _chk(action_msgs, "action_msgs", 8)
+    Mc, Ma = cm.shape[1], am.shape[1]
+    i32 = lambda t: None if t is None else t.to(torch.int32).contiguous()
+    si, sc, oc, pm, et = i32(start_index), i32(step_counter), i32(order_id_counter), i32(perm), i32(end_time_s)
+    out = torch.empty((E, Mc + Ma + n_data, 8), dtype=torch.int32, device=md.device)
+    newc = torch.empty((E,), dtype=torch.int32, device=md.device)
+    rc = _capi.lib().vitmarl_build_step_msgs(_stream(), E, md.shape[0], n_data, Mc, Ma, _ptr(md), _ptr(si), _ptr(sc), _ptr(et),
+                                             _ptr(cm), _ptr(am), _ptr(pm), _ptr(oc), _ptr(out), _ptr(newc))
+    _capi.check(rc)
+    return out, newc

@@ -23,7 +23,7 @@ from .config import JAXLOB_Configuration
 
 __all__ = ["init_orderside", "init_msgs_from_l2", "scan_through_entire_array",
            "scan_through_entire_array_save_bidask", "get_best_bid_and_ask_inclQuants",
-           "get_L2_state", "get_vision_L2_state"]
+           "get_L2_state", "get_vision_L2_state", "getCancelMsgs", "get_agent_trades"]
 
 
 def _stream() -> int:
@@ -147,3 +147,22 @@ def get_vision_L2_state(asks, bids, n_levels: int, cfg: JAXLOB_Configuration) ->
     _capi.check(_capi.lib().vitmarl_lob_render(_stream(), E, N, n_levels, 1, _ptr(asks), _ptr(bids), None,
                                                _ptr(raw), None, None, None, _capi.IMG_NONE, 0, 0))
     return raw
+
+
+def getCancelMsgs(bookside, agentID: int, size: int, side: int, cancel_time: torch.Tensor) -> torch.Tensor:
+    """JOBA:756-782 batched: bookside [E,N,6], cancel_time int32 [E,2] (time_s, time_ns) -> int32 [E,size,8]."""
+    book = _chk(bookside, "bookside", 6)
+    E, N, _ = book.shape
+    ct = cancel_time.to(torch.int32).contiguous()
+    out = torch.empty((E, size, 8), dtype=torch.int32, device=book.device)
+    _capi.check(_capi.lib().vitmarl_get_cancel_msgs(_stream(), E, N, size, _ptr(book), int(agentID), int(side), _ptr(ct), _ptr(out)))
+    return out
+
+
+def get_agent_trades(trades, agent_id: int) -> torch.Tensor:
+    """JOBA:824-831 batched: trades [E,T,8] -> same shape, rows not involving agent_id (or not executed) zeroed."""
+    tr = _chk(trades, "trades", 8)
+    E, T, _ = tr.shape
+    out = torch.empty_like(tr)
+    _capi.check(_capi.lib().vitmarl_get_agent_trades(_stream(), E, T, _ptr(tr), int(agent_id), _ptr(out)))
+    return out
