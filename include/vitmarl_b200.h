@@ -153,6 +153,10 @@ int vitmarl_gemm_bf16(void* stream, int M, int N, int K,
                       void* C, int ldc, int epi, const float* bias, const void* residual, int ldr,
                       const float* pos, int pos_period, float out_scale);
 
+/* Select the 2-CTA (tcgen05 cta_group::2, 256-row tiles per CTA pair) GEMM where it applies (1, default) or the
+ * 1-CTA kernel only (0). */
+int vitmarl_gemm_set_2cta(int enable);
+
 /* Shape of the encoder (docs/VIT_SPEC.md): pre-LN ViT, learned position embedding, no class
  * token, final LayerNorm then mean pool -> [B, dim].  Requires (H/P)*(W/P) == 64 tokens and
  * head dim 64 (ViT-Tiny/8 @ 64x64: dim 192, heads 3; ViT-S/16 @ 128x128: dim 384, heads 6). */

@@ -42,6 +42,7 @@ SIGNATURES = {
     "vitmarl_lob_best_bid_ask": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "vitmarl_lob_render": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I]),
     "vitmarl_gemm_bf16": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, ctypes.c_float]),
+    "vitmarl_gemm_set_2cta": (_I, [_I]),
     "vitmarl_vit_num_params": (_I, [_P]),
     "vitmarl_vit_param_elems": (ctypes.c_longlong, [_P, _I, _P]),
     "vitmarl_vit_workspace_bytes": (_SZ, [_P, _I]),

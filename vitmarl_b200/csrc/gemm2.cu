@@ -1,0 +1,220 @@
+// 2-CTA variant of the tcgen05 GEMM: a CTA PAIR (thread-block cluster of 2, one TPC) computes a 256 x BN tile with
+// `tcgen05.mma.cta_group::2` (M = 256 per instruction).  Each CTA stages its own 128 rows of A and HALF of the B tile
+// (BN/2 rows), so every weight byte is fetched once per 256 output rows and the per-instruction issue cost is amortised
+// over twice the work of the 1-CTA kernel in gemm.cu.  K-major operands only (activations x weights[out,in]).
+//
+// Protocol (leader = cluster rank 0):
+//   * both CTAs: TMA producer loads with `.cta_group::2`, completing transaction bytes on the LEADER's full barrier;
+//   * leader only: MMA issuer waits the full barrier, issues the MMAs, `tcgen05.commit...multicast::cluster` arrives on
+//     the empty barrier of BOTH CTAs (stage free) and on both accumulator-full barriers;
+//   * both CTAs: epilogue warps drain their own TMEM (rows of their CTA) and arrive on the LEADER's accumulator-empty
+//     barrier (count = 2 x epilogue warps).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tc_common.cuh"
+#include "vit_kernels.h"
+#include "gemm_epilogue.cuh"
+#include "../../include/vitmarl_b200.h"
+
+namespace vitmarl {
+
+namespace g2 {
+constexpr int BM = 128;            // rows per CTA (256 per pair)
+constexpr int BK = 64;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+}  // namespace g2
+
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int kStages = 6;
+  static constexpr int kABytes = g2::BM * g2::BK * 2;          // 16 KB
+  static constexpr int kBBytes = (BN / 2) * g2::BK * 2;        // this CTA's half of the B tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = BN * 2 <= 128 ? 128 : (BN * 2 <= 256 ? 256 : 512);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst_smem, const CUtensorMap* m, int c0, int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst_smem),
+      "l"(m), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using namespace g2;
+  using Cfg = Gemm2Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int num_clusters = gridDim.x >> 1, cluster = blockIdx.x >> 1;
+  const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM), tiles_n = p.N / BN;
+  const int KB = (p.K + BK - 1) / BK;
+  const int num_work = tiles_m * tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kEpiWarps); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(Cfg::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                   // barriers of both CTAs initialised before any remote signal
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs) =================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int w = cluster; w < num_work; w += num_clusters) {
+        const int tn = w % tiles_n, tm = w / tiles_n;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * Cfg::kStageBytes);      // bytes of BOTH CTAs land on the leader's barrier
+          const uint32_t sa = smem_base + s * Cfg::kStageBytes, sb = sa + Cfg::kABytes;
+          const uint32_t lbar = full_bar(s) & kPeerMask;
+          tma_load_2d_2sm(sa, &tmA, kb * BK, tm * 2 * BM + (int)rank * BM, lbar);
+          tma_load_2d_2sm(sb, &tmB, kb * BK, tn * BN + (int)rank * (BN / 2), lbar);
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, false, false);
+      int s = 0; uint32_t ph = 0;
+      int it = 0;
+      for (int w = cluster; w < num_work; w += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * Cfg::kStageBytes, sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_2sm(d_tmem, umma_desc_sw128(sa + k * 32, 16, 1024), umma_desc_sw128(sb + k * 32, 16, 1024), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(empty_bar(s));
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+        }
+        umma_commit_2sm(tfull_bar(acc));
+      }
+    }
+  } else {
+    // ================= epilogue (both CTAs; warps 2..9) =================
+    const int quad = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
+    int it = 0;
+    for (int w = cluster; w < num_work; w += num_clusters, ++it) {
+      const int tn = w % tiles_n, tm = w / tiles_n;
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(tfull_bar(acc), acc_ph);
+      tc_fence_after();
+      const int row = tm * 2 * BM + (int)rank * BM + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = chalf * kColsPerWarp; c < (chalf + 1) * kColsPerWarp; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c, r);
+        tmem_ld_wait();
+        gemm_epilogue_chunk(p, r, row, row_ok, tn * BN + c);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_bar(acc) & kPeerMask);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                   // neither CTA exits while the other may still signal it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+static bool g_use_2cta = true;
+void gemm_set_2cta(bool on) { g_use_2cta = on; }
+
+bool gemm2_supported(const GemmDesc& g) {
+  return g_use_2cta && !g.a_mn_major && !g.b_mn_major && g.epi != EPI_ATOMIC_F32 && g.M >= 512 && g.N % 192 == 0;
+}
+
+int launch_gemm2(cudaStream_t stream, const GemmDesc& g) {
+  using namespace g2;
+  constexpr int BN = 192;
+  using Cfg = Gemm2Cfg<BN>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_tmap_2d_bf16(&tmA, g.A, g.M, g.K, (uint64_t)g.lda * 2, BM, BK))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmB, g.B, g.N, g.K, (uint64_t)g.ldb * 2, BN / 2, BK))) return rc;
+  GemmParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K; p.kb_per_split = 0; p.splits = 1;
+  p.epi = g.epi; p.C = g.C; p.C2 = g.C2; p.ldc = g.ldc; p.bias = g.bias; p.residual = g.residual; p.ldr = g.ldr;
+  p.pos = g.pos; p.pos_period = g.pos_period > 0 ? g.pos_period : 1; p.out_scale = g.out_scale;
+  auto kern = gemm2_kernel<BN>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  if (err != cudaSuccess) return check_cuda(err);
+  const int work = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
+  const int clusters = min(work, num_sms() / 2);
+  kern<<<2 * clusters, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  return check_cuda(cudaGetLastError());
+}
+
+}  // namespace vitmarl

@@ -388,3 +388,9 @@ extern "C" int vitmarl_debug_fused_mlp_timeline(long long* device_buf) {
   fused_attn_set_debug(device_buf ? device_buf + 256 : nullptr);
   return VITMARL_OK;
 }
+
+// Use the 2-CTA (cta_group::2) GEMM where it applies (1, default) or only the 1-CTA kernel (0).
+extern "C" int vitmarl_gemm_set_2cta(int enable) {
+  gemm_set_2cta(enable != 0);
+  return VITMARL_OK;
+}

@@ -31,6 +31,10 @@ struct GemmDesc {
 
 int num_sms();
 int launch_gemm(cudaStream_t stream, const GemmDesc& g);
+// 2-CTA (cta_group::2, M = 256 per CTA pair) variant for K-major operands; used by launch_gemm when supported
+bool gemm2_supported(const GemmDesc& g);
+int launch_gemm2(cudaStream_t stream, const GemmDesc& g);
+void gemm_set_2cta(bool on);
 
 // x[B,H,W,C] bf16 -> patches [B*T, P*P*C] bf16, token t = py*(W/P)+px, feature (ph, pw, c)
 int launch_patchify(cudaStream_t s, const __nv_bfloat16* x, __nv_bfloat16* out, int B, int H, int W, int C, int P);
