@@ -42,9 +42,10 @@ constexpr int OFF_W1 = OFF_H + NB * H_BYTES;
 constexpr int OFF_W2 = OFF_W1 + NS1 * S1_BYTES;
 constexpr int OFF_BAR = OFF_W2 + NS2 * S2_BYTES;
 constexpr int OFF_MISC = OFF_BAR + 512;                           // LN partials [128][2] float2, gamma/beta, biases
-constexpr int MISC_BYTES = 128 * 2 * 8 + (2 * D + HID + D) * 4;
+constexpr int MISC_BYTES = 128 * 4 * 8 + (2 * D + HID + D) * 4;
 constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;
-constexpr int THREADS = 96 + 256;                                 // 3 control warps + 8 compute warps
+constexpr int NCW = 16;                                           // compute warps: 4 per TMEM lane quadrant, each owns a quarter of the columns
+constexpr int THREADS = 96 + 32 * NCW;                            // 3 control warps + 16 compute warps
 constexpr int TMEM_COLS = 512;                                    // acc1[2] @ 0,128 ; acc2 @ 256 (192 cols)
 constexpr int ACC2_COL = 256;
 // barrier slots (8 bytes each)
@@ -75,8 +76,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
   auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
-  float2* ln_part = reinterpret_cast<float2*>(sptr + OFF_MISC);                    // [128][2]
-  float* s_gamma = reinterpret_cast<float*>(sptr + OFF_MISC + 128 * 2 * 8);
+  float2* ln_part = reinterpret_cast<float2*>(sptr + OFF_MISC);                    // [128][4]
+  float* s_gamma = reinterpret_cast<float*>(sptr + OFF_MISC + 128 * 4 * 8);
   float* s_beta = s_gamma + D;
   float* s_b1 = s_beta + D;
   float* s_b2 = s_b1 + HID;
@@ -86,11 +87,11 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmOut);
-    mbar_init(bar(B_XFULL), 1); mbar_init(bar(B_XEMPTY), 1); mbar_init(bar(B_XNREADY), 8);
-    mbar_init(bar(B_ACC2FULL), 1); mbar_init(bar(B_ACC2EMPTY), 8); mbar_init(bar(B_RESFULL), 1); mbar_init(bar(B_RESREAD), 8);
+    mbar_init(bar(B_XFULL), 1); mbar_init(bar(B_XEMPTY), 1); mbar_init(bar(B_XNREADY), NCW);
+    mbar_init(bar(B_ACC2FULL), 1); mbar_init(bar(B_ACC2EMPTY), NCW); mbar_init(bar(B_RESFULL), 1); mbar_init(bar(B_RESREAD), NCW);
     for (int i = 0; i < NB; ++i) {
-      mbar_init(bar(B_ACC1FULL + i), 1); mbar_init(bar(B_ACC1EMPTY + i), 8);
-      mbar_init(bar(B_HREADY + i), 8); mbar_init(bar(B_HEMPTY + i), 1);
+      mbar_init(bar(B_ACC1FULL + i), 1); mbar_init(bar(B_ACC1EMPTY + i), NCW);
+      mbar_init(bar(B_HREADY + i), NCW); mbar_init(bar(B_HEMPTY + i), 1);
     }
     for (int i = 0; i < NS1; ++i) { mbar_init(bar(B_W1FULL + i), 1); mbar_init(bar(B_W1EMPTY + i), 1); }
     for (int i = 0; i < NS2; ++i) { mbar_init(bar(B_W2FULL + i), 1); mbar_init(bar(B_W2EMPTY + i), 1); }
@@ -204,10 +205,10 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
     }
   } else {
-    // =============================== compute warps (3..10) ===============================
+    // =============================== compute warps (3..18) ===============================
     const int cw = warp - 3;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int hf = cw >> 2;                    // column half
+    const int cq = cw >> 2;                    // column quarter (0..3)
     const int row = quad * 32 + lane;          // row within the tile
     const uint32_t tm_lane = (uint32_t)(quad * 32) << 16;
     const uint32_t sw = (uint32_t)(row & 7);
@@ -216,28 +217,29 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const bool stamp = (warp == 3 && lane == 0);
       if (stamp) { bulk_wait_read0(); FMLP_STAMP(0); }      // previous tile's TMA store has finished reading the staging smem
-      // ---- LayerNorm in place: thread (row, hf) owns columns [hf*96, hf*96+96) = 12 chunks of 8 bf16 ----
+      // ---- LayerNorm in place: thread (row, cq) owns columns [cq*48, cq*48+48) = 6 chunks of 8 bf16 ----
       mbar_wait(bar(B_XFULL), it & 1);
       if (stamp) FMLP_STAMP(1);
-      uint4 v[12];
+      uint4 v[6];
       float s = 0.f, q = 0.f;
 #pragma unroll
-      for (int i = 0; i < 12; ++i) {
-        const int col = hf * 96 + i * 8, kb = col >> 6, ch = (col & 63) >> 3;
+      for (int i = 0; i < 6; ++i) {
+        const int col = cq * 48 + i * 8, kb = col >> 6, ch = (col & 63) >> 3;
         v[i] = *reinterpret_cast<const uint4*>(sptr + OFF_XN + kb * TM * 128 + row * 128 + ((ch ^ sw) << 4));
         const uint32_t* w = &v[i].x;
 #pragma unroll
         for (int j = 0; j < 4; ++j) { float a = bf16_lo(w[j]), b = bf16_hi(w[j]); s += a + b; q += a * a + b * b; }
       }
-      ln_part[row * 2 + hf] = make_float2(s, q);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float2 o = ln_part[row * 2 + (hf ^ 1)];
-      const float mean = (s + o.x) * (1.0f / D);
-      const float var = fmaxf((q + o.y) * (1.0f / D) - mean * mean, 0.f);
+      ln_part[row * 4 + cq] = make_float2(s, q);
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+#pragma unroll
+      for (int k = 1; k < 4; ++k) { const float2 o = ln_part[row * 4 + ((cq + k) & 3)]; s += o.x; q += o.y; }
+      const float mean = s * (1.0f / D);
+      const float var = fmaxf(q * (1.0f / D) - mean * mean, 0.f);
       const float rstd = rsqrtf(var + p.eps);
 #pragma unroll
-      for (int i = 0; i < 12; ++i) {
-        const int col = hf * 96 + i * 8, kb = col >> 6, ch = (col & 63) >> 3;
+      for (int i = 0; i < 6; ++i) {
+        const int col = cq * 48 + i * 8, kb = col >> 6, ch = (col & 63) >> 3;
         uint32_t* w = &v[i].x;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -251,40 +253,36 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       fence_proxy_async_smem();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_XNREADY));
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // ln_part reuse safety for the next tile
+      asm volatile("bar.sync 1, 512;" ::: "memory");   // ln_part reuse safety for the next tile
       if (stamp) FMLP_STAMP(2);
 
-      // ---- hidden chunks: GELU epilogue into the FC2 A operand (thread: row, 32 of the chunk's 64 columns) ----
+      // ---- hidden chunks: GELU epilogue into the FC2 A operand (thread: row, 32 of the chunk's 128 columns) ----
       for (int c = 0; c < NCHUNK; ++c, ++gc) {
         const uint32_t b = gc % NB, use = gc / NB;
         mbar_wait(bar(B_ACC1FULL + b), use & 1);
         tc_fence_after();
         if (stamp) FMLP_STAMP(10 + 4 * c);
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32(tmem_base + tm_lane + b * HC + hf * 64, r0);
-        tmem_ld_32x32(tmem_base + tm_lane + b * HC + hf * 64 + 32, r1);
+        uint32_t r0[32];
+        tmem_ld_32x32(tmem_base + tm_lane + b * HC + cq * 32, r0);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_ACC1EMPTY + b));          // accumulator drained
-        const float* bias = s_b1 + c * HC + hf * 64;
-        uint32_t pk[32];
+        const float* bias = s_b1 + c * HC + cq * 32;
+        uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 bv = *reinterpret_cast<const float4*>(bias + 4 * j);
-          const float4 bw = *reinterpret_cast<const float4*>(bias + 32 + 4 * j);
           pk[2 * j] = gelu_tanh_bf16x2(pack_bf16(__uint_as_float(r0[4 * j]) + bv.x, __uint_as_float(r0[4 * j + 1]) + bv.y));
           pk[2 * j + 1] = gelu_tanh_bf16x2(pack_bf16(__uint_as_float(r0[4 * j + 2]) + bv.z, __uint_as_float(r0[4 * j + 3]) + bv.w));
-          pk[16 + 2 * j] = gelu_tanh_bf16x2(pack_bf16(__uint_as_float(r1[4 * j]) + bw.x, __uint_as_float(r1[4 * j + 1]) + bw.y));
-          pk[16 + 2 * j + 1] = gelu_tanh_bf16x2(pack_bf16(__uint_as_float(r1[4 * j + 2]) + bw.z, __uint_as_float(r1[4 * j + 3]) + bw.w));
         }
         if (stamp) FMLP_STAMP(11 + 4 * c);
         mbar_wait(bar(B_HEMPTY + b), (use & 1) ^ 1);                // FC2 of the previous user has finished reading this H buffer
         if (stamp) FMLP_STAMP(12 + 4 * c);
-        uint8_t* hrow = sptr + OFF_H + b * H_BYTES + hf * TM * 128 + row * 128;    // K-block hf of the chunk
+        uint8_t* hrow = sptr + OFF_H + b * H_BYTES + (cq >> 1) * TM * 128 + row * 128;    // K-block (cq>>1), chunks (cq&1)*4 ..
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch)
-          *reinterpret_cast<uint4*>(hrow + ((ch ^ sw) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        for (int ch = 0; ch < 4; ++ch)
+          *reinterpret_cast<uint4*>(hrow + ((((cq & 1) * 4 + ch) ^ sw) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_HREADY + b));
@@ -295,23 +293,25 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       mbar_wait(bar(B_RESFULL), it & 1);
       tc_fence_after();
       if (stamp) FMLP_STAMP(60);
-#pragma unroll
-      for (int cc = 0; cc < 3; ++cc) {
-        const int col = hf * 96 + cc * 32;
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + tm_lane + ACC2_COL + col, r);
+      {
+        const int col0 = cq * 48;
+        uint32_t ra[32], rb[16];
+        tmem_ld_32x32(tmem_base + tm_lane + ACC2_COL + col0, ra);
+        tmem_ld_32x16(tmem_base + tm_lane + ACC2_COL + col0 + 32, rb);
         tmem_ld_wait();
-        const int kb = col >> 6, ch0 = (col & 63) >> 3;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t off = (uint32_t)(kb * TM * 128 + row * 128) + ((((uint32_t)(ch0 + j)) ^ sw) << 4);
+        for (int j = 0; j < 6; ++j) {
+          const int col = col0 + 8 * j, kb = col >> 6, ch = (col & 63) >> 3;
+          const uint32_t off = (uint32_t)(kb * TM * 128 + row * 128) + ((((uint32_t)ch) ^ sw) << 4);
           const uint4 xr = *reinterpret_cast<const uint4*>(sptr + OFF_XN + off);
           const uint32_t* xw = &xr.x;
           uint32_t ow[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int e = 8 * j + 2 * k;
-            ow[k] = pack_bf16(__uint_as_float(r[e]) + s_b2[col + e] + bf16_lo(xw[k]), __uint_as_float(r[e + 1]) + s_b2[col + e + 1] + bf16_hi(xw[k]));
+            const float a0 = __uint_as_float(e < 32 ? ra[e & 31] : rb[(e - 32) & 15]);
+            const float a1 = __uint_as_float(e + 1 < 32 ? ra[(e + 1) & 31] : rb[(e - 31) & 15]);
+            ow[k] = pack_bf16(a0 + s_b2[col0 + e] + bf16_lo(xw[k]), a1 + s_b2[col0 + e + 1] + bf16_hi(xw[k]));
           }
           *reinterpret_cast<uint4*>(sptr + OFF_H + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
@@ -320,7 +320,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_RESREAD));
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       if (stamp) {
         for (int kb = 0; kb < KB_X; ++kb) tma_store_2d(&tmOut, sbase + OFF_H + kb * TM * 128, kb * 64, tile * TM);
         bulk_commit();
