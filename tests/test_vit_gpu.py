@@ -54,7 +54,10 @@ def test_forward_matches_fp32_oracle(cfg, B):
     lib = _capi.lib()
     lib.vitmarl_vit_set_fused(0)
     y_unfused = enc.apply({"params": params}, x)
+    lib.vitmarl_vit_set_fused(2)             # legacy 1-CTA fused block kernels
+    y_legacy = enc.apply({"params": params}, x)
     lib.vitmarl_vit_set_fused(1)
+    assert _rel(y_legacy, ref) <= ACT_TOL, _rel(y_legacy, ref)
     assert torch.equal(y_unfused, y_train)    # saving activations must not change the result
     assert torch.equal(y, enc.apply({"params": params}, x))   # forward is bitwise deterministic
 

@@ -66,8 +66,9 @@ static size_t param_elems(const Dims& d, int idx, bool* is_matrix) {
 
 // ---- workspace layout -------------------------------------------------------------------------
 struct Ws {
-  size_t patches, x, xm, ln1, ln2, qkv, att, hpre, hact, st1, st2, stf, dA, dB, dC, dH, dQKV, total;
+  size_t patches, x, xm, ln1, ln2, qkv, att, hpre, hact, st1, st2, stf, dA, dB, dC, dH, dQKV, fold, total;
   size_t sz_md, sz_mh, sz_mq, sz_st;   // per-layer strides (bytes)
+  size_t sz_fold, f_w1, f_b1, f_w2;    // inference: folded parameters per layer (vit_fold.cu), offsets within a layer's slot
 };
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 static Ws layout(const Dims& d, bool save) {
@@ -93,6 +94,13 @@ static Ws layout(const Dims& d, bool save) {
     w.dA = take(w.sz_md); w.dB = take(w.sz_md); w.dC = take(w.sz_md);
     w.dH = take(w.sz_mh); w.dQKV = take(w.sz_mq);
   }
+  if (!save) {
+    size_t o = 0;
+    auto slot = [&](size_t bytes) { size_t r = o; o += al(bytes); return r; };
+    w.f_w1 = slot((size_t)d.mlp * d.D * 2); w.f_b1 = slot((size_t)d.mlp * 2); w.f_w2 = slot((size_t)d.D * d.mlp * 2);
+    w.sz_fold = o;
+    w.fold = take(w.sz_fold * d.L);
+  }
   w.total = off;
   return w;
 }
@@ -109,7 +117,7 @@ struct OpTiming {
   double flops = 0.0;     // algorithmic FLOPs of the tensor-core launches (categories 0-2)
 };
 static OpTiming g_timing;
-static bool g_use_fused = true;   // fused block kernels on the inference path (vitmarl_vit_set_fused)
+static int g_fused_mode = 1;      // inference path: 0 unfused kernel sequence, 1 fused block kernels (CTA-pair MLP), 2 legacy 1-CTA fused kernels
 
 template <typename F>
 static int timed(cudaStream_t st, int cat, double flops, F&& launch) {
@@ -160,6 +168,18 @@ static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, c
   auto ST1 = [&](int l) { return save ? reinterpret_cast<float*>(ws + w.st1 + (size_t)l * w.sz_st) : nullptr; };
   auto ST2 = [&](int l) { return save ? reinterpret_cast<float*>(ws + w.st2 + (size_t)l * w.sz_st) : nullptr; };
 
+  // inference: fold LayerNorm scale/shift (and the GELU 1/2) into the projections that follow, all layers in one launch
+  const bool fuse_mlp2 = !save && g_fused_mode == 1 && fused_mlp2_supported(D, d.mlp) && d.L * 2 <= 48;
+  auto FW = [&](int l, size_t o) { return reinterpret_cast<bf16*>(ws + w.fold + (size_t)l * w.sz_fold + o); };
+  if (fuse_mlp2) {
+    FoldJobs jobs{};
+    for (int l = 0; l < d.L; ++l) {
+      jobs.job[jobs.n++] = FoldJob{PB(p_layer(l, L_FC1_W)), PF(p_layer(l, L_FC1_B)), PF(p_layer(l, L_LN2_G)), PF(p_layer(l, L_LN2_B)),
+                                   FW(l, w.f_w1), FW(l, w.f_b1), d.mlp, D, 1, 1.0f};
+      jobs.job[jobs.n++] = FoldJob{PB(p_layer(l, L_FC2_W)), nullptr, nullptr, nullptr, FW(l, w.f_w2), nullptr, D, d.mlp, 0, 0.5f};
+    }
+    VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_fold_params(st, jobs); }));
+  }
   // patch embedding: tokens = patches . Wpe^T + b + pos
   VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_patchify(st, x, patches, d.B, d.H, d.W, d.C, d.P); }));
   {
@@ -168,7 +188,7 @@ static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, c
     VM_TRY(timed_gemm(st, g));
   }
   for (int l = 0; l < d.L; ++l) {
-    const bool fuse_attn = !save && g_use_fused && fused_attn_supported(D, d.heads, d.T);
+    const bool fuse_attn = !save && g_fused_mode && fused_attn_supported(D, d.heads, d.T);
     if (fuse_attn) {
       // inference: LN1 + QKV + softmax(QK^T)V + out-projection + residual in one kernel
       VM_TRY(timed(st, CAT_FUSED_ATTN, 8.0 * M * D * D + 4.0 * M * d.T * D, [&] {
@@ -189,8 +209,15 @@ static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, c
       VM_TRY(timed_gemm(st, g));
     }
     }
-    if (!save && g_use_fused && fused_mlp_supported(D, d.mlp)) {
-      // inference: LN2 + FC1 + GELU + FC2 + residual in one kernel (hidden activations stay on chip)
+    if (fuse_mlp2) {
+      // inference: LN2 + FC1 + GELU + FC2 + residual in one CTA-pair kernel on the folded parameters
+      VM_TRY(timed(st, CAT_FUSED_MLP, 4.0 * M * D * d.mlp, [&] {
+        return launch_fused_mlp2(st, XM(l), X(l + 1), FW(l, w.f_w1), FW(l, w.f_b1), FW(l, w.f_w2), PF(p_layer(l, L_FC2_B)), M, D, d.mlp, d.eps);
+      }));
+      continue;
+    }
+    if (!save && g_fused_mode && fused_mlp_supported(D, d.mlp)) {
+      // legacy 1-CTA fused MLP block
       VM_TRY(timed(st, CAT_FUSED_MLP, 4.0 * M * D * d.mlp, [&] {
         return launch_fused_mlp(st, XM(l), X(l + 1), PF(p_layer(l, L_LN2_G)), PF(p_layer(l, L_LN2_B)), PB(p_layer(l, L_FC1_W)),
                                 PF(p_layer(l, L_FC1_B)), PB(p_layer(l, L_FC2_W)), PF(p_layer(l, L_FC2_B)), M, D, d.mlp, d.eps);
@@ -375,9 +402,9 @@ extern "C" int vitmarl_vit_gemm_timing_read(double* total_ms, long long* launche
   return VITMARL_OK;
 }
 
-// Select the fused block kernels (1, default) or the unfused v0 kernel sequence (0) for the inference forward.
-extern "C" int vitmarl_vit_set_fused(int enable) {
-  g_use_fused = enable != 0;
+// Inference forward: 1 (default) fused block kernels, 0 the unfused v0 kernel sequence, 2 the legacy 1-CTA fused kernels.
+extern "C" int vitmarl_vit_set_fused(int mode) {
+  g_fused_mode = mode < 0 ? 0 : (mode > 2 ? 1 : mode);
   return VITMARL_OK;
 }
 
@@ -385,6 +412,7 @@ extern "C" int vitmarl_vit_set_fused(int enable) {
 // [0,256) fused MLP, [256,512) fused attention block.
 extern "C" int vitmarl_debug_fused_mlp_timeline(long long* device_buf) {
   fused_mlp_set_debug(device_buf);
+  fused_mlp2_set_debug(device_buf);
   fused_attn_set_debug(device_buf ? device_buf + 256 : nullptr);
   return VITMARL_OK;
 }

@@ -71,6 +71,23 @@ int launch_fused_attn(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16
 bool fused_attn_supported(int D, int heads, int tokens);
 void fused_attn_set_debug(long long* buf);
 
+// CTA-pair (cta_group::2) fused MLP block on FOLDED parameters (vit_fold.cu): w1f = W1.diag(gamma), b1p = bf16(b1 + W1.beta),
+// w2h = W2/2.  out = x + fc2(gelu(fc1(LN(x))));  `out` may alias `x`
+int launch_fused_mlp2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16* out, const __nv_bfloat16* w1f, const __nv_bfloat16* b1p,
+                      const __nv_bfloat16* w2h, const float* b2, int M, int D, int hidden, float eps);
+bool fused_mlp2_supported(int D, int hidden);
+void fused_mlp2_set_debug(long long* buf);
+
+// parameter folding: Wf = scale * W . diag(gamma) (bf16 [N,K]), bias_out = bias + W . beta (fp32 or bf16 [N]); null = identity
+struct FoldJob {
+  const __nv_bfloat16* W; const float* bias; const float* gamma; const float* beta;
+  __nv_bfloat16* Wf; void* bias_out;
+  int N, K, bias_out_bf16;
+  float scale;
+};
+struct FoldJobs { FoldJob job[48]; int n; };
+int launch_fold_params(cudaStream_t s, const FoldJobs& jobs);
+
 // elementwise helpers
 int launch_gelu_bwd(cudaStream_t s, const __nv_bfloat16* pre, const __nv_bfloat16* dy, __nv_bfloat16* dx, size_t n);   // dx = dy * gelu'(pre)
 int launch_colsum(cudaStream_t s, const __nv_bfloat16* x, float* out, int M, int N);                                  // out[N] += sum_m x[m,n]
