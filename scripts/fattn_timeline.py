@@ -1,5 +1,7 @@
+"""clock64 timeline of the fused attention block kernel (CTA 0, its second tile) + per-layer kernel times."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes
 import torch
 from vitmarl_b200 import vit, _capi
 lib = _capi.lib()
@@ -12,10 +14,18 @@ for _ in range(2): enc.apply_packed(packed, x)
 lib.vitmarl_debug_fused_mlp_timeline(buf.data_ptr())
 enc.apply_packed(packed, x); torch.cuda.synchronize()
 lib.vitmarl_debug_fused_mlp_timeline(None)
-t = buf.cpu().tolist()[256:]; t0 = t[0]
+t = buf.cpu().tolist()[256:]
+t0 = min(v for v in t if v)
 r = lambda i: t[i] - t0 if t[i] else None
-print("compute: XFULL", r(1), "LN done", r(2), "| mma xnready", r(99), "QKV0 issued", r(100))
 for h in range(3):
-    b = 8 * h
-    print(f" h{h}: C: qkvfull {r(10+b)} epi_done {r(11+b)} sfull {r(12+b)} p_done {r(13+b)} ofull {r(14+b)} o_done {r(15+b)} | M: qkready {r(101+b)} S_issued {r(102+b)} nextQKV_issued {r(103+b)} pready {r(104+b)} PV_issued {r(105+b)}")
-print("proj start", r(130), "issued", r(131), "| C: pfull", r(60), "tile end", r(61))
+    b = 4 * h
+    print(f" h{h}: CV: qkvfull {r(30+2*h)} epi_done {r(31+2*h)} | SM: sfull {r(10+b)} p_done {r(11+b)} oc_done(CV) {r(13+b)} | MMA: S {r(100+b)} QKVnext {r(101+b)} PV {r(102+b)}")
+print(" LN(next) done", r(50), "| proj start", r(130), "issued", r(131), "| CV: projfull", r(60), "tile end", r(61))
+lib.vitmarl_vit_gemm_timing_enable(1)
+for _ in range(5): enc.apply_packed(packed, x)
+torch.cuda.synchronize()
+ms, n = (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
+lib.vitmarl_vit_timing_read_categories(ms, n)
+lib.vitmarl_vit_gemm_timing_enable(0)
+names = ["gemm", "fused_mlp", "fused_attn", "attention", "layernorm", "other", "dw", "dx"]
+print({nm: round(ms[i] / max(n[i], 1) * 1e3, 1) for i, nm in enumerate(names) if n[i]}, "us per launch")

@@ -84,21 +84,6 @@ struct FusedMlp2Params {
 #define FM2_WAIT(acc, call) do { if (p.dbg) { const long long t__ = clock64(); call; if (j == 1) acc += clock64() - t__; } else { call; } } while (0)
 #define FM2_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && j == 1 && (threadIdx.x & 31) == 0) p.dbg[(slot)] = clock64(); } while (0)
 
-__device__ __forceinline__ uint32_t bf16x2_fma(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t d;
-  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-}
-__device__ __forceinline__ uint32_t bf16x2_mul(uint32_t a, uint32_t b) {
-  uint32_t d;
-  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
-}
-__device__ __forceinline__ uint32_t bf16x2_add(uint32_t a, uint32_t b) {
-  uint32_t d;
-  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
-}
 // x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))) on a packed pair = 2 gelu_tanh(x); the 1/2 lives in the FC2 weights
 __device__ __forceinline__ uint32_t gelu2_bf16x2(uint32_t x) {
   const uint32_t C0 = 0x3F4C3F4Cu;   // bf16(0.7978845608) x2
@@ -110,30 +95,6 @@ __device__ __forceinline__ uint32_t gelu2_bf16x2(uint32_t x) {
   asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t) : "r"(u));
   return bf16x2_fma(x, t, x);
 }
-// mixed-precision accumulate: s += lo + hi, q += lo^2 + hi^2 for a packed bf16 pair (FHADD / FHFMA, no unpacking)
-__device__ __forceinline__ void stats_bf16x2(uint32_t w, float& s, float& q) {
-  asm("{\n\t.reg .b16 lo, hi;\n\t"
-      "mov.b32 {lo, hi}, %2;\n\t"
-      "add.f32.bf16 %0, lo, %0;\n\t"
-      "add.f32.bf16 %0, hi, %0;\n\t"
-      "fma.rn.f32.bf16 %1, lo, lo, %1;\n\t"
-      "fma.rn.f32.bf16 %1, hi, hi, %1;\n\t}"
-      : "+f"(s), "+f"(q)
-      : "r"(w));
-}
-// (x - mean) * rstd for a packed pair: fp32 FMAs with bf16 multiplicands (x, rstd_b), fp32 addend -mean * rstd_b
-__device__ __forceinline__ uint32_t norm_bf16x2(uint32_t w, uint32_t rstd_b, float nmr) {
-  float a, b;
-  asm("{\n\t.reg .b16 lo, hi, r;\n\t"
-      "mov.b32 {lo, hi}, %2;\n\t"
-      "mov.b32 {r, _}, %3;\n\t"
-      "fma.rn.f32.bf16 %0, lo, r, %4;\n\t"
-      "fma.rn.f32.bf16 %1, hi, r, %4;\n\t}"
-      : "=f"(a), "=f"(b)
-      : "r"(w), "r"(rstd_b), "f"(nmr));
-  return pack_bf16(a, b);
-}
-
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fmlp2::THREADS, 1)
 fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut, const FusedMlp2Params p) {
@@ -237,7 +198,7 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       auto fc1 = [&](int g) {
         const int j = g / NCHUNK, c = g % NCHUNK;
         const uint32_t b = g & 1;
-        if (c == 0) FM2_WAIT(w_xn, mbar_wait_cluster(bar(B_XNREADY), j & 1));   // LayerNorm of tile j done in both CTAs
+        if (c == 0) FM2_WAIT(w_xn, mbar_wait_guard(bar(B_XNREADY), j & 1));   // LayerNorm of tile j done in both CTAs
         tc_fence_after();
         FM2_STAMP(100 + 4 * c);
         FM2_WAIT(w_w1, mbar_wait_guard(bar(B_W1FULL + s1), ph1));
@@ -262,8 +223,8 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       auto fc2 = [&](int g) {
         const int j = g / NCHUNK, c = g % NCHUNK;
         const uint32_t b = g & 1;
-        if (c == 0) FM2_WAIT(w_a2, mbar_wait_cluster(bar(B_ACC2EMPTY), (j & 1) ^ 1));   // previous tile's final epilogue drained acc2
-        FM2_WAIT(w_h, mbar_wait_cluster(bar(B_HREADY + b), (g >> 1) & 1));
+        if (c == 0) FM2_WAIT(w_a2, mbar_wait_guard(bar(B_ACC2EMPTY), (j & 1) ^ 1));   // previous tile's final epilogue drained acc2
+        FM2_WAIT(w_h, mbar_wait_guard(bar(B_HREADY + b), (g >> 1) & 1));
         tc_fence_after();
         FM2_STAMP(102 + 4 * c);
         FM2_WAIT(w_w2, mbar_wait_guard(bar(B_W2FULL + s2), ph2));

@@ -86,6 +86,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand in tensor memory (TS form): A[m, k] at lane m, 32-bit column a_tmem + k/2 (bf16 pairs)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued MMAs of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -133,6 +142,29 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
       "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+// the same 32-bit word to 32 consecutive columns of the thread's lane (zero fill)
+__device__ __forceinline__ void tmem_st_32x32_fill(uint32_t taddr, uint32_t v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+      "r"(v)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16_fill(uint32_t taddr, uint32_t v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(v)
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -224,6 +256,9 @@ __device__ __forceinline__ void mbar_wait_guard(uint32_t bar, uint32_t parity) {
   }
 }
 
+// (Measured: letting ONE lane poll and parking the other 31 at __syncwarp() is ~1.7x SLOWER end to end than all 32 lanes
+// executing try_wait -- the divergent spin delays the warp's wake-up -- so waits are always executed by the whole warp.)
+
 // ---- small math -------------------------------------------------------------------------------
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
@@ -261,6 +296,46 @@ __device__ __forceinline__ uint32_t gelu_tanh_bf16x2(uint32_t x) {
   asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(y) : "r"(hx), "r"(t));
   return y;
 }
+// ---- packed bf16x2 / mixed-precision helpers (HFMA2.BF16, FHADD.BF16, FHFMA.BF16) ----
+__device__ __forceinline__ uint32_t bf16x2_fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t bf16x2_mul(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t bf16x2_add(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+// mixed-precision accumulate: s += lo + hi, q += lo^2 + hi^2 for a packed bf16 pair (FHADD / FHFMA, no unpacking)
+__device__ __forceinline__ void stats_bf16x2(uint32_t w, float& s, float& q) {
+  asm("{\n\t.reg .b16 lo, hi;\n\t"
+      "mov.b32 {lo, hi}, %2;\n\t"
+      "add.f32.bf16 %0, lo, %0;\n\t"
+      "add.f32.bf16 %0, hi, %0;\n\t"
+      "fma.rn.f32.bf16 %1, lo, lo, %1;\n\t"
+      "fma.rn.f32.bf16 %1, hi, hi, %1;\n\t}"
+      : "+f"(s), "+f"(q)
+      : "r"(w));
+}
+// (x - mean) * rstd for a packed pair: fp32 FMAs with bf16 multiplicands (x, rstd_b), fp32 addend -mean * rstd_b
+__device__ __forceinline__ uint32_t norm_bf16x2(uint32_t w, uint32_t rstd_b, float nmr) {
+  float a, b;
+  asm("{\n\t.reg .b16 lo, hi, r;\n\t"
+      "mov.b32 {lo, hi}, %2;\n\t"
+      "mov.b32 {r, _}, %3;\n\t"
+      "fma.rn.f32.bf16 %0, lo, r, %4;\n\t"
+      "fma.rn.f32.bf16 %1, hi, r, %4;\n\t}"
+      : "=f"(a), "=f"(b)
+      : "r"(w), "r"(rstd_b), "f"(nmr));
+  return pack_bf16(a, b);
+}
+
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 #endif  // __CUDACC__

@@ -68,7 +68,7 @@ static size_t param_elems(const Dims& d, int idx, bool* is_matrix) {
 struct Ws {
   size_t patches, x, xm, ln1, ln2, qkv, att, hpre, hact, st1, st2, stf, dA, dB, dC, dH, dQKV, fold, total;
   size_t sz_md, sz_mh, sz_mq, sz_st;   // per-layer strides (bytes)
-  size_t sz_fold, f_w1, f_b1, f_w2;    // inference: folded parameters per layer (vit_fold.cu), offsets within a layer's slot
+  size_t sz_fold, f_w1, f_b1, f_w2, f_wqkv, f_bq, f_bv, f_bo;   // inference: folded parameters per layer (vit_fold.cu), offsets within a layer's slot
 };
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 static Ws layout(const Dims& d, bool save) {
@@ -98,6 +98,7 @@ static Ws layout(const Dims& d, bool save) {
     size_t o = 0;
     auto slot = [&](size_t bytes) { size_t r = o; o += al(bytes); return r; };
     w.f_w1 = slot((size_t)d.mlp * d.D * 2); w.f_b1 = slot((size_t)d.mlp * 2); w.f_w2 = slot((size_t)d.D * d.mlp * 2);
+    w.f_wqkv = slot((size_t)3 * d.D * d.D * 2); w.f_bq = slot((size_t)d.D * 2); w.f_bv = slot((size_t)d.D * 4); w.f_bo = slot((size_t)d.D * 4);
     w.sz_fold = o;
     w.fold = take(w.sz_fold * d.L);
   }
@@ -168,17 +169,34 @@ static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, c
   auto ST1 = [&](int l) { return save ? reinterpret_cast<float*>(ws + w.st1 + (size_t)l * w.sz_st) : nullptr; };
   auto ST2 = [&](int l) { return save ? reinterpret_cast<float*>(ws + w.st2 + (size_t)l * w.sz_st) : nullptr; };
 
-  // inference: fold LayerNorm scale/shift (and the GELU 1/2) into the projections that follow, all layers in one launch
-  const bool fuse_mlp2 = !save && g_fused_mode == 1 && fused_mlp2_supported(D, d.mlp) && d.L * 2 <= 48;
+  // inference: fold LayerNorm scale/shift, the GELU 1/2, the softmax scale and the K / V biases into the projections
+  // (vit_fold.cu), all layers in two launches (the second one needs the folded V bias of the first)
+  const bool fuse_mlp2 = !save && g_fused_mode == 1 && fused_mlp2_supported(D, d.mlp) && d.L * 5 <= 64;
+  const bool fuse_attn2 = !save && g_fused_mode == 1 && fused_attn2_supported(D, d.heads, d.T) && d.L * 5 <= 64;
   auto FW = [&](int l, size_t o) { return reinterpret_cast<bf16*>(ws + w.fold + (size_t)l * w.sz_fold + o); };
-  if (fuse_mlp2) {
-    FoldJobs jobs{};
+  auto FF = [&](int l, size_t o) { return reinterpret_cast<float*>(ws + w.fold + (size_t)l * w.sz_fold + o); };
+  if (fuse_mlp2 || fuse_attn2) {
+    FoldJobs jobs{}, jobs2{};
     for (int l = 0; l < d.L; ++l) {
-      jobs.job[jobs.n++] = FoldJob{PB(p_layer(l, L_FC1_W)), PF(p_layer(l, L_FC1_B)), PF(p_layer(l, L_LN2_G)), PF(p_layer(l, L_LN2_B)),
-                                   FW(l, w.f_w1), FW(l, w.f_b1), d.mlp, D, 1, 1.0f};
-      jobs.job[jobs.n++] = FoldJob{PB(p_layer(l, L_FC2_W)), nullptr, nullptr, nullptr, FW(l, w.f_w2), nullptr, D, d.mlp, 0, 0.5f};
+      if (fuse_mlp2) {
+        jobs.job[jobs.n++] = FoldJob{PB(p_layer(l, L_FC1_W)), PF(p_layer(l, L_FC1_B)), PF(p_layer(l, L_LN2_G)), PF(p_layer(l, L_LN2_B)),
+                                     FW(l, w.f_w1), FW(l, w.f_b1), d.mlp, D, 1, 1.0f};
+        jobs.job[jobs.n++] = FoldJob{PB(p_layer(l, L_FC2_W)), nullptr, nullptr, nullptr, FW(l, w.f_w2), nullptr, D, d.mlp, 0, 0.5f};
+      }
+      if (fuse_attn2) {
+        const bf16* wqkv = PB(p_layer(l, L_QKV_W));
+        const float* bqkv = PF(p_layer(l, L_QKV_B));
+        const float *g1 = PF(p_layer(l, L_LN1_G)), *b1 = PF(p_layer(l, L_LN1_B));
+        bf16* wf = FW(l, w.f_wqkv);
+        const float qscale = 0.125f * 1.4426950408889634f;          // softmax(q.k / 8) evaluated as 2^(s - max)
+        jobs.job[jobs.n++] = FoldJob{wqkv, bqkv, g1, b1, wf, FW(l, w.f_bq), D, D, 1, qscale};                                   // Q rows
+        jobs.job[jobs.n++] = FoldJob{wqkv + (size_t)D * D, nullptr, g1, nullptr, wf + (size_t)D * D, nullptr, D, D, 0, 1.0f};   // K rows: bias cancels in the softmax
+        jobs.job[jobs.n++] = FoldJob{wqkv + (size_t)2 * D * D, bqkv + 2 * D, g1, b1, wf + (size_t)2 * D * D, FF(l, w.f_bv), D, D, 0, 1.0f};   // V rows
+        jobs2.job[jobs2.n++] = FoldJob{PB(p_layer(l, L_OUT_W)), PF(p_layer(l, L_OUT_B)), nullptr, FF(l, w.f_bv), nullptr, FF(l, w.f_bo), D, D, 0, 1.0f};
+      }
     }
     VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_fold_params(st, jobs); }));
+    if (jobs2.n) VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_fold_params(st, jobs2); }));
   }
   // patch embedding: tokens = patches . Wpe^T + b + pos
   VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_patchify(st, x, patches, d.B, d.H, d.W, d.C, d.P); }));
@@ -189,8 +207,13 @@ static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, c
   }
   for (int l = 0; l < d.L; ++l) {
     const bool fuse_attn = !save && g_fused_mode && fused_attn_supported(D, d.heads, d.T);
-    if (fuse_attn) {
-      // inference: LN1 + QKV + softmax(QK^T)V + out-projection + residual in one kernel
+    if (fuse_attn2) {
+      // inference: LN1 + QKV + softmax(QK^T)V + out-projection + residual in one kernel on the folded parameters
+      VM_TRY(timed(st, CAT_FUSED_ATTN, 8.0 * M * D * D + 4.0 * M * d.T * D, [&] {
+        return launch_fused_attn2(st, X(l), XM(l), FW(l, w.f_wqkv), FW(l, w.f_bq), PB(p_layer(l, L_OUT_W)), FF(l, w.f_bo), M, D, d.heads, d.eps);
+      }));
+    } else if (fuse_attn) {
+      // legacy 1-CTA fused attention block
       VM_TRY(timed(st, CAT_FUSED_ATTN, 8.0 * M * D * D + 4.0 * M * d.T * D, [&] {
         return launch_fused_attn(st, X(l), XM(l), PF(p_layer(l, L_LN1_G)), PF(p_layer(l, L_LN1_B)), PB(p_layer(l, L_QKV_W)),
                                  PF(p_layer(l, L_QKV_B)), PB(p_layer(l, L_OUT_W)), PF(p_layer(l, L_OUT_B)), M, D, d.heads, d.eps);
@@ -414,6 +437,7 @@ extern "C" int vitmarl_debug_fused_mlp_timeline(long long* device_buf) {
   fused_mlp_set_debug(device_buf);
   fused_mlp2_set_debug(device_buf);
   fused_attn_set_debug(device_buf ? device_buf + 256 : nullptr);
+  fused_attn2_set_debug(device_buf ? device_buf + 256 : nullptr);
   return VITMARL_OK;
 }
 

@@ -1,8 +1,10 @@
 // On-the-fly parameter folding for the fused inference kernels (one launch per forward, ~10 MB of traffic):
 //     Wf[n, k]  = bf16( scale * W[n, k] * gamma[k] )            (LayerNorm scale folded into the following projection)
-//     bf[n]     = bias[n] + sum_k W[n, k] * beta[k]             (LayerNorm shift folded into its bias)
+//     bf[n]     = scale * (bias[n] + sum_k W[n, k] * beta[k])   (LayerNorm shift folded into its bias)
 // so that  (LN(x) * gamma + beta) . W^T + bias  ==  ((x - mean) * rstd) . Wf^T + bf   and the kernels' LayerNorm is a
-// pure normalisation.  `scale` = 1/2 folds the 0.5 of gelu_tanh into FC2.  The caller's parameter table is never
+// pure normalisation.  `scale` = 1/2 folds the 0.5 of gelu_tanh into FC2; `scale` = log2(e)/8 on the Q rows folds the softmax
+// scale; a job with Wf = null only produces a bias (output bias + Wo . folded V bias: the V bias commutes with the
+// row-stochastic P).  The caller's parameter table is never
 // modified (the C ABI treats it as const; an optimiser may have updated it since the previous call).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -25,13 +27,13 @@ __global__ void __launch_bounds__(256) fold_params_kernel(const __grid_constant_
   for (int k2 = lane; k2 < J.K / 2; k2 += 32) {
     const float2 v = __bfloat1622float2(w[k2]);
     const float g0 = J.gamma ? J.gamma[2 * k2] : 1.f, g1 = J.gamma ? J.gamma[2 * k2 + 1] : 1.f;
-    wf[k2] = __floats2bfloat162_rn(J.scale * v.x * g0, J.scale * v.y * g1);
+    if (J.Wf) wf[k2] = __floats2bfloat162_rn(J.scale * v.x * g0, J.scale * v.y * g1);
     if (J.beta) acc += v.x * J.beta[2 * k2] + v.y * J.beta[2 * k2 + 1];
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0 && J.bias_out) {
-    const float b = (J.bias ? J.bias[n] : 0.f) + acc;
+    const float b = J.scale * ((J.bias ? J.bias[n] : 0.f) + acc);
     if (J.bias_out_bf16) reinterpret_cast<__nv_bfloat16*>(J.bias_out)[n] = __float2bfloat16_rn(b);
     else reinterpret_cast<float*>(J.bias_out)[n] = b;
   }

@@ -78,6 +78,13 @@ int launch_fused_mlp2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16
 bool fused_mlp2_supported(int D, int hidden);
 void fused_mlp2_set_debug(long long* buf);
 
+// Second-generation fused attention block on FOLDED parameters (vit_fold.cu): wqkvf = Wqkv.diag(gamma) with the Q rows scaled
+// by log2(e)/8, bqp = bf16 folded Q bias, bof = bo + Wo.(bv + Wv.beta).  `out` may alias `x`
+int launch_fused_attn2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16* out, const __nv_bfloat16* wqkvf, const __nv_bfloat16* bqp,
+                       const __nv_bfloat16* wo, const float* bof, int M, int D, int heads, float eps);
+bool fused_attn2_supported(int D, int heads, int tokens);
+void fused_attn2_set_debug(long long* buf);
+
 // parameter folding: Wf = scale * W . diag(gamma) (bf16 [N,K]), bias_out = bias + W . beta (fp32 or bf16 [N]); null = identity
 struct FoldJob {
   const __nv_bfloat16* W; const float* bias; const float* gamma; const float* beta;
@@ -85,7 +92,7 @@ struct FoldJob {
   int N, K, bias_out_bf16;
   float scale;
 };
-struct FoldJobs { FoldJob job[48]; int n; };
+struct FoldJobs { FoldJob job[64]; int n; };
 int launch_fold_params(cudaStream_t s, const FoldJobs& jobs);
 
 // elementwise helpers
