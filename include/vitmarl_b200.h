@@ -196,12 +196,15 @@ int vitmarl_vit_bwd(void* stream, const VitmarlVitShape* s, const void* const* p
                     void* workspace, size_t workspace_bytes, const float* dy,
                     void* const* dparams, void* dx);
 
-/* Inference forward: use the fused per-block kernels (1, default) or the unfused kernel sequence (0). */
-int vitmarl_vit_set_fused(int enable);
+/* Inference forward: 1 (default) the fused per-block kernels (CTA-pair MLP block, warp-specialised attention block on
+ * folded parameters), 0 the unfused kernel sequence, 2 the first-generation 1-CTA fused kernels. */
+int vitmarl_vit_set_fused(int mode);
 
 /* Debug hook: device buffer (>= 512 int64) that receives clock64() phase stamps of the fused block kernels
  * (CTA 0, second tile; [0,256) MLP block, [256,512) attention block); NULL switches it off. */
 int vitmarl_debug_fused_mlp_timeline(long long* device_buf);
+/* Debug hook: tuning switches of the fused attention block (0 = defaults). */
+int vitmarl_debug_set_flags(int attn_flags);
 
 /* Measurement hook: CUDA-event timing (on the launch stream) of every tensor-core GEMM launch
  * (plain GEMMs and fused block kernels) issued by vitmarl_vit_fwd / vitmarl_vit_bwd.  enable(1) resets the log;

@@ -15,7 +15,8 @@
 //     Q's are folded into the weights (the K bias cancels inside the softmax, the V bias moves into the output bias),
 //     so the epilogues are convert-and-store;
 //   * the x tile is consumed by the LayerNorm only (the residual is re-read from L2 in the final epilogue), so the next
-//     tile's TMA load is issued as soon as the LayerNorm has read the current one;
+//     tile's TMA load is issued as soon as the LayerNorm has read the current one (reading x for the LayerNorm straight
+//     from L2 instead was tried: its latency lands on the tile-boundary critical path, 146 -> 180 us);
 //   * tile boundary: the next tile's first QKV projection is issued BEFORE this tile's output projection, which
 //     accumulates into the (dead) S|O columns, so the tensor pipe never drains between tiles.
 // TMEM columns: XN 0..95 (LN(x), bf16 pairs) | QKV 96..287 | S / P 288..415 | O 416..479;  projection accumulator = 288..479.
@@ -66,6 +67,7 @@ struct FusedAttn2Params {
   const float* bo;              // [D] folded output bias (bo + Wo . bv')
   float eps;
   long long* dbg;
+  int flags;                    // bit 0: projection of head n+1 is held back until S(n) has retired (tuning switch)
 };
 
 #define FA2_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && j == 1 && lane == 0) p.dbg[(slot)] = clock64(); } while (0)
@@ -188,6 +190,7 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       for (int j = 0; j < nt; ++j) {
         for (int h = 0; h + 1 < NH; ++h, ++n) {
           mbar_wait_guard(bar(B_QKVEMPTY), n & 1);             // accumulator of head n drained (early in its epilogue)
+          if (p.flags & 1) mbar_wait_guard(bar(B_SFULL), n & 1); // S(n) first: the projection then overlaps the softmax, not S / P.V
           tc_fence_after();
           FA2_STAMP(101 + 4 * h);
           qkv_gemm();
@@ -241,8 +244,8 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           const uint32_t ph = n & 1;
           // ---- S = Q K^T (both images; the diagonal 64x64 blocks are used).  Issued after P.V of the previous head by the
           //      same thread, so the in-order tensor pipe has finished reading P before S overwrites it ----
-          mbar_wait_guard(bar(B_QKREADY), ph);
           if (h == 0) mbar_wait_guard(bar(B_PROJEMPTY), (j & 1) ^ 1);      // previous tile's final epilogue drained cols 288..479
+          mbar_wait_guard(bar(B_QKREADY), ph);
           tc_fence_after();
           FA2_STAMP(100 + 4 * h);
           {
@@ -255,9 +258,10 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             __syncwarp();
           }
           // ---- O = P V  (P in tensor memory over the S columns, V an MN-major B operand) ----
-          mbar_wait_guard(bar(B_PREADY), ph);
+          // the barriers that complete early first: only one wait latency is left once the softmax arrives on PREADY
           mbar_wait_guard(bar(B_VREADY), ph);
           if (n > 0) mbar_wait_guard(bar(B_OCREADY), (n - 1) & 1);          // previous O drained from TMEM
+          mbar_wait_guard(bar(B_PREADY), ph);
           tc_fence_after();
           FA2_STAMP(102 + 4 * h);
           {
@@ -327,8 +331,11 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const uint32_t sw = (uint32_t)(row & 7);
 
     // ---- LayerNorm (scale/shift folded into Wqkv'/bq'): x K-block `part` of this row -> bf16 pairs in TMEM (XN) ----
-    auto layer_norm = [&](int j) {
-      mbar_wait_guard(bar(B_XFULL), j & 1);
+    auto layer_norm = [&](int jn) {
+      const int j = jn - 1;                                   // (stamps are keyed on the tile that is current while this runs)
+      if (warp == W_CV0) FA2_STAMP(51);
+      mbar_wait_guard(bar(B_XFULL), jn & 1);
+      if (warp == W_CV0) FA2_STAMP(52);
       const uint8_t* xr = sptr + OFF_X + part * KBLK + row * 128;
       uint4 v[8];
       float s = 0.f, q = 0.f;
@@ -341,6 +348,7 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_XFREE));                            // x tile consumed (values live in registers)
       asm volatile("bar.sync 1, 384;" ::: "memory");
+      if (warp == W_CV0) FA2_STAMP(53);
 #pragma unroll
       for (int k = 1; k < 3; ++k) { const float2 o = ln_part[row * 3 + (part + k) % 3]; s += o.x; q += o.y; }
       const float mean = s * (1.0f / D);
@@ -353,7 +361,8 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         w[4 * c + 0] = norm_bf16x2(v[c].x, rstd_b, nmr); w[4 * c + 1] = norm_bf16x2(v[c].y, rstd_b, nmr);
         w[4 * c + 2] = norm_bf16x2(v[c].z, rstd_b, nmr); w[4 * c + 3] = norm_bf16x2(v[c].w, rstd_b, nmr);
       }
-      if (j > 0) { mbar_wait_guard(bar(B_XNFREE), (j - 1) & 1); tc_fence_after(); }   // previous tile's last QKV projection has read XN
+      if (jn > 0) { mbar_wait_guard(bar(B_XNFREE), (jn - 1) & 1); tc_fence_after(); }   // previous tile's last QKV projection has read XN
+      if (warp == W_CV0) FA2_STAMP(54);
       tmem_st_32x32(tmem_base + tm_lane + COL_XN + part * 32, w);
       tmem_st_wait();
       tc_fence_before();
@@ -387,100 +396,106 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       if (warp == W_CV0) FA2_STAMP(13 + 4 * h);
     };
 
-    if (nt > 0) layer_norm(0);
-    uint32_t n = 0;
-    for (int j = 0; j < nt; ++j) {
-      for (int h = 0; h < NH; ++h, ++n) {
-        const uint32_t ph = n & 1;
-        // ---- QKV epilogue: 64 accumulator columns of Q_h, K_h or V_h -> bf16 -> swizzled operand tile in smem ----
-        mbar_wait_guard(bar(B_QKVFULL), ph);
-        tc_fence_after();
-        if (warp == W_CV0) FA2_STAMP(30 + 2 * h);
-        uint32_t w[32];
+    // ---- QKV epilogue of head n: 64 accumulator columns of Q_h, K_h or V_h -> bf16 -> swizzled operand tile in smem ----
+    auto qkv_epilogue = [&](int j, int h, uint32_t n) {
+      mbar_wait_guard(bar(B_QKVFULL), n & 1);
+      tc_fence_after();
+      if (warp == W_CV0) FA2_STAMP(30 + 2 * h);
+      uint32_t w[32];
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + tm_lane + COL_QKV + part * 64 + hf * 32, r);
-          tmem_ld_wait();
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + tm_lane + COL_QKV + part * 64 + hf * 32, r);
+        tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) w[hf * 16 + i] = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(B_QKVEMPTY));                       // accumulator drained: the next projection may start
-        if (part == 0) {
-          const uint4* bq = reinterpret_cast<const uint4*>(s_bqp + h * 32);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint4 b = bq[c];
-            w[4 * c] = bf16x2_add(w[4 * c], b.x); w[4 * c + 1] = bf16x2_add(w[4 * c + 1], b.y);
-            w[4 * c + 2] = bf16x2_add(w[4 * c + 2], b.z); w[4 * c + 3] = bf16x2_add(w[4 * c + 3], b.w);
-          }
-        }
-        // operand buffers of the previous head must be dead: Q, K once S has completed; V once P.V has completed
-        if (n > 0) {
-          if (part == 2) mbar_wait_guard(bar(B_OFULL), (n - 1) & 1);
-          else mbar_wait_guard(bar(B_SFULL), (n - 1) & 1);
-        }
-        uint8_t* dst = sptr + (part == 0 ? OFF_Q : (part == 1 ? OFF_K : OFF_V)) + row * 128;
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(dst + ((((uint32_t)c) ^ sw) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(part == 2 ? B_VREADY : B_QKREADY));
-        if (warp == W_CV0) FA2_STAMP(31 + 2 * h);
-        if (h > 0) o_epilogue(j, h - 1, n - 1);
+        for (int i = 0; i < 16; ++i) w[hf * 16 + i] = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
       }
-      // ---- next tile's LayerNorm (its x tile was prefetched during this tile) overlaps this tile's P.V / projection ----
-      if (j + 1 < nt) layer_norm(j + 1);
-      if (warp == W_CV0) FA2_STAMP(50);
-      o_epilogue(j, NH - 1, n - 1);
-
-      // ---- final epilogue: out = proj + bo' + x (residual from L2), staged over concat(O) K-block `part`, stored by the IO warp ----
-      {
-        const int grow = tile_row(j) + row;
-        uint4 xr[8];
-        if (grow < p.M) {
-          const uint4* gx = reinterpret_cast<const uint4*>(p.x + (size_t)grow * D + part * 64);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_QKVEMPTY));                         // accumulator drained: the next projection may start
+      if (part == 0) {
+        const uint4* bq = reinterpret_cast<const uint4*>(s_bqp + h * 32);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) xr[c] = gx[c];
-        } else {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) xr[c] = make_uint4(0u, 0u, 0u, 0u);
+        for (int c = 0; c < 8; ++c) {
+          const uint4 b = bq[c];
+          w[4 * c] = bf16x2_add(w[4 * c], b.x); w[4 * c + 1] = bf16x2_add(w[4 * c + 1], b.y);
+          w[4 * c + 2] = bf16x2_add(w[4 * c + 2], b.z); w[4 * c + 3] = bf16x2_add(w[4 * c + 3], b.w);
         }
-        mbar_wait_guard(bar(B_PROJFULL), j & 1);
-        tc_fence_after();
-        if (warp == W_CV0) FA2_STAMP(60);
-        uint8_t* orow = sptr + OFF_OC + part * KBLK + row * 128;
-        const float* bo = s_bo + part * 64;
+      }
+      // operand buffers of the previous head must be dead: Q, K once S has completed; V once P.V has completed
+      if (n > 0) {
+        if (part == 2) mbar_wait_guard(bar(B_OFULL), (n - 1) & 1);
+        else mbar_wait_guard(bar(B_SFULL), (n - 1) & 1);
+      }
+      uint8_t* dst = sptr + (part == 0 ? OFF_Q : (part == 1 ? OFF_K : OFF_V)) + row * 128;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + tm_lane + COL_PROJ + part * 64 + half * 32, r);
-          tmem_ld_wait();
-          if (half == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(B_PROJEMPTY));                  // accumulator drained: the next tile's S may overwrite it
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(dst + ((((uint32_t)c) ^ sw) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(part == 2 ? B_VREADY : B_QKREADY));
+      if (warp == W_CV0) FA2_STAMP(31 + 2 * h);
+    };
+
+    // ---- final epilogue: out = proj + bo' + x (residual from L2), staged over concat(O) K-block `part`, stored by the IO warp ----
+    auto final_epilogue = [&](int j) {
+      const int grow = tile_row(j) + row;
+      uint4 xr[8];
+      if (grow < p.M) {
+        const uint4* gx = reinterpret_cast<const uint4*>(p.x + (size_t)grow * D + part * 64);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) xr[c] = gx[c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) xr[c] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      mbar_wait_guard(bar(B_PROJFULL), j & 1);
+      tc_fence_after();
+      if (warp == W_CV0) FA2_STAMP(60);
+      uint8_t* orow = sptr + OFF_OC + part * KBLK + row * 128;
+      const float* bo = s_bo + part * 64;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + tm_lane + COL_PROJ + part * 64 + half * 32, r);
+        tmem_ld_wait();
+        if (half == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(B_PROJEMPTY));                    // accumulator drained: the next tile's S may overwrite it
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t* xw = &xr[half * 4 + c].x;
+          uint32_t ow[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int e = 8 * c + 2 * k;
+            ow[k] = bf16x2_add(pack_bf16(__uint_as_float(r[e]) + bo[half * 32 + e], __uint_as_float(r[e + 1]) + bo[half * 32 + e + 1]), xw[k]);
           }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t* xw = &xr[half * 4 + c].x;
-            uint32_t ow[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int e = 8 * c + 2 * k;
-              ow[k] = bf16x2_add(pack_bf16(__uint_as_float(r[e]) + bo[half * 32 + e], __uint_as_float(r[e + 1]) + bo[half * 32 + e + 1]), xw[k]);
-            }
-            *reinterpret_cast<uint4*>(orow + ((((uint32_t)(half * 4 + c)) ^ sw) << 4)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-          }
+          *reinterpret_cast<uint4*>(orow + ((((uint32_t)(half * 4 + c)) ^ sw) << 4)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_OUTREADY));
       if (warp == W_CV0) FA2_STAMP(61);
+    };
+
+    // (A version software-pipelined over tiles -- next tile's first QKV epilogue before this tile's final epilogue, next
+    // LayerNorm after head 1 -- measured slower, 146 -> 171 us: it lengthens the conversion warps' serial chain.)
+    if (nt > 0) layer_norm(0);
+    uint32_t n = 0;
+    for (int j = 0; j < nt; ++j) {
+      for (int h = 0; h < NH; ++h, ++n) {
+        qkv_epilogue(j, h, n);
+        if (h > 0) o_epilogue(j, h - 1, n - 1);
+      }
+      // next tile's LayerNorm (its x tile was prefetched during this tile) overlaps this tile's P.V / projection
+      if (j + 1 < nt) layer_norm(j + 1);
+      if (warp == W_CV0) FA2_STAMP(50);
+      o_epilogue(j, NH - 1, n - 1);
+      final_epilogue(j);
     }
   }
   tc_fence_before();
@@ -492,6 +507,8 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 }
 
 static long long* g_fattn2_dbg = nullptr;
+static int g_fattn2_flags = 0;
+void fused_attn2_set_flags(int f) { g_fattn2_flags = f; }
 void fused_attn2_set_debug(long long* buf) { g_fattn2_dbg = buf; }
 
 bool fused_attn2_supported(int D, int heads, int tokens) { return D == fattn2::D && heads == fattn2::NH && tokens == 64; }
@@ -510,7 +527,7 @@ int launch_fused_attn2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat1
   if ((rc = make_tmap_2d_bf16(&tmOut, out, M, D, (uint64_t)D * 2, TM, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmWqkv, wqkvf, 3 * D, D, (uint64_t)D * 2, 64, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmWo, wo, D, D, (uint64_t)D * 2, D, 64))) return rc;
-  FusedAttn2Params p{M, x, reinterpret_cast<const uint32_t*>(bqp), bof, eps, g_fattn2_dbg};
+  FusedAttn2Params p{M, x, reinterpret_cast<const uint32_t*>(bqp), bof, eps, g_fattn2_dbg, g_fattn2_flags};
   cudaError_t e = cudaFuncSetAttribute(fused_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return check_cuda(e);
   const int tiles = (M + TM - 1) / TM;

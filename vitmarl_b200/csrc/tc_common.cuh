@@ -244,6 +244,17 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
   }
 }
 // CTA-scope wait with the same watchdog
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {   // non-blocking poll (no hardware suspend)
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_guard(uint32_t bar, uint32_t parity) {
   uint32_t polls = 0;
   long long t0 = 0;

@@ -441,6 +441,12 @@ extern "C" int vitmarl_debug_fused_mlp_timeline(long long* device_buf) {
   return VITMARL_OK;
 }
 
+// Tuning switches of the fused kernels (debug / experiments; 0 = defaults).
+extern "C" int vitmarl_debug_set_flags(int attn_flags) {
+  fused_attn2_set_flags(attn_flags);
+  return VITMARL_OK;
+}
+
 // Use the 2-CTA (cta_group::2) GEMM where it applies (1, default) or only the 1-CTA kernel (0).
 extern "C" int vitmarl_gemm_set_2cta(int enable) {
   gemm_set_2cta(enable != 0);
