@@ -229,14 +229,21 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     peaks = _peaks()
-    # roofline of the dominant kernel (tcgen05 GEMM): logged over the timed region AND the warm-up steps
-    gemm_ms_total, gemm_launches, gemm_flops = ms.value, n.value, fl.value
-    gemm_ms_per_launch = gemm_ms_total / max(gemm_launches, 1)
-    achieved_tf = gemm_flops / max(gemm_ms_total * 1e-3, 1e-12) / 1e12
-    steps_logged = W + K                      # the log covers warm-up + timed steps of the device-resident run
+    steps_logged = W + K                      # the event log covers warm-up + timed steps of the device-resident run
     names = ["gemm", "fused_mlp", "fused_attn_block", "attention", "layernorm", "other"]
     breakdown = {nm: {"ms_per_step": cat_ms[i] / steps_logged, "launches_per_step": cat_n[i] / steps_logged}
                  for i, nm in enumerate(names) if cat_n[i]}
+    # roofline of the DOMINANT kernel = the fused MLP block (largest share of the step): algorithmic FLOPs per launch
+    # 4 * tokens * D * mlp (DESIGN.md "Kernels") / its average launch duration (CUDA events around every launch)
+    tokens = E * vcfg.tokens
+    mlp_flops = 4.0 * tokens * vcfg.dim * vcfg.mlp_dim
+    attn_flops = 8.0 * tokens * vcfg.dim * vcfg.dim + 4.0 * tokens * vcfg.tokens * vcfg.dim
+    mlp_us = cat_ms[1] / max(cat_n[1], 1) * 1e3
+    attn_us = cat_ms[2] / max(cat_n[2], 1) * 1e3
+    dom_tf = mlp_flops / max(mlp_us * 1e-6, 1e-12) / 1e12
+    # all tcgen05 launches of the step together (patch-embed GEMM + 24 fused block kernels)
+    gemm_ms_total, gemm_launches, gemm_flops = ms.value, n.value, fl.value
+    all_tf = gemm_flops / max(gemm_ms_total * 1e-3, 1e-12) / 1e12
     value = world * E * K / t_dev
     e2e = world * E * K / t_e2e
     # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
@@ -255,15 +262,21 @@ def run_ours(args):
                    "envs_per_gpu": E, "msgs_per_step": M, "image": "64x64x2 bf16", "vit": "tiny/8 D192 L12",
                    "l2": "per-step working set ~300 MB (residual stream 100 MB + patches 67 MB + raster 67 MB + books/trades 35 MB + weights) > 126 MB L2; no flush needed",
                    "parallelism": f"env-sharded x{world}, no data-path collective"},
-        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved_tf / peaks["bf16_tflops_sustained"],
-                     # dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused block kernels at this shape,
-                     # from the ncu --set full capture profiles/r01_fused_blocks_ncu_full_v2.md (algorithmic: 100.7 MB in + 100.7 MB out)
-                     "traffic": 143.0e6,
-                     "kernel": "tcgen05 kernels of the step (vitmarl::gemm_kernel + fused block kernels), CUDA events per launch",
+        "roofline": {"bound": "tensor", "achieved": dom_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": dom_tf / peaks["bf16_tflops_sustained"],
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch of fused_mlp2_kernel at this shape, from the
+                     # ncu --set full capture profiles/r01_fused_blocks_ncu_full_v3.md (algorithmic: 100.7 MB in + 100.7 MB out;
+                     # part of the write-back is still in L2 when the kernel ends)
+                     "traffic": 143.8e6,
+                     "kernel": "vitmarl::fused_mlp2_kernel (LN2+FC1+GELU+FC2+residual, CTA-pair tcgen05), 12 launches per step",
+                     "flops_per_launch": mlp_flops, "avg_launch_us": mlp_us, "share_of_step": cat_ms[1] / steps_logged / (t_dev / K * 1e3),
+                     "second_kernel": {"kernel": "vitmarl::fused_attn2_kernel (LN1+QKV+softmax+PV+proj+residual)", "flops_per_launch": attn_flops,
+                                       "avg_launch_us": attn_us, "achieved": attn_flops / max(attn_us * 1e-6, 1e-12) / 1e12,
+                                       "frac": attn_flops / max(attn_us * 1e-6, 1e-12) / 1e12 / peaks["bf16_tflops_sustained"]},
+                     "all_tcgen05_launches": {"achieved": all_tf, "frac": all_tf / peaks["bf16_tflops_sustained"], "launches_timed": gemm_launches,
+                                              "flops_per_step": gemm_flops / max(steps_logged, 1),
+                                              "share_of_step": (gemm_ms_total / max(steps_logged, 1)) / (t_dev / K * 1e3)},
                      "per_step_ms_by_kernel_class": breakdown,
-                     "launches_timed": gemm_launches, "avg_launch_us": gemm_ms_per_launch * 1e3,
-                     "flops_per_step": gemm_flops / max(steps_logged, 1), "gemm_share_of_step": (gemm_ms_total / max(steps_logged, 1)) / (t_dev / K * 1e3),
                      "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": eng.h2d_bytes_per_step * world, "d2h_bytes_per_step": eng.d2h_bytes_per_step * world,

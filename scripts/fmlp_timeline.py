@@ -5,6 +5,7 @@ import ctypes
 import torch
 from vitmarl_b200 import vit, _capi
 lib = _capi.lib()
+if len(sys.argv) > 1: lib.vitmarl_debug_set_flags(int(sys.argv[1], 0))
 cfg = vit.ViTConfig(64, 64, 2, 8, 192, 1, 3, 768)
 enc = vit.ViTEncoder(cfg)
 packed = vit.pack_params(cfg, vit.init_params(cfg, 0, "cuda"))

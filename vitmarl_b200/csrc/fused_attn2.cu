@@ -67,7 +67,8 @@ struct FusedAttn2Params {
   const float* bo;              // [D] folded output bias (bo + Wo . bv')
   float eps;
   long long* dbg;
-  int flags;                    // bit 0: projection of head n+1 is held back until S(n) has retired (tuning switch)
+  int flags;                    // tuning switches: bit 0 projection of head n+1 held back until S(n) has retired; bit 1 output projection
+                                // (and its weights) before the next tile's first QKV projection
 };
 
 #define FA2_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && j == 1 && lane == 0) p.dbg[(slot)] = clock64(); } while (0)
@@ -108,7 +109,7 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   }
   if (warp == W_MMA) tmem_alloc<TMEM_COLS>(bar(B_TMEMSLOT));
   for (int i = threadIdx.x; i < D / 2; i += THREADS) s_bqp[i] = p.bqp[i];
-  for (int i = threadIdx.x; i < D; i += THREADS) s_bo[i] = p.bo[i];
+  for (int i = threadIdx.x; i < D / 2; i += THREADS) s_bo[i] = __uint_as_float(pack_bf16(p.bo[2 * i], p.bo[2 * i + 1]));   // packed bf16x2
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -132,13 +133,15 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       for (int j = 0; j < nt; ++j) {
         load_qkv(1);
         load_qkv(2);
-        if (j + 1 < nt) load_qkv(0);
+        const bool wo_first = (p.flags & 2) != 0;
+        if (!wo_first && j + 1 < nt) load_qkv(0);
         for (int kb = 0; kb < KB_X; ++kb) {                  // Wo K-block [192 x 64]
           mbar_wait_guard(bar(B_WEMPTY + ws), wph ^ 1);
           mbar_arrive_expect_tx(bar(B_WFULL + ws), STAGE_BYTES);
           tma_load_2d(sbase + OFF_W + ws * STAGE_BYTES, &tmWo, kb * 64, 0, bar(B_WFULL + ws));
           if (++ws == NSTW) { ws = 0; wph ^= 1; }
         }
+        if (wo_first && j + 1 < nt) load_qkv(0);
       }
     }
   } else if (warp == W_IO) {
@@ -201,15 +204,19 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           __syncwarp();
         }
         ++n;                                                   // n = 3 (j + 1): heads of this tile all issued
-        // ---- tile boundary: the next tile's first projection goes first, then this tile's output projection ----
-        if (j + 1 < nt) {
-          mbar_wait_guard(bar(B_XNREADY), (j + 1) & 1);
-          mbar_wait_guard(bar(B_QKVEMPTY), (n - 1) & 1);
-          tc_fence_after();
-          qkv_gemm();
-          if (elect_one()) umma_commit(bar(B_QKVFULL));
-          __syncwarp();
-        }
+        // ---- tile boundary: this tile's output projection and the next tile's first QKV projection (order = ring order) ----
+        const bool wo_first = (p.flags & 2) != 0;
+        auto next_qkv = [&]() {
+          if (j + 1 < nt) {
+            mbar_wait_guard(bar(B_XNREADY), (j + 1) & 1);
+            mbar_wait_guard(bar(B_QKVEMPTY), (n - 1) & 1);
+            tc_fence_after();
+            qkv_gemm();
+            if (elect_one()) umma_commit(bar(B_QKVFULL));
+            __syncwarp();
+          }
+        };
+        if (!wo_first) next_qkv();
         // concat(O) complete (implies P.V of the last head has retired).  A per-TILE barrier: this warp does not follow the
         // per-head OCREADY phases, and a parity wait on a barrier that may be two or more phases ahead aliases.
         mbar_wait_guard(bar(B_OCDONE), j & 1);
@@ -231,6 +238,7 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         if (elect_one()) umma_commit(bar(B_PROJFULL));
         __syncwarp();
         FA2_STAMP(131);
+        if (wo_first) next_qkv();
       }
     }
   } else if (warp == W_MMA2) {
@@ -453,7 +461,7 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       tc_fence_after();
       if (warp == W_CV0) FA2_STAMP(60);
       uint8_t* orow = sptr + OFF_OC + part * KBLK + row * 128;
-      const float* bo = s_bo + part * 64;
+      const uint4* bo = reinterpret_cast<const uint4*>(s_bo + part * 32);   // 64 columns = 32 packed pairs = 8 uint4
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t r[32];
@@ -466,14 +474,13 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const uint32_t* xw = &xr[half * 4 + c].x;
-          uint32_t ow[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int e = 8 * c + 2 * k;
-            ow[k] = bf16x2_add(pack_bf16(__uint_as_float(r[e]) + bo[half * 32 + e], __uint_as_float(r[e + 1]) + bo[half * 32 + e + 1]), xw[k]);
-          }
-          *reinterpret_cast<uint4*>(orow + ((((uint32_t)(half * 4 + c)) ^ sw) << 4)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          const uint4 xv = xr[half * 4 + c], bv = bo[half * 4 + c];
+          uint4 ov;
+          ov.x = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1])), bv.x), xv.x);
+          ov.y = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3])), bv.y), xv.y);
+          ov.z = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5])), bv.z), xv.z);
+          ov.w = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7])), bv.w), xv.w);
+          *reinterpret_cast<uint4*>(orow + ((((uint32_t)(half * 4 + c)) ^ sw) << 4)) = ov;
         }
       }
       fence_proxy_async_smem();

@@ -79,6 +79,7 @@ struct FusedMlp2Params {
   const float* b2;              // [D]
   float eps;
   long long* dbg;               // optional clock64 timeline of cluster 0 / leader (second tile); null in production
+  int ln_after;                 // the next tile's LayerNorm runs after this GELU chunk (tuning switch)
 };
 
 #define FM2_WAIT(acc, call) do { if (p.dbg) { const long long t__ = clock64(); call; if (j == 1) acc += clock64() - t__; } else { call; } } while (0)
@@ -132,7 +133,7 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < HID / 2; i += THREADS) s_b1p[i] = p.b1p[i];
-  for (int i = threadIdx.x; i < D; i += THREADS) s_b2[i] = p.b2[i];
+  for (int i = threadIdx.x; i < D / 2; i += THREADS) s_b2[i] = __uint_as_float(pack_bf16(p.b2[2 * i], p.b2[2 * i + 1]));   // packed bf16x2
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                                   // barriers of both CTAs initialised before any remote signal
@@ -328,7 +329,7 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(l_hready + 8u * b);
         if (stamp) FM2_STAMP(12 + 4 * c);
-        if (c == LN_AFTER_CHUNK && j + 1 < nt) {
+        if (c == p.ln_after && j + 1 < nt) {
           layer_norm(j + 1);                                        // overlaps the tensor pipe's FC1(c+2) / FC2(c) of this tile
           if (stamp) FM2_STAMP(50);
         }
@@ -353,12 +354,13 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         uint8_t* xb = sptr + OFF_X + (j & 1) * X_BYTES;
         auto emit = [&](const uint32_t* acc, int i) {     // 8 output columns col0 + 8 i .. from acc[0..8)
           const int col = col0 + 8 * i, kb = col >> 6, ch = (col & 63) >> 3;
-          const uint32_t* xw = &xr[i].x;
-          uint32_t ow[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ow[k] = bf16x2_add(pack_bf16(__uint_as_float(acc[2 * k]) + s_b2[col + 2 * k], __uint_as_float(acc[2 * k + 1]) + s_b2[col + 2 * k + 1]), xw[k]);
-          *reinterpret_cast<uint4*>(xb + kb * KBLK + row * 128 + ((((uint32_t)ch) ^ sw) << 4)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          const uint4 xv = xr[i], bv = *reinterpret_cast<const uint4*>(s_b2 + (col >> 1));
+          uint4 ov;
+          ov.x = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(acc[0]), __uint_as_float(acc[1])), bv.x), xv.x);
+          ov.y = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(acc[2]), __uint_as_float(acc[3])), bv.y), xv.y);
+          ov.z = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(acc[4]), __uint_as_float(acc[5])), bv.z), xv.z);
+          ov.w = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(acc[6]), __uint_as_float(acc[7])), bv.w), xv.w);
+          *reinterpret_cast<uint4*>(xb + kb * KBLK + row * 128 + ((((uint32_t)ch) ^ sw) << 4)) = ov;
         };
         uint32_t ra[32];
         tmem_ld_32x32(tmem_base + tm_lane + ACC2_COL + col0, ra);
@@ -391,6 +393,8 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 }
 
 static long long* g_fmlp2_dbg = nullptr;
+static int g_fmlp2_ln_after = fmlp2::LN_AFTER_CHUNK;
+void fused_mlp2_set_flags(int f) { g_fmlp2_ln_after = (f >= 0 && f < fmlp2::NCHUNK) ? f : fmlp2::LN_AFTER_CHUNK; }
 void fused_mlp2_set_debug(long long* buf) { g_fmlp2_dbg = buf; }
 
 bool fused_mlp2_supported(int D, int hidden) { return D == fmlp2::D && hidden == fmlp2::HID; }
@@ -407,7 +411,7 @@ int launch_fused_mlp2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16
   if ((rc = make_tmap_2d_bf16(&tmOut, out, M, D, (uint64_t)D * 2, TM, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmW1, w1f, HID, D, (uint64_t)D * 2, HC / 2, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmW2, w2h, fmlp2::D, HID, (uint64_t)HID * 2, fmlp2::D / 2, 64))) return rc;
-  FusedMlp2Params p{M, x, reinterpret_cast<const uint32_t*>(b1p), b2, eps, g_fmlp2_dbg};
+  FusedMlp2Params p{M, x, reinterpret_cast<const uint32_t*>(b1p), b2, eps, g_fmlp2_dbg, g_fmlp2_ln_after};
   cudaError_t e = cudaFuncSetAttribute(fused_mlp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return check_cuda(e);
   const int pair_tiles = (M + 2 * TM - 1) / (2 * TM);
