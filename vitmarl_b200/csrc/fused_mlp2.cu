@@ -12,7 +12,8 @@
 //     (FHFMA/FHADD, no unpacking), the bias add and GELU run on packed bf16x2 with the 0.5 folded into W2.
 //
 // Per-CTA warp roles (640 threads): warp 0 x-tile TMA loads + output TMA stores, warp 1 TMEM allocator + (leader only)
-// MMA issuer, warp 2 / 3 W1 / W2 weight-ring producers, warps 4-19 compute (LayerNorm, GELU epilogue, final epilogue).
+// MMA issuer, warp 2 / 3 W1 / W2 weight-ring producers, warps 4-11 GELU epilogue (MUFU-bound), warps 12-19 LayerNorm of the
+// next tile + final epilogue of the previous one (running concurrently with the GELU warps).
 // Hidden dimension in 6 chunks of 128: acc1[g&1] = LN(x) . W1'[c]^T (TMEM, double buffered); the GELU epilogue writes
 // H = gelu(acc1 + b1') as packed bf16 back into the SAME TMEM columns it was read from (tcgen05.st; thread (row, 32 cols)
 // overwrites the first 16 of its own 32 columns = two K=16 steps), and acc2 += H . (W2/2)[:,c]^T runs with the A operand
@@ -55,15 +56,16 @@ constexpr int OFF_W1 = OFF_X + NXB * X_BYTES;
 constexpr int OFF_W2 = OFF_W1 + NS1 * S1_BYTES;
 constexpr int OFF_BAR = OFF_W2 + NS2 * S2_BYTES;
 constexpr int OFF_MISC = OFF_BAR + 512;
-constexpr int MISC_BYTES = 128 * 4 * 8 + HID * 2 + D * 4;         // LN partials [128][4] float2, b1' (bf16), b2 (fp32)
+constexpr int MISC_BYTES = 128 * 4 * 8 + HID * 2 + D * 4;         // LN partials [128][2] float2 (+ spare), b1' (bf16), b2 (packed bf16)
 constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;
-constexpr int NCW = 16;                                           // compute warps per CTA
-constexpr int FIRST_CW = 4;
+constexpr int NGW = 8, NAW = 8;                                   // GELU warps / aux warps (LayerNorm + final epilogue) per CTA
+constexpr int NCW = NGW + NAW;
+constexpr int FIRST_CW = 4, FIRST_AUX = FIRST_CW + NGW;
 constexpr int THREADS = 32 * (FIRST_CW + NCW);
 constexpr int TMEM_COLS = 512;                                    // acc1[2] @ 0,128 ; acc2 @ 256 (192 cols)
 constexpr int ACC2_COL = 256;
 constexpr int LN_AFTER_CHUNK = 3;                                 // the next tile's LayerNorm runs after this GELU chunk
-enum { B_XFULL = 0, B_OUTREADY = B_XFULL + NXB, B_XNREADY, B_ACC2FULL, B_ACC2EMPTY,
+enum { B_XFULL = 0, B_OUTREADY = B_XFULL + NXB, B_XNREADY, B_ACC2FULL = B_XNREADY + NXB, B_ACC2EMPTY,
        B_ACC1FULL, B_HREADY = B_ACC1FULL + NB,
        B_W1FULL = B_HREADY + NB, B_W1EMPTY = B_W1FULL + NS1, B_W2FULL = B_W1EMPTY + NS1, B_W2EMPTY = B_W2FULL + NS2,
        B_TMEMSLOT = B_W2EMPTY + NS2, B_COUNT };
@@ -118,11 +120,11 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmOut);
     for (int i = 0; i < NXB; ++i) mbar_init(bar(B_XFULL + i), 1);
-    mbar_init(bar(B_OUTREADY), NCW);
-    mbar_init(bar(B_XNREADY), 2 * NCW);
-    mbar_init(bar(B_ACC2FULL), 1); mbar_init(bar(B_ACC2EMPTY), 2 * NCW);
+    mbar_init(bar(B_OUTREADY), NAW);
+    for (int i = 0; i < NXB; ++i) mbar_init(bar(B_XNREADY + i), 2 * NAW);   // one per x buffer: a LayerNorm may run two tiles ahead of the issuer
+    mbar_init(bar(B_ACC2FULL), 1); mbar_init(bar(B_ACC2EMPTY), 2 * NAW);
     for (int i = 0; i < NB; ++i) {
-      mbar_init(bar(B_ACC1FULL + i), 1); mbar_init(bar(B_HREADY + i), 2 * NCW);
+      mbar_init(bar(B_ACC1FULL + i), 1); mbar_init(bar(B_HREADY + i), 2 * NGW);
     }
     for (int i = 0; i < NS1; ++i) { mbar_init(bar(B_W1FULL + i), 1); mbar_init(bar(B_W1EMPTY + i), 1); }
     for (int i = 0; i < NS2; ++i) { mbar_init(bar(B_W2FULL + i), 1); mbar_init(bar(B_W2EMPTY + i), 1); }
@@ -199,7 +201,7 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       auto fc1 = [&](int g) {
         const int j = g / NCHUNK, c = g % NCHUNK;
         const uint32_t b = g & 1;
-        if (c == 0) FM2_WAIT(w_xn, mbar_wait_guard(bar(B_XNREADY), j & 1));   // LayerNorm of tile j done in both CTAs
+        if (c == 0) FM2_WAIT(w_xn, mbar_wait_guard(bar(B_XNREADY + (j & 1)), (j >> 1) & 1));   // LayerNorm of tile j done in both CTAs
         tc_fence_after();
         FM2_STAMP(100 + 4 * c);
         FM2_WAIT(w_w1, mbar_wait_guard(bar(B_W1FULL + s1), ph1));
@@ -254,134 +256,148 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[200] = w_xn; p.dbg[202] = w_w1; p.dbg[203] = w_a2; p.dbg[204] = w_h; p.dbg[205] = w_w2; }
     }
   } else {
-    // =============================== compute warps (4..19) ===============================
-    const int cw = warp - FIRST_CW;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int cq = cw >> 2;                    // column quarter (0..3)
     const int row = quad * 32 + lane;          // row within this CTA's tile
     const uint32_t tm_lane = (uint32_t)(quad * 32) << 16;
     const uint32_t sw = (uint32_t)(row & 7);
-    const uint32_t l_xnready = mapa_rank(bar(B_XNREADY), 0), l_acc2empty = mapa_rank(bar(B_ACC2EMPTY), 0);
-    const uint32_t l_hready = mapa_rank(bar(B_HREADY), 0);
-
-    // ---- LayerNorm (scale/shift folded into W1'/b1') in place: thread (row, cq) owns columns [cq*48, cq*48+48) ----
-    auto layer_norm = [&](int j) {
-      uint8_t* xb = sptr + OFF_X + (j & 1) * X_BYTES;
-      mbar_wait_guard(bar(B_XFULL + (j & 1)), (j >> 1) & 1);
-      uint4 v[6];
-      float s = 0.f, q = 0.f;
+    if (warp < FIRST_AUX) {
+      // =============================== GELU warps (4..11): thread = (row, 64 of the chunk's 128 columns) ===============================
+      // The GELU epilogue is bound by the MUFU pipe (tanh: 16 lanes/clk/SM -> ~1000 cycles per chunk whatever the warp count),
+      // so it gets its own warps and nothing else: LayerNorm and the final epilogue run concurrently on the aux warps.
+      const int ch = (warp - FIRST_CW) >> 2;   // column half (0..1)
+      const uint32_t l_hready = mapa_rank(bar(B_HREADY), 0);
+      int g = 0;
+      long long w_a1f = 0;
+      for (int j = 0; j < nt; ++j) {
+        const bool stamp = (warp == FIRST_CW && lane == 0);
+        if (stamp) FM2_STAMP(0);
+        for (int c = 0; c < NCHUNK; ++c, ++g) {
+          const uint32_t b = g & 1, use = (g >> 1) & 1;
+          FM2_WAIT(w_a1f, mbar_wait_guard(bar(B_ACC1FULL + b), use));
+          tc_fence_after();
+          if (stamp) FM2_STAMP(10 + 4 * c);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const int col = cq * 48 + i * 8, kb = col >> 6, ch = (col & 63) >> 3;
-        v[i] = *reinterpret_cast<const uint4*>(xb + kb * KBLK + row * 128 + ((ch ^ sw) << 4));
-        stats_bf16x2(v[i].x, s, q); stats_bf16x2(v[i].y, s, q); stats_bf16x2(v[i].z, s, q); stats_bf16x2(v[i].w, s, q);
-      }
-      ln_part[row * 4 + cq] = make_float2(s, q);
-      asm volatile("bar.sync 1, 512;" ::: "memory");
+          for (int hh = 0; hh < 2; ++hh) {
+            const int c32 = ch * 2 + hh;                                    // 32-column group of the chunk
+            uint32_t r0[32];
+            tmem_ld_32x32(tmem_base + tm_lane + b * HC + c32 * 32, r0);
+            tmem_ld_wait();
+            const uint4* bias = reinterpret_cast<const uint4*>(s_b1p + (c * HC + c32 * 32) / 2);
+            uint32_t pk[16];
 #pragma unroll
-      for (int k = 1; k < 4; ++k) { const float2 o = ln_part[row * 4 + ((cq + k) & 3)]; s += o.x; q += o.y; }
-      const float mean = s * (1.0f / D);
-      const float var = fmaxf(q * (1.0f / D) - mean * mean, 0.f);
-      const uint32_t rstd_b = pack_bf16(rsqrtf(var + p.eps), 0.f);
-      const float nmr = -mean * bf16_lo(rstd_b);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const int col = cq * 48 + i * 8, kb = col >> 6, ch = (col & 63) >> 3;
-        v[i].x = norm_bf16x2(v[i].x, rstd_b, nmr); v[i].y = norm_bf16x2(v[i].y, rstd_b, nmr);
-        v[i].z = norm_bf16x2(v[i].z, rstd_b, nmr); v[i].w = norm_bf16x2(v[i].w, rstd_b, nmr);
-        *reinterpret_cast<uint4*>(xb + kb * KBLK + row * 128 + ((ch ^ sw) << 4)) = v[i];
-      }
-      fence_proxy_async_smem();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(l_xnready);
-      asm volatile("bar.sync 1, 512;" ::: "memory");   // ln_part reuse safety
-    };
-
-    if (nt > 0) layer_norm(0);
-    int g = 0;
-    long long w_a1f = 0, w_a2f = 0;
-    for (int j = 0; j < nt; ++j) {
-      const bool stamp = (warp == FIRST_CW && lane == 0);
-      if (stamp) FM2_STAMP(0);
-      // ---- hidden chunks: GELU epilogue into the FC2 A operand (thread: row, 32 of the chunk's 128 columns) ----
-      for (int c = 0; c < NCHUNK; ++c, ++g) {
-        const uint32_t b = g & 1, use = (g >> 1) & 1;
-        FM2_WAIT(w_a1f, mbar_wait_guard(bar(B_ACC1FULL + b), use));
-        tc_fence_after();
-        if (stamp) FM2_STAMP(10 + 4 * c);
-        uint32_t r0[32];
-        tmem_ld_32x32(tmem_base + tm_lane + b * HC + cq * 32, r0);
-        tmem_ld_wait();
-        const uint4* bias = reinterpret_cast<const uint4*>(s_b1p + (c * HC + cq * 32) / 2);
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint4 bv = bias[i];
-          pk[4 * i + 0] = gelu2_bf16x2(bf16x2_add(pack_bf16(__uint_as_float(r0[8 * i + 0]), __uint_as_float(r0[8 * i + 1])), bv.x));
-          pk[4 * i + 1] = gelu2_bf16x2(bf16x2_add(pack_bf16(__uint_as_float(r0[8 * i + 2]), __uint_as_float(r0[8 * i + 3])), bv.y));
-          pk[4 * i + 2] = gelu2_bf16x2(bf16x2_add(pack_bf16(__uint_as_float(r0[8 * i + 4]), __uint_as_float(r0[8 * i + 5])), bv.z));
-          pk[4 * i + 3] = gelu2_bf16x2(bf16x2_add(pack_bf16(__uint_as_float(r0[8 * i + 6]), __uint_as_float(r0[8 * i + 7])), bv.w));
+            for (int i = 0; i < 4; ++i) {
+              const uint4 bv = bias[i];
+              pk[4 * i + 0] = gelu2_bf16x2(bf16x2_add(pack_bf16(__uint_as_float(r0[8 * i + 0]), __uint_as_float(r0[8 * i + 1])), bv.x));
+              pk[4 * i + 1] = gelu2_bf16x2(bf16x2_add(pack_bf16(__uint_as_float(r0[8 * i + 2]), __uint_as_float(r0[8 * i + 3])), bv.y));
+              pk[4 * i + 2] = gelu2_bf16x2(bf16x2_add(pack_bf16(__uint_as_float(r0[8 * i + 4]), __uint_as_float(r0[8 * i + 5])), bv.z));
+              pk[4 * i + 3] = gelu2_bf16x2(bf16x2_add(pack_bf16(__uint_as_float(r0[8 * i + 6]), __uint_as_float(r0[8 * i + 7])), bv.w));
+            }
+            // H (packed bf16, two K=16 steps) over the first 16 columns of the 32-column group it was read from: the FC2 A operand
+            tmem_st_32x16(tmem_base + tm_lane + b * HC + c32 * 32, pk);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(l_hready + 8u * b);
+          if (stamp) FM2_STAMP(12 + 4 * c);
         }
-        // H (packed bf16, two K=16 steps) over the first 16 of this thread's own 32 accumulator columns: the FC2 A operand
-        tmem_st_32x16(tmem_base + tm_lane + b * HC + cq * 32, pk);
-        tmem_st_wait();
-        tc_fence_before();
+      }
+      if (p.dbg && blockIdx.x == 0 && warp == FIRST_CW && lane == 0) p.dbg[210] = w_a1f;
+    } else {
+      // =============================== aux warps (12..19): LayerNorm + final epilogue, thread = (row, 96 of the 192 columns) ===============================
+      const int half = (warp - FIRST_AUX) >> 2;
+      const int col0 = half * 96;
+      const uint32_t l_xnready = mapa_rank(bar(B_XNREADY), 0), l_acc2empty = mapa_rank(bar(B_ACC2EMPTY), 0);
+      const bool stamp = (warp == FIRST_AUX && lane == 0);
+
+      // ---- LayerNorm (scale/shift folded into W1'/b1') in place in the x buffer ----
+      auto layer_norm = [&](int jn) {
+        uint8_t* xb = sptr + OFF_X + (jn & 1) * X_BYTES;
+        mbar_wait_guard(bar(B_XFULL + (jn & 1)), (jn >> 1) & 1);
+        uint4 v[12];
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const int col = col0 + i * 8, kb = col >> 6, c8 = (col & 63) >> 3;
+          v[i] = *reinterpret_cast<const uint4*>(xb + kb * KBLK + row * 128 + ((c8 ^ sw) << 4));
+          stats_bf16x2(v[i].x, s, q); stats_bf16x2(v[i].y, s, q); stats_bf16x2(v[i].z, s, q); stats_bf16x2(v[i].w, s, q);
+        }
+        ln_part[row * 2 + half] = make_float2(s, q);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float2 o = ln_part[row * 2 + (half ^ 1)];
+        s += o.x; q += o.y;
+        const float mean = s * (1.0f / D);
+        const float var = fmaxf(q * (1.0f / D) - mean * mean, 0.f);
+        const uint32_t rstd_b = pack_bf16(rsqrtf(var + p.eps), 0.f);
+        const float nmr = -mean * bf16_lo(rstd_b);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const int col = col0 + i * 8, kb = col >> 6, c8 = (col & 63) >> 3;
+          v[i].x = norm_bf16x2(v[i].x, rstd_b, nmr); v[i].y = norm_bf16x2(v[i].y, rstd_b, nmr);
+          v[i].z = norm_bf16x2(v[i].z, rstd_b, nmr); v[i].w = norm_bf16x2(v[i].w, rstd_b, nmr);
+          *reinterpret_cast<uint4*>(xb + kb * KBLK + row * 128 + ((c8 ^ sw) << 4)) = v[i];
+        }
+        fence_proxy_async_smem();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive_remote(l_hready + 8u * b);
-        if (stamp) FM2_STAMP(12 + 4 * c);
-        if (c == p.ln_after && j + 1 < nt) {
-          layer_norm(j + 1);                                        // overlaps the tensor pipe's FC1(c+2) / FC2(c) of this tile
-          if (stamp) FM2_STAMP(50);
-        }
-      }
-      // ---- final epilogue: out = acc2 + b2 + x.  The residual is re-read from L2 (issued before the accumulator wait),
-      //      the output tile is staged in the x buffer (LN(x) is dead once ACC2FULL has fired) and stored by warp 0 (TMA) ----
-      {
-        const int col0 = cq * 48;
-        const int grow = tile_row(j) + row;
-        uint4 xr[6];
-        if (grow < p.M) {
-          const uint4* gx = reinterpret_cast<const uint4*>(p.x + (size_t)grow * D + col0);
-#pragma unroll
-          for (int i = 0; i < 6; ++i) xr[i] = gx[i];
-        } else {
-#pragma unroll
-          for (int i = 0; i < 6; ++i) xr[i] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        FM2_WAIT(w_a2f, mbar_wait_guard(bar(B_ACC2FULL), j & 1));
+        if (lane == 0) mbar_arrive_remote(l_xnready + 8u * (jn & 1));
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // ln_part reuse safety
+      };
+
+      // ---- final epilogue: out = acc2 + b2 + x.  Residual re-read from L2 (issued before the accumulator wait); the output
+      //      tile is staged in the x buffer (LN(x) is dead once ACC2FULL has fired) and stored by warp 0 (TMA) ----
+      auto final_epilogue = [&](int j) {
+        mbar_wait_guard(bar(B_ACC2FULL), j & 1);
         tc_fence_after();
         if (stamp) FM2_STAMP(60);
-        uint8_t* xb = sptr + OFF_X + (j & 1) * X_BYTES;
-        auto emit = [&](const uint32_t* acc, int i) {     // 8 output columns col0 + 8 i .. from acc[0..8)
-          const int col = col0 + 8 * i, kb = col >> 6, ch = (col & 63) >> 3;
-          const uint4 xv = xr[i], bv = *reinterpret_cast<const uint4*>(s_b2 + (col >> 1));
-          uint4 ov;
-          ov.x = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(acc[0]), __uint_as_float(acc[1])), bv.x), xv.x);
-          ov.y = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(acc[2]), __uint_as_float(acc[3])), bv.y), xv.y);
-          ov.z = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(acc[4]), __uint_as_float(acc[5])), bv.z), xv.z);
-          ov.w = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(acc[6]), __uint_as_float(acc[7])), bv.w), xv.w);
-          *reinterpret_cast<uint4*>(xb + kb * KBLK + row * 128 + ((((uint32_t)ch) ^ sw) << 4)) = ov;
-        };
-        uint32_t ra[32];
-        tmem_ld_32x32(tmem_base + tm_lane + ACC2_COL + col0, ra);
-        tmem_ld_wait();
+        // drain acc2 first (packed to bf16 at once) so that the next tile's FC2(0) is released as early as possible ...
+        uint32_t acc[48];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) emit(ra + 8 * i, i);
-        uint32_t rb[16];
-        tmem_ld_32x16(tmem_base + tm_lane + ACC2_COL + col0 + 32, rb);
-        tmem_ld_wait();
+        for (int g3 = 0; g3 < 3; ++g3) {
+          uint32_t ra[32];
+          tmem_ld_32x32(tmem_base + tm_lane + ACC2_COL + col0 + g3 * 32, ra);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[g3 * 16 + i] = pack_bf16(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1]));
+        }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_remote(l_acc2empty);             // acc2 drained: the next tile's FC2(0) may overwrite it
+        if (lane == 0) mbar_arrive_remote(l_acc2empty);
+        // ... then add bias + residual (re-read from L2; these warps have slack) and stage the tile in the x buffer
+        const int grow = tile_row(j) + row;
+        uint8_t* xb = sptr + OFF_X + (j & 1) * X_BYTES;
+        const uint4* gx = reinterpret_cast<const uint4*>(p.x + (size_t)grow * D + col0);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) emit(rb + 8 * i, 4 + i);
+        for (int g3 = 0; g3 < 3; ++g3) {
+          uint4 xr[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xr[i] = grow < p.M ? gx[g3 * 4 + i] : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int col = col0 + g3 * 32 + 8 * i, kb = col >> 6, c8 = (col & 63) >> 3;
+            const uint4 bv = *reinterpret_cast<const uint4*>(s_b2 + (col >> 1));
+            const uint32_t* a4 = &acc[g3 * 16 + 4 * i];
+            uint4 ov;
+            ov.x = bf16x2_add(bf16x2_add(a4[0], bv.x), xr[i].x);
+            ov.y = bf16x2_add(bf16x2_add(a4[1], bv.y), xr[i].y);
+            ov.z = bf16x2_add(bf16x2_add(a4[2], bv.z), xr[i].z);
+            ov.w = bf16x2_add(bf16x2_add(a4[3], bv.w), xr[i].w);
+            *reinterpret_cast<uint4*>(xb + kb * KBLK + row * 128 + ((((uint32_t)c8) ^ sw) << 4)) = ov;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_OUTREADY));
+        if (stamp) FM2_STAMP(61);
+      };
+
+      // x(0), x(1) are loaded up front; x(j+2) is loaded into tile j's buffer once its output store has read it
+      if (nt > 0) layer_norm(0);
+      if (nt > 1) layer_norm(1);
+      for (int j = 0; j < nt; ++j) {
+        final_epilogue(j);
+        if (j + 2 < nt) { layer_norm(j + 2); if (stamp) FM2_STAMP(50); }
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_OUTREADY));
-      if (stamp) FM2_STAMP(61);
     }
-    if (p.dbg && blockIdx.x == 0 && warp == FIRST_CW && lane == 0) { p.dbg[210] = w_a1f; p.dbg[212] = w_a2f; }
   }
   tc_fence_before();
   __syncthreads();

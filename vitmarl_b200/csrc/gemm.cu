@@ -99,7 +99,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    // The whole warp runs the loop and one elected lane issues (a plain predicated instruction stream; under
+    // `if (lane == 0)` the compiler wraps every tcgen05.mma in a per-active-thread loop); descriptors are built once per
+    // stage and advanced by immediates (+32 B along K inside a swizzled row = +2, +2048 B for an MN-major K step = +128).
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
       int s = 0; uint32_t ph = 0;
       int it = 0;
@@ -115,16 +118,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint32_t sa = smem_base + s * Cfg::kStageBytes, sb = sa + Cfg::kABytes;
+          const uint32_t la = umma_desc_lo(sa, A_MN ? 8192 : 16), lb = umma_desc_lo(sb, B_MN ? 8192 : 16);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = A_MN ? umma_desc_sw128(sa + k * 2048, 8192, 1024) : umma_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? umma_desc_sw128(sb + k * 2048, 8192, 1024) : umma_desc_sw128(sb + k * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(d_tmem, umma_desc_from_lo(la + k * (A_MN ? 128 : 2)), umma_desc_from_lo(lb + k * (B_MN ? 128 : 2)), idesc,
+                        (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit(empty_bar(s));                   // frees the smem stage when these MMAs retire
           }
-          umma_commit(empty_bar(s));                     // frees the smem stage when these MMAs retire
+          __syncwarp();
           if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
         }
-        umma_commit(tfull_bar(acc));                     // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(tfull_bar(acc));    // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else {

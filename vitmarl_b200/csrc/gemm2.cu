@@ -96,8 +96,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (leader CTA only) =================
-    if (rank == 0 && lane == 0) {
+    // ================= MMA issuer (leader CTA only; whole warp loops, one elected lane issues) =================
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, false, false);
       int s = 0; uint32_t ph = 0;
       int it = 0;
@@ -111,14 +111,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint32_t sa = smem_base + s * Cfg::kStageBytes, sb = sa + Cfg::kABytes;
+          const uint32_t la = umma_desc_lo(sa), lb = umma_desc_lo(sb);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16_2sm(d_tmem, umma_desc_sw128(sa + k * 32, 16, 1024), umma_desc_sw128(sb + k * 32, 16, 1024), idesc,
-                          (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit_2sm(empty_bar(s));
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_2sm(d_tmem, umma_desc_from_lo(la + 2 * k), umma_desc_from_lo(lb + 2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit_2sm(empty_bar(s));
+          }
+          __syncwarp();
           if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
         }
-        umma_commit_2sm(tfull_bar(acc));
+        if (elect_one()) umma_commit_2sm(tfull_bar(acc));
+        __syncwarp();
       }
     }
   } else {
