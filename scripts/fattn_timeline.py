@@ -21,6 +21,7 @@ r = lambda i: t[i] - t0 if t[i] else None
 for h in range(3):
     b = 4 * h
     print(f" h{h}: CV: qkvfull {r(30+2*h)} epi_done {r(31+2*h)} | SM: sfull {r(10+b)} p_done {r(11+b)} oc_done(CV) {r(13+b)} | MMA: S {r(100+b)} QKVnext {r(101+b)} PV {r(102+b)}")
+print(" epi(h1): ld+pack done", r(70), "waits done", r(71), "sts issued", r(72), "fence done", r(73))
 print(" LN(next): start", r(51), "xfull", r(52), "stats+bar", r(53), "xnfree", r(54))
 print(" LN(next) done", r(50), "| proj start", r(130), "issued", r(131), "| CV: projfull", r(60), "tile end", r(61))
 lib.vitmarl_vit_gemm_timing_enable(1)

@@ -55,7 +55,7 @@ constexpr int THREADS = 32 * (W_CV0 + N_CV);       // 768
 constexpr int TMEM_COLS = 512;
 constexpr int COL_XN = 0, COL_QKV = 96, COL_S = 288, COL_O = 416, COL_PROJ = 288;
 enum { B_XFULL = 0, B_XFREE, B_XNREADY, B_XNFREE, B_QKVFULL, B_QKVEMPTY, B_QKREADY, B_VREADY, B_SFULL, B_PREADY, B_OFULL, B_OCREADY,
-       B_PROJFULL, B_PROJEMPTY, B_OUTREADY, B_OCFREE, B_OCDONE, B_WFULL, B_WEMPTY = B_WFULL + NSTW, B_TMEMSLOT = B_WEMPTY + NSTW, B_COUNT };
+       B_PROJFULL, B_PROJEMPTY, B_OUTREADY, B_OCFREE, B_OCDONE, B_SISSUED, B_WFULL, B_WEMPTY = B_WFULL + NSTW, B_TMEMSLOT = B_WEMPTY + NSTW, B_COUNT };
 static_assert(B_COUNT * 8 <= 256, "barrier area");
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 }  // namespace fattn2
@@ -103,7 +103,7 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     mbar_init(bar(B_XFULL), 1); mbar_init(bar(B_XFREE), N_CV); mbar_init(bar(B_XNREADY), N_CV); mbar_init(bar(B_XNFREE), 1);
     mbar_init(bar(B_QKVFULL), 1); mbar_init(bar(B_QKVEMPTY), N_CV); mbar_init(bar(B_QKREADY), 8); mbar_init(bar(B_VREADY), 4);
     mbar_init(bar(B_SFULL), 1); mbar_init(bar(B_PREADY), N_SM); mbar_init(bar(B_OFULL), 1); mbar_init(bar(B_OCREADY), N_OE);
-    mbar_init(bar(B_PROJFULL), 1); mbar_init(bar(B_PROJEMPTY), N_CV); mbar_init(bar(B_OUTREADY), N_CV); mbar_init(bar(B_OCFREE), 1); mbar_init(bar(B_OCDONE), N_OE);
+    mbar_init(bar(B_PROJFULL), 1); mbar_init(bar(B_PROJEMPTY), N_CV); mbar_init(bar(B_OUTREADY), N_CV); mbar_init(bar(B_OCFREE), 1); mbar_init(bar(B_OCDONE), N_OE); mbar_init(bar(B_SISSUED), 1);
     for (int i = 0; i < NSTW; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
     fence_mbar_init();
   }
@@ -193,6 +193,7 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       for (int j = 0; j < nt; ++j) {
         for (int h = 0; h + 1 < NH; ++h, ++n) {
           mbar_wait_guard(bar(B_QKVEMPTY), n & 1);             // accumulator of head n drained (early in its epilogue)
+          mbar_wait_guard(bar(B_SISSUED), n & 1);              // S(n) is in the pipe: the long projection queues BEHIND the short S product
           if (p.flags & 1) mbar_wait_guard(bar(B_SFULL), n & 1); // S(n) first: the projection then overlaps the softmax, not S / P.V
           tc_fence_after();
           FA2_STAMP(101 + 4 * h);
@@ -207,6 +208,7 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         // ---- tile boundary: this tile's output projection and the next tile's first QKV projection (order = ring order) ----
         const bool wo_first = (p.flags & 2) != 0;
         auto next_qkv = [&]() {
+          mbar_wait_guard(bar(B_SISSUED), (n - 1) & 1);        // (every phase is consumed, also on the last tile)
           if (j + 1 < nt) {
             mbar_wait_guard(bar(B_XNREADY), (j + 1) & 1);
             mbar_wait_guard(bar(B_QKVEMPTY), (n - 1) & 1);
@@ -262,6 +264,7 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
               for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + COL_S, umma_desc_from_lo(la + 2 * k), umma_desc_from_lo(lb + 2 * k), id_s, k ? 1u : 0u);
               umma_commit(bar(B_SFULL));
+              mbar_arrive(bar(B_SISSUED));
             }
             __syncwarp();
           }
@@ -418,6 +421,7 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
         for (int i = 0; i < 16; ++i) w[hf * 16 + i] = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
       }
+      if (warp == W_CV0 && h == 1) FA2_STAMP(70);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_QKVEMPTY));                         // accumulator drained: the next projection may start
@@ -435,11 +439,14 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         if (part == 2) mbar_wait_guard(bar(B_OFULL), (n - 1) & 1);
         else mbar_wait_guard(bar(B_SFULL), (n - 1) & 1);
       }
+      if (warp == W_CV0 && h == 1) FA2_STAMP(71);
       uint8_t* dst = sptr + (part == 0 ? OFF_Q : (part == 1 ? OFF_K : OFF_V)) + row * 128;
 #pragma unroll
       for (int c = 0; c < 8; ++c)
         *reinterpret_cast<uint4*>(dst + ((((uint32_t)c) ^ sw) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+      if (warp == W_CV0 && h == 1) FA2_STAMP(72);
       fence_proxy_async_smem();
+      if (warp == W_CV0 && h == 1) FA2_STAMP(73);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(part == 2 ? B_VREADY : B_QKREADY));
       if (warp == W_CV0) FA2_STAMP(31 + 2 * h);
