@@ -203,7 +203,7 @@ int vitmarl_vit_set_fused(int mode);
 /* Debug hook: device buffer (>= 512 int64) that receives clock64() phase stamps of the fused block kernels
  * (CTA 0, second tile; [0,256) MLP block, [256,512) attention block); NULL switches it off. */
 int vitmarl_debug_fused_mlp_timeline(long long* device_buf);
-/* Debug hook: tuning switches of the fused block kernels (0 = defaults; bits 0..7 attention block, bits 8..11 MLP block). */
+/* Debug hook: tuning switches of the fused attention block (0 = defaults; see FusedAttn2Params::flags). */
 int vitmarl_debug_set_flags(int flags);
 
 /* Measurement hook: CUDA-event timing (on the launch stream) of every tensor-core GEMM launch

@@ -64,7 +64,6 @@ constexpr int FIRST_CW = 4, FIRST_AUX = FIRST_CW + NGW;
 constexpr int THREADS = 32 * (FIRST_CW + NCW);
 constexpr int TMEM_COLS = 512;                                    // acc1[2] @ 0,128 ; acc2 @ 256 (192 cols)
 constexpr int ACC2_COL = 256;
-constexpr int LN_AFTER_CHUNK = 3;                                 // the next tile's LayerNorm runs after this GELU chunk
 enum { B_XFULL = 0, B_OUTREADY = B_XFULL + NXB, B_XNREADY, B_ACC2FULL = B_XNREADY + NXB, B_ACC2EMPTY,
        B_ACC1FULL, B_HREADY = B_ACC1FULL + NB,
        B_W1FULL = B_HREADY + NB, B_W1EMPTY = B_W1FULL + NS1, B_W2FULL = B_W1EMPTY + NS1, B_W2EMPTY = B_W2FULL + NS2,
@@ -81,7 +80,6 @@ struct FusedMlp2Params {
   const float* b2;              // [D]
   float eps;
   long long* dbg;               // optional clock64 timeline of cluster 0 / leader (second tile); null in production
-  int ln_after;                 // the next tile's LayerNorm runs after this GELU chunk (tuning switch)
 };
 
 #define FM2_WAIT(acc, call) do { if (p.dbg) { const long long t__ = clock64(); call; if (j == 1) acc += clock64() - t__; } else { call; } } while (0)
@@ -409,8 +407,6 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 }
 
 static long long* g_fmlp2_dbg = nullptr;
-static int g_fmlp2_ln_after = fmlp2::LN_AFTER_CHUNK;
-void fused_mlp2_set_flags(int f) { g_fmlp2_ln_after = (f >= 0 && f < fmlp2::NCHUNK) ? f : fmlp2::LN_AFTER_CHUNK; }
 void fused_mlp2_set_debug(long long* buf) { g_fmlp2_dbg = buf; }
 
 bool fused_mlp2_supported(int D, int hidden) { return D == fmlp2::D && hidden == fmlp2::HID; }
@@ -427,7 +423,7 @@ int launch_fused_mlp2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16
   if ((rc = make_tmap_2d_bf16(&tmOut, out, M, D, (uint64_t)D * 2, TM, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmW1, w1f, HID, D, (uint64_t)D * 2, HC / 2, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmW2, w2h, fmlp2::D, HID, (uint64_t)HID * 2, fmlp2::D / 2, 64))) return rc;
-  FusedMlp2Params p{M, x, reinterpret_cast<const uint32_t*>(b1p), b2, eps, g_fmlp2_dbg, g_fmlp2_ln_after};
+  FusedMlp2Params p{M, x, reinterpret_cast<const uint32_t*>(b1p), b2, eps, g_fmlp2_dbg};
   cudaError_t e = cudaFuncSetAttribute(fused_mlp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return check_cuda(e);
   const int pair_tiles = (M + 2 * TM - 1) / (2 * TM);

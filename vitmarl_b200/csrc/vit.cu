@@ -444,7 +444,6 @@ extern "C" int vitmarl_debug_fused_mlp_timeline(long long* device_buf) {
 // Tuning switches of the fused kernels (debug / experiments; 0 = defaults).
 extern "C" int vitmarl_debug_set_flags(int flags) {
   fused_attn2_set_flags(flags & 0xff);
-  fused_mlp2_set_flags(((flags >> 8) & 0xf) - 1);      // bits 8..11: 1 + GELU chunk after which the next tile's LayerNorm runs (0 = default)
   return VITMARL_OK;
 }
 

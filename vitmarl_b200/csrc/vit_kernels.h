@@ -77,7 +77,6 @@ int launch_fused_mlp2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16
                       const __nv_bfloat16* w2h, const float* b2, int M, int D, int hidden, float eps);
 bool fused_mlp2_supported(int D, int hidden);
 void fused_mlp2_set_debug(long long* buf);
-void fused_mlp2_set_flags(int ln_after_chunk);
 
 // Second-generation fused attention block on FOLDED parameters (vit_fold.cu): wqkvf = Wqkv.diag(gamma) with the Q rows scaled
 // by log2(e)/8, bqp = bf16 folded Q bias, bof = bo + Wo.(bv + Wv.beta).  `out` may alias `x`
