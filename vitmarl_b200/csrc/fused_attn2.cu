@@ -50,7 +50,8 @@ constexpr int OFF_MISC = OFF_BAR + 256;
 constexpr int MISC_BYTES = 128 * 3 * 8 + D * 2 + D * 4 + 128 * 2 * 8 + 2 * 128 * 4;   // LN partials [128][3] float2, bq' (bf16), bo' (fp32), softmax partials [128][2] float2, 1/sum [2][128]
 constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;
 constexpr int W_TMA = 0, W_MMA = 1, W_IO = 2, W_MMA2 = 3, W_SM0 = 4, W_CV0 = 12;   // + 8 softmax warps 4..11, 12 conversion warps 12..23
-constexpr int N_CV = 12, N_SM = 8, N_OE = 8;   // conversion / softmax warps; conversion warps that run the O epilogue (parts 0, 1)
+constexpr int N_CV = 12, N_SM = 8, N_OE = 4;   // conversion / softmax warps; conversion warps that run the O epilogue (part 2: the V warps,
+                                                // which wait for P.V anyway -- the Q / K warps stay decoupled from the softmax chain)
 constexpr int THREADS = 32 * (W_CV0 + N_CV);       // 768
 constexpr int TMEM_COLS = 512;
 constexpr int COL_XN = 0, COL_QKV = 96, COL_S = 288, COL_O = 416, COL_PROJ = 288;
@@ -193,7 +194,9 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       for (int j = 0; j < nt; ++j) {
         for (int h = 0; h + 1 < NH; ++h, ++n) {
           mbar_wait_guard(bar(B_QKVEMPTY), n & 1);             // accumulator of head n drained (early in its epilogue)
-          mbar_wait_guard(bar(B_SISSUED), n & 1);              // S(n) is in the pipe: the long projection queues BEHIND the short S product
+          // default: wait until S(n) is in the pipe so that the long projection queues BEHIND the short S product;
+          // flag bit 2: issue the projection at once (the phase is then consumed after the issue -- every phase must be)
+          if (!(p.flags & 4)) mbar_wait_guard(bar(B_SISSUED), n & 1);
           if (p.flags & 1) mbar_wait_guard(bar(B_SFULL), n & 1); // S(n) first: the projection then overlaps the softmax, not S / P.V
           tc_fence_after();
           FA2_STAMP(101 + 4 * h);
@@ -203,6 +206,7 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             if (h + 2 == NH) umma_commit(bar(B_XNFREE));       // last read of LN(x): the next tile's LayerNorm may overwrite XN
           }
           __syncwarp();
+          if (p.flags & 4) mbar_wait_guard(bar(B_SISSUED), n & 1);
         }
         ++n;                                                   // n = 3 (j + 1): heads of this tile all issued
         // ---- tile boundary: this tile's output projection and the next tile's first QKV projection (order = ring order) ----
@@ -382,29 +386,32 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       asm volatile("bar.sync 1, 384;" ::: "memory");                       // ln_part reuse safety
     };
 
-    // ---- O_h epilogue (parts 0, 1): normalise by the row's 1 / sum, convert, K-block h of the projection's A operand ----
+    // ---- O_h epilogue (part 2 warps, thread = row): normalise by the row's 1 / sum, convert, K-block h of the projection's A operand ----
     auto o_epilogue = [&](int j, int h, uint32_t n) {
-      if (part == 2) return;
+      if (part != 2) return;
       mbar_wait_guard(bar(B_OFULL), n & 1);
       if (h == 0) mbar_wait_guard(bar(B_OCFREE), (j & 1) ^ 1);             // previous tile's output store has read the staging tile
       tc_fence_after();
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + tm_lane + COL_O + part * 32, r);
-      tmem_ld_wait();
-      tc_fence_before();
       const float inv = s_inv[(n & 1) * 128 + row];
       uint8_t* orow = sptr + OFF_OC + h * KBLK + row * 128;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<uint4*>(orow + ((((uint32_t)(part * 4 + c)) ^ sw) << 4)) =
-            make_uint4(pack_bf16(__uint_as_float(r[8 * c]) * inv, __uint_as_float(r[8 * c + 1]) * inv),
-                       pack_bf16(__uint_as_float(r[8 * c + 2]) * inv, __uint_as_float(r[8 * c + 3]) * inv),
-                       pack_bf16(__uint_as_float(r[8 * c + 4]) * inv, __uint_as_float(r[8 * c + 5]) * inv),
-                       pack_bf16(__uint_as_float(r[8 * c + 6]) * inv, __uint_as_float(r[8 * c + 7]) * inv));
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + tm_lane + COL_O + hf * 32, r);
+        tmem_ld_wait();
+        if (hf == 1) tc_fence_before();
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(orow + ((((uint32_t)(hf * 4 + c)) ^ sw) << 4)) =
+              make_uint4(pack_bf16(__uint_as_float(r[8 * c]) * inv, __uint_as_float(r[8 * c + 1]) * inv),
+                         pack_bf16(__uint_as_float(r[8 * c + 2]) * inv, __uint_as_float(r[8 * c + 3]) * inv),
+                         pack_bf16(__uint_as_float(r[8 * c + 4]) * inv, __uint_as_float(r[8 * c + 5]) * inv),
+                         pack_bf16(__uint_as_float(r[8 * c + 6]) * inv, __uint_as_float(r[8 * c + 7]) * inv));
+      }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) { mbar_arrive(bar(B_OCREADY)); if (h == NH - 1) mbar_arrive(bar(B_OCDONE)); }
-      if (warp == W_CV0) FA2_STAMP(13 + 4 * h);
+      if (warp == W_CV0 + 8) FA2_STAMP(13 + 4 * h);
     };
 
     // ---- QKV epilogue of head n: 64 accumulator columns of Q_h, K_h or V_h -> bf16 -> swizzled operand tile in smem ----
@@ -521,7 +528,7 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 }
 
 static long long* g_fattn2_dbg = nullptr;
-static int g_fattn2_flags = 0;
+static int g_fattn2_flags = 4;
 void fused_attn2_set_flags(int f) { g_fattn2_flags = f; }
 void fused_attn2_set_debug(long long* buf) { g_fattn2_dbg = buf; }
 
