@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "common.cuh"
 
@@ -262,7 +263,12 @@ __device__ __forceinline__ void mbar_wait_guard(uint32_t bar, uint32_t parity) {
     if ((++polls & 1023u) == 0) {
       const long long t = clock64();
       if (t0 == 0) t0 = t;
-      else if (t - t0 > 4000000000LL) __trap();
+      else if (t - t0 > 4000000000LL) {
+#ifdef VITMARL_WATCHDOG_PRINT   // names the barrier that hung (debug builds only: the printf costs a stack frame and spills)
+        if ((threadIdx.x & 31) == 0) printf("vitmarl watchdog: block %d warp %d stuck on mbarrier +0x%x parity %u\n", blockIdx.x, threadIdx.x >> 5, bar & 0x3ff, parity);
+#endif
+        __trap();
+      }
     }
   }
 }
