@@ -58,7 +58,7 @@ constexpr int OFF_BAR = OFF_W2 + NS2 * S2_BYTES;
 constexpr int OFF_MISC = OFF_BAR + 512;
 constexpr int MISC_BYTES = 128 * 4 * 8 + HID * 2 + D * 4;         // LN partials [128][2] float2 (+ spare), b1' (bf16), b2 (packed bf16)
 constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;
-constexpr int NGW = 8, NAW = 8;                                   // GELU warps / aux warps (LayerNorm + final epilogue) per CTA
+constexpr int NGW = 8, NAW = 8;                                     // GELU warps / aux warps (LayerNorm + final epilogue) per CTA
 constexpr int NCW = NGW + NAW;
 constexpr int FIRST_CW = 4, FIRST_AUX = FIRST_CW + NGW;
 constexpr int THREADS = 32 * (FIRST_CW + NCW);
@@ -259,10 +259,11 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint32_t tm_lane = (uint32_t)(quad * 32) << 16;
     const uint32_t sw = (uint32_t)(row & 7);
     if (warp < FIRST_AUX) {
-      // =============================== GELU warps (4..11): thread = (row, 64 of the chunk's 128 columns) ===============================
+      // =============================== GELU warps: thread = (row, 32 or 64 of the chunk's 128 columns) ===============================
       // The GELU epilogue is bound by the MUFU pipe (tanh: 16 lanes/clk/SM -> ~1000 cycles per chunk whatever the warp count),
       // so it gets its own warps and nothing else: LayerNorm and the final epilogue run concurrently on the aux warps.
-      const int ch = (warp - FIRST_CW) >> 2;   // column half (0..1)
+      constexpr int GROUPS = 4 / (NGW / 4);    // 32-column groups of a chunk per thread (NGW = 16 -> 1, NGW = 8 -> 2)
+      const int cg = (warp - FIRST_CW) >> 2;   // column group set (0 .. NGW/4 - 1)
       const uint32_t l_hready = mapa_rank(bar(B_HREADY), 0);
       int g = 0;
       long long w_a1f = 0;
@@ -275,8 +276,8 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           tc_fence_after();
           if (stamp) FM2_STAMP(10 + 4 * c);
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int c32 = ch * 2 + hh;                                    // 32-column group of the chunk
+          for (int hh = 0; hh < GROUPS; ++hh) {
+            const int c32 = cg * GROUPS + hh;                               // 32-column group of the chunk
             uint32_t r0[32];
             tmem_ld_32x32(tmem_base + tm_lane + b * HC + c32 * 32, r0);
             tmem_ld_wait();
@@ -302,7 +303,7 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
       if (p.dbg && blockIdx.x == 0 && warp == FIRST_CW && lane == 0) p.dbg[210] = w_a1f;
     } else {
-      // =============================== aux warps (12..19): LayerNorm + final epilogue, thread = (row, 96 of the 192 columns) ===============================
+      // =============================== aux warps: LayerNorm + final epilogue, thread = (row, 96 of the 192 columns) ===============================
       const int half = (warp - FIRST_AUX) >> 2;
       const int col0 = half * 96;
       const uint32_t l_xnready = mapa_rank(bar(B_XNREADY), 0), l_acc2empty = mapa_rank(bar(B_ACC2EMPTY), 0);
