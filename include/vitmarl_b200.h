@@ -186,7 +186,10 @@ long long vitmarl_vit_param_elems(const VitmarlVitShape* s, int index, int* is_b
 /* Bytes of caller-owned activation workspace for fwd (save_for_bwd = 0) or fwd+bwd (1). */
 size_t vitmarl_vit_workspace_bytes(const VitmarlVitShape* s, int save_for_bwd);
 
-/* y[B,D] (fp32) = ViT(x[B,H,W,C] bf16).  Replaces `module.apply({'params': p}, x)`. */
+/* y[B,D] (fp32) = ViT(x[B,H,W,C] bf16).  Replaces `module.apply({'params': p}, x)`.
+ * save_for_bwd: 0 inference, 1 keep the activations vitmarl_vit_bwd needs, 2 inference that REUSES the folded
+ * parameters a previous call (mode 0, same workspace, same batch size, unchanged `params` contents) left in the
+ * workspace -- the rollout loop between two optimiser updates; skips the two parameter-fold launches. */
 int vitmarl_vit_fwd(void* stream, const VitmarlVitShape* s, const void* const* params,
                     const void* x, float* y, void* workspace, size_t workspace_bytes, int save_for_bwd);
 

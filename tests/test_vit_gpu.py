@@ -141,3 +141,24 @@ def test_rejects_unsupported_shapes():
     enc = vit.ViTEncoder(vit.ViTConfig(64, 64, 2, 4, 192, 1, 3, 768))     # 256 tokens: not the 64-token tile
     with pytest.raises(_capi.VitmarlError):
         enc.apply({"params": vit.init_params(enc.cfg, 0, "cuda")}, torch.zeros(2, 64, 64, 2, device="cuda"))
+
+
+def test_folded_parameter_reuse_in_the_rollout_loop():
+    """save_for_bwd = 2: the fold launches are skipped and the folded parameters of the previous call are reused."""
+    cfg = vit.VIT_PARITY
+    params = _perturbed_params(cfg, 5)
+    x = _images(40, cfg, 2)
+    enc = vit.ViTEncoder(cfg)
+    packed = vit.pack_params(cfg, params)
+    y0 = enc.apply_packed(packed, x).clone()
+    y1 = enc.apply_packed(packed, x, params_unchanged=True).clone()
+    assert torch.equal(y0, y1)
+    # an optimiser step changes the table's contents: the caller must NOT claim "unchanged", and the result must move
+    packed[3 + 8].mul_(1.5)                              # block 0 fc1.kernel
+    y2 = enc.apply_packed(packed, x).clone()
+    assert not torch.equal(y0, y2)
+    y3 = enc.apply_packed(packed, x, params_unchanged=True)
+    assert torch.equal(y2, y3)
+    # a different batch size lays the workspace out differently: the claim is ignored and the parameters are folded again
+    y4 = enc.apply_packed(packed, x[:8], params_unchanged=True)
+    assert torch.equal(y4, y2[:8])

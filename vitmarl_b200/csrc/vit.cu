@@ -152,7 +152,7 @@ static GemmDesc gd(int M, int N, int K, const bf16* A, int lda, bool amn, const 
   return g;
 }
 
-static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, const bf16* x, float* y, uint8_t* ws, bool save) {
+static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, const bf16* x, float* y, uint8_t* ws, bool save, bool reuse_folded = false) {
   const Ws w = layout(d, save);
   const int M = d.M, D = d.D;
   auto PB = [&](int i) { return static_cast<const bf16*>(prm[i]); };
@@ -175,7 +175,7 @@ static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, c
   const bool fuse_attn2 = !save && g_fused_mode == 1 && fused_attn2_supported(D, d.heads, d.T) && d.L * 5 <= 64;
   auto FW = [&](int l, size_t o) { return reinterpret_cast<bf16*>(ws + w.fold + (size_t)l * w.sz_fold + o); };
   auto FF = [&](int l, size_t o) { return reinterpret_cast<float*>(ws + w.fold + (size_t)l * w.sz_fold + o); };
-  if (fuse_mlp2 || fuse_attn2) {
+  if ((fuse_mlp2 || fuse_attn2) && !reuse_folded) {
     FoldJobs jobs{}, jobs2{};
     for (int l = 0; l < d.L; ++l) {
       if (fuse_mlp2) {
@@ -359,7 +359,7 @@ extern "C" long long vitmarl_vit_param_elems(const VitmarlVitShape* s, int index
 extern "C" size_t vitmarl_vit_workspace_bytes(const VitmarlVitShape* s, int save_for_bwd) {
   Dims d;
   if (get_dims(s, d)) return 0;
-  return layout(d, save_for_bwd != 0).total;
+  return layout(d, save_for_bwd == 1).total;
 }
 
 extern "C" int vitmarl_vit_fwd(void* stream, const VitmarlVitShape* s, const void* const* params, const void* x, float* y,
@@ -368,8 +368,9 @@ extern "C" int vitmarl_vit_fwd(void* stream, const VitmarlVitShape* s, const voi
   VM_TRY(get_dims(s, d));
   if (d.B == 0) return VITMARL_OK;
   if (!params || !x || !y || !workspace) return VITMARL_EINVAL;
-  if (workspace_bytes < layout(d, save_for_bwd != 0).total) { set_last_error("vit_fwd: workspace too small"); return VITMARL_EINVAL; }
-  return vit_forward(static_cast<cudaStream_t>(stream), d, params, static_cast<const bf16*>(x), y, static_cast<uint8_t*>(workspace), save_for_bwd != 0);
+  const bool save = save_for_bwd == 1;
+  if (workspace_bytes < layout(d, save).total) { set_last_error("vit_fwd: workspace too small"); return VITMARL_EINVAL; }
+  return vit_forward(static_cast<cudaStream_t>(stream), d, params, static_cast<const bf16*>(x), y, static_cast<uint8_t*>(workspace), save, save_for_bwd == 2);
 }
 
 extern "C" int vitmarl_vit_bwd(void* stream, const VitmarlVitShape* s, const void* const* params, void* workspace,

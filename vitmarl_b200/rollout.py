@@ -22,11 +22,11 @@ __all__ = ["RolloutEncoder", "kernels_per_step"]
 
 def kernels_per_step(vit_cfg: vvit.ViTConfig) -> int:
     """Launches of this library's kernels in one rollout step.
-    ViT-Tiny (D=192, 3 heads): 1 env-step + 2 parameter-fold launches + patchify + patch-embed GEMM
-    + L x (fused attention block + fused MLP block) + final LN/pool.  Other shapes run the unfused sequence: (1 + 4 L) GEMMs + 2 L LayerNorm + L attention."""
+    ViT-Tiny (D=192, 3 heads): 1 env-step + patchify + patch-embed GEMM + L x (fused attention block + fused MLP block)
+    + final LN/pool (the 2 parameter-fold launches run only on the engine's first step).  Other shapes run the unfused sequence: (1 + 4 L) GEMMs + 2 L LayerNorm + L attention."""
     L = vit_cfg.depth
     if vit_cfg.dim == 192 and vit_cfg.heads == 3 and vit_cfg.mlp_dim == 768 and vit_cfg.tokens == 64:
-        return 1 + 2 + 1 + 1 + 2 * L + 1
+        return 1 + 1 + 1 + 2 * L + 1
     return 1 + 1 + (1 + 4 * L) + 2 * L + L + 1
 
 
@@ -53,7 +53,8 @@ class RolloutEncoder:
         self.state, out = venv.step(self.cfg, self.state, msgs, n_levels=self.n_levels, want_obs=True,
                                     image_hw=(c.img_h, c.img_w), image_dtype=torch.bfloat16, inplace=True)
         self.last = out
-        return self.encoder.apply_packed(self.packed, out.image)
+        # the parameters are fixed for the lifetime of this engine (a new one is built after an optimiser update)
+        return self.encoder.apply_packed(self.packed, out.image, params_unchanged=True)
 
     def step_host(self, msgs_pinned: torch.Tensor):
         """Host-buffer entry: H2D of the step's messages, the step, D2H of the encoding and the vision tensor."""

@@ -129,6 +129,7 @@ class ViTEncoder:
         self._packed = None
         self._ws = None
         self._ws_shape = None
+        self._fold_key = None
 
     # ---- flax-like surface -------------------------------------------------------------------------
     def init(self, seed: int = 0, x: Optional[torch.Tensor] = None, device="cuda") -> Dict:
@@ -158,7 +159,11 @@ class ViTEncoder:
             self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=device)
         return self._ws
 
-    def apply_packed(self, packed, x: torch.Tensor, *, train: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def apply_packed(self, packed, x: torch.Tensor, *, train: bool = False, out: Optional[torch.Tensor] = None,
+                     params_unchanged: bool = False) -> torch.Tensor:
+        """``params_unchanged=True`` (inference only) tells the library that the CONTENTS of ``packed`` are the same as in the
+        previous call, so the folded parameters it left in the workspace are reused (the rollout loop between two optimiser
+        updates).  It is honoured only when that previous call used the same workspace, batch size and table."""
         if not x.is_cuda:
             raise _capi.VitmarlError(_capi.ENODEVICE, "ViT input must be a CUDA tensor (there is no CPU fallback)")
         c = self.cfg
@@ -170,9 +175,12 @@ class ViTEncoder:
         ws = self._workspace(shape, train, x.device)
         y = out if out is not None else torch.empty((B, c.dim), dtype=torch.float32, device=x.device)
         ptrs = (ctypes.c_void_p * len(packed))(*[t.data_ptr() for t in packed])
+        key = (ws.data_ptr(), B, id(packed))
+        mode = 1 if train else (2 if (params_unchanged and self._fold_key == key) else 0)
         rc = _capi.lib().vitmarl_vit_fwd(torch.cuda.current_stream().cuda_stream, ctypes.byref(shape), ptrs, x.data_ptr(),
-                                         y.data_ptr(), ws.data_ptr(), ws.numel(), int(train))
+                                         y.data_ptr(), ws.data_ptr(), ws.numel(), mode)
         _capi.check(rc)
+        self._fold_key = None if train else key          # a training pass lays the workspace out differently
         self._ws_shape = (B, train)
         return y
 
