@@ -29,29 +29,39 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 }  // namespace g2
 
-template <int BN>
+template <int BN, bool TMAEPI>
 struct Gemm2Cfg {
-  static constexpr int kStages = 6;
+  static constexpr int kStages = TMAEPI ? 4 : 6;
   static constexpr int kABytes = g2::BM * g2::BK * 2;          // 16 KB
   static constexpr int kBBytes = (BN / 2) * g2::BK * 2;        // this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kOutBytes = g2::BM * BN * 2;            // bf16 output tile of this CTA, BN/64 swizzled [128 x 64] sub-tiles
   static constexpr int kTmemCols = BN * 2 <= 128 ? 128 : (BN * 2 <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + (TMAEPI ? 2 * kOutBytes : 0) + 1024 + 256;
 };
 
-template <int BN>
+// TMAEPI = true (bf16 outputs): the epilogue goes through shared memory.  A tcgen05.ld hands every thread one ROW of the
+// accumulator, so per-thread global loads / stores touch 32 different cache lines per warp instruction (the residual,
+// the position embedding and the output all have that shape) and the epilogue -- not the tensor pipe -- bounded the
+// small-K projections of the ViT.  Here the addend tile (residual, or a [128, N] bf16 position-embedding tile) is
+// TMA-loaded into a swizzled staging tile while the mainloop runs, each thread adds its row segment in place, and the
+// tile (plus, for bias+GELU, a second tile with the pre-activation saved for backward) leaves through TMA stores.
+template <int BN, bool TMAEPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
-gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+             const __grid_constant__ CUtensorMap tmC2, const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   using namespace g2;
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, TMAEPI>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t out_base = smem_base + Cfg::kStages * Cfg::kStageBytes;                 // TMAEPI: two staging tiles
+  const uint32_t bar_base = out_base + (TMAEPI ? 2 * Cfg::kOutBytes : 0);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  auto res_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::kStages + 5 + b); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -64,7 +74,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kEpiWarps); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kEpiWarps); mbar_init(res_bar(a), 1); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -125,8 +135,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
       }
     }
-  } else {
-    // ================= epilogue (both CTAs; warps 2..9) =================
+  } else if constexpr (!TMAEPI) {
+    // ================= epilogue (both CTAs; warps 2..9): per-thread global accesses =================
     const int quad = warp & 3;
     const int chalf = (warp - 2) >> 2;
     constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
@@ -151,6 +161,98 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_bar(acc) & kPeerMask);
     }
+  } else {
+    // ================= epilogue (both CTAs; warps 2..9): staged in shared memory, TMA in / out =================
+    extern __shared__ uint8_t smem_gen[];
+    uint8_t* sgen = smem_gen + (smem_base - smem_u32(smem_gen));          // generic pointer to the aligned base
+    const int quad = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
+    const int trow = quad * 32 + lane;                                     // row within this CTA's tile
+    const uint32_t sw = (uint32_t)(trow & 7);
+    const bool has_add = p.add_mode != 0;                                  // 1 residual tile, 2 position-embedding tile (row 0)
+    const bool two_out = p.epi == EPI_BIAS_GELU && p.C2 != nullptr;
+    const bool elected = (warp == 2 && lane == 0);
+    int it = 0;
+    for (int w = cluster; w < num_work; w += num_clusters, ++it) {
+      const int tn = w % tiles_n, tm = w / tiles_n;
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      const int buf = two_out ? 0 : (it & 1);
+      const uint32_t res_ph = two_out ? (it & 1) : ((it >> 1) & 1);
+      const int grow0 = tm * 2 * BM + (int)rank * BM;                      // first row of this CTA's tile
+      const uint32_t out0 = out_base + buf * Cfg::kOutBytes, out1 = out_base + Cfg::kOutBytes;
+      if (elected) {
+        // the staging tile(s) of this iteration must have been read by their previous TMA store
+        if (two_out) bulk_wait_read0(); else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (has_add) {                                                     // lands while the mainloop of this tile runs
+          mbar_arrive_expect_tx(res_bar(buf), Cfg::kOutBytes);
+          for (int kb = 0; kb < BN / 64; ++kb)
+            tma_load_2d(out0 + kb * (BM * 128), &tmR, tn * BN + kb * 64, p.add_mode == 1 ? grow0 : 0, res_bar(buf));
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(tfull_bar(acc), acc_ph);
+      if (has_add) mbar_wait(res_bar(buf), res_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+      uint8_t* o0 = sgen + (out0 - smem_base);
+      uint8_t* o1 = sgen + (out1 - smem_base);
+#pragma unroll 1
+      for (int c = chalf * kColsPerWarp; c < (chalf + 1) * kColsPerWarp; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c, r);
+        tmem_ld_wait();
+        if (c + 32 >= (chalf + 1) * kColsPerWarp) {                        // last read of the accumulator by this warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_bar(acc) & kPeerMask);
+        }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + tn * BN + c + j));   // same address in every lane
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        const uint32_t tile_off = (uint32_t)((c >> 6) * (BM * 128) + trow * 128);
+        const uint32_t ch0 = (uint32_t)((c & 63) >> 3);
+        if (p.epi == EPI_BIAS_GELU) {
+          if (two_out) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(o1 + tile_off + (((ch0 + j) ^ sw) << 4)) =
+                  make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                             pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4* slot = reinterpret_cast<uint4*>(o0 + tile_off + (((ch0 + j) ^ sw) << 4));
+          if (has_add) {
+            const uint4 a = *slot;
+            v[8 * j + 0] += bf16_lo(a.x); v[8 * j + 1] += bf16_hi(a.x); v[8 * j + 2] += bf16_lo(a.y); v[8 * j + 3] += bf16_hi(a.y);
+            v[8 * j + 4] += bf16_lo(a.z); v[8 * j + 5] += bf16_hi(a.z); v[8 * j + 6] += bf16_lo(a.w); v[8 * j + 7] += bf16_hi(a.w);
+          }
+          *slot = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                             pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+        }
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (elected) {
+        for (int kb = 0; kb < BN / 64; ++kb) tma_store_2d(&tmC, out0 + kb * (BM * 128), tn * BN + kb * 64, grow0);
+        if (two_out)
+          for (int kb = 0; kb < BN / 64; ++kb) tma_store_2d(&tmC2, out1 + kb * (BM * 128), tn * BN + kb * 64, grow0);
+        bulk_commit();
+      }
+    }
+    if (elected) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -168,25 +270,46 @@ bool gemm2_supported(const GemmDesc& g) {
   return g_use_2cta && !g.a_mn_major && !g.b_mn_major && g.epi != EPI_ATOMIC_F32 && g.M >= 512 && g.N % 192 == 0;
 }
 
-int launch_gemm2(cudaStream_t stream, const GemmDesc& g) {
+template <bool TMAEPI>
+static int launch_gemm2_t(cudaStream_t stream, const GemmDesc& g, int add_mode, const __nv_bfloat16* add, int add_rows, int add_ld) {
   using namespace g2;
   constexpr int BN = 192;
-  using Cfg = Gemm2Cfg<BN>;
-  CUtensorMap tmA, tmB;
+  using Cfg = Gemm2Cfg<BN, TMAEPI>;
+  CUtensorMap tmA, tmB, tmC, tmC2, tmR;
   int rc;
   if ((rc = make_tmap_2d_bf16(&tmA, g.A, g.M, g.K, (uint64_t)g.lda * 2, BM, BK))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmB, g.B, g.N, g.K, (uint64_t)g.ldb * 2, BN / 2, BK))) return rc;
+  tmC = tmA; tmC2 = tmA; tmR = tmA;                      // placeholders when unused
+  if (TMAEPI) {
+    if ((rc = make_tmap_2d_bf16(&tmC, g.C, g.M, g.N, (uint64_t)g.ldc * 2, BM, 64))) return rc;
+    if (g.C2 && (rc = make_tmap_2d_bf16(&tmC2, g.C2, g.M, g.N, (uint64_t)g.ldc * 2, BM, 64))) return rc;
+    if (add_mode && (rc = make_tmap_2d_bf16(&tmR, add, add_rows, g.N, (uint64_t)add_ld * 2, BM, 64))) return rc;
+  }
   GemmParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K; p.kb_per_split = 0; p.splits = 1;
   p.epi = g.epi; p.C = g.C; p.C2 = g.C2; p.ldc = g.ldc; p.bias = g.bias; p.residual = g.residual; p.ldr = g.ldr;
   p.pos = g.pos; p.pos_period = g.pos_period > 0 ? g.pos_period : 1; p.out_scale = g.out_scale;
-  auto kern = gemm2_kernel<BN>;
+  p.add_mode = TMAEPI ? add_mode : 0;
+  auto kern = gemm2_kernel<BN, TMAEPI>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (err != cudaSuccess) return check_cuda(err);
   const int work = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
   const int clusters = min(work, num_sms() / 2);
-  kern<<<2 * clusters, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  kern<<<2 * clusters, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmC2, tmR, p);
   return check_cuda(cudaGetLastError());
+}
+
+int launch_gemm2(cudaStream_t stream, const GemmDesc& g) {
+  // shared-memory-staged epilogue for bf16 outputs whose addend (if any) is available as a bf16 tile source
+  const bool bf16_out = g.epi == EPI_STORE_BF16 || g.epi == EPI_BIAS_GELU;
+  const bool aligned = (g.ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && (!g.C2 || (reinterpret_cast<uintptr_t>(g.C2) & 15) == 0);
+  if (bf16_out && aligned && !(g.pos && g.residual)) {
+    if (g.residual && (g.ldr % 8) == 0 && (reinterpret_cast<uintptr_t>(g.residual) & 15) == 0 && g.epi == EPI_STORE_BF16)
+      return launch_gemm2_t<true>(stream, g, 1, g.residual, g.M, g.ldr);
+    if (g.pos && g.pos_tile && g.epi == EPI_STORE_BF16) return launch_gemm2_t<true>(stream, g, 2, g.pos_tile, g2::BM, g.N);
+    if (!g.pos && !g.residual) return launch_gemm2_t<true>(stream, g, 0, nullptr, 0, 0);
+  }
+  return launch_gemm2_t<false>(stream, g, 0, nullptr, 0, 0);
 }
 
 }  // namespace vitmarl

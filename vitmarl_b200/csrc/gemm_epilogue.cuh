@@ -20,6 +20,7 @@ struct GemmParams {
   const __nv_bfloat16* residual; int ldr;   // [M, N] bf16 or null
   const float* pos; int pos_period;         // [pos_period, N] fp32 (row % pos_period) or null
   float out_scale;
+  int add_mode;           // shared-memory-staged epilogue (gemm2): 0 no addend, 1 residual tile, 2 position-embedding tile
 };
 
 

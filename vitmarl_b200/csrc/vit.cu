@@ -66,7 +66,7 @@ static size_t param_elems(const Dims& d, int idx, bool* is_matrix) {
 
 // ---- workspace layout -------------------------------------------------------------------------
 struct Ws {
-  size_t patches, x, xm, ln1, ln2, qkv, att, hpre, hact, st1, st2, stf, dA, dB, dC, dH, dQKV, fold, total;
+  size_t patches, x, xm, ln1, ln2, qkv, att, hpre, hact, st1, st2, stf, dA, dB, dC, dH, dQKV, fold, pos_tile, total;
   size_t sz_md, sz_mh, sz_mq, sz_st;   // per-layer strides (bytes)
   size_t sz_fold, f_w1, f_b1, f_w2, f_wqkv, f_bq, f_bv, f_bo;   // inference: folded parameters per layer (vit_fold.cu), offsets within a layer's slot
 };
@@ -94,6 +94,7 @@ static Ws layout(const Dims& d, bool save) {
     w.dA = take(w.sz_md); w.dB = take(w.sz_md); w.dC = take(w.sz_md);
     w.dH = take(w.sz_mh); w.dQKV = take(w.sz_mq);
   }
+  w.pos_tile = take((size_t)128 * d.D * 2);           // bf16 position-embedding tile (addend of the patch-embedding GEMM)
   if (!save) {
     size_t o = 0;
     auto slot = [&](size_t bytes) { size_t r = o; o += al(bytes); return r; };
@@ -198,11 +199,15 @@ static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, c
     VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_fold_params(st, jobs); }));
     if (jobs2.n) VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_fold_params(st, jobs2); }));
   }
+  const bool pos_tiled = 128 % d.T == 0;
+  bf16* pos_tile = reinterpret_cast<bf16*>(ws + w.pos_tile);
+  if (pos_tiled && !reuse_folded) VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_pos_tile(st, PF(P_POS), pos_tile, d.T, D); }));
   // patch embedding: tokens = patches . Wpe^T + b + pos
   VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_patchify(st, x, patches, d.B, d.H, d.W, d.C, d.P); }));
   {
     GemmDesc g = gd(M, D, d.Kp, patches, d.Kp, false, PB(P_PE_W), d.Kp, false, X(0), D, EPI_STORE_BF16);
     g.bias = PF(P_PE_B); g.pos = PF(P_POS); g.pos_period = d.T;
+    if (pos_tiled) g.pos_tile = pos_tile;
     VM_TRY(timed_gemm(st, g));
   }
   for (int l = 0; l < d.L; ++l) {

@@ -39,6 +39,19 @@ __global__ void __launch_bounds__(256) fold_params_kernel(const __grid_constant_
   }
 }
 
+// pos [T, D] fp32 -> bf16 [128, D], rows repeated with period T (T divides 128): the addend tile of the patch-embedding GEMM
+__global__ void __launch_bounds__(256) pos_tile_kernel(const float* __restrict__ pos, __nv_bfloat16* __restrict__ out, int T, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 128 * D) return;
+  const int r = i / D, c = i - r * D;
+  out[i] = __float2bfloat16_rn(pos[(size_t)(r % T) * D + c]);
+}
+
+int launch_pos_tile(cudaStream_t s, const float* pos, __nv_bfloat16* out, int T, int D) {
+  pos_tile_kernel<<<(128 * D + 255) / 256, 256, 0, s>>>(pos, out, T, D);
+  return check_cuda(cudaGetLastError());
+}
+
 int launch_fold_params(cudaStream_t s, const FoldJobs& jobs) {
   if (jobs.n <= 0) return VITMARL_OK;
   int max_n = 0;

@@ -26,6 +26,8 @@ struct GemmDesc {
   const float* bias = nullptr;
   const __nv_bfloat16* residual = nullptr; int ldr = 0;
   const float* pos = nullptr; int pos_period = 0;
+  const __nv_bfloat16* pos_tile = nullptr;   // optional [128, N] bf16 copy of `pos` tiled to 128 rows (pos_period must divide 128):
+                                             // lets the 2-CTA GEMM add it through its shared-memory-staged epilogue
   float out_scale = 1.0f;
 };
 
@@ -95,6 +97,7 @@ struct FoldJob {
 };
 struct FoldJobs { FoldJob job[64]; int n; };
 int launch_fold_params(cudaStream_t s, const FoldJobs& jobs);
+int launch_pos_tile(cudaStream_t s, const float* pos, __nv_bfloat16* out, int T, int D);   // [T,D] fp32 -> [128,D] bf16 (T | 128)
 
 // elementwise helpers
 int launch_gelu_bwd(cudaStream_t s, const __nv_bfloat16* pre, const __nv_bfloat16* dy, __nv_bfloat16* dx, size_t n);   // dx = dy * gelu'(pre)
