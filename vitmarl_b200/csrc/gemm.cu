@@ -27,28 +27,33 @@ constexpr int BM = 128, BK = 64;
 constexpr int kEpiWarps = 8;                       // 2 warps per TMEM lane quadrant, each owns half of the tile's columns
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 
-template <int BN>
+template <int BN, bool STAGED>
 struct GemmCfg {
-  static constexpr int kStages = BN >= 192 ? 5 : (BN >= 128 ? 6 : 8);
+  // STAGED: two bf16 staging tiles for the shared-memory epilogue (gemm_epilogue.cuh) take the place of ring stages
+  static constexpr int kStages = STAGED ? (BN >= 192 ? 3 : (BN >= 128 ? 4 : 6)) : (BN >= 192 ? 5 : (BN >= 128 ? 6 : 8));
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kOutBytes = BM * BN * 2;
   static constexpr int kTmemCols = BN * 2 <= 128 ? 128 : (BN * 2 <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + (STAGED ? 2 * kOutBytes : 0) + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool STAGED>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+            const __grid_constant__ CUtensorMap tmC2, const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
+  using Cfg = GemmCfg<BN, STAGED>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t out_base = smem_base + Cfg::kStages * Cfg::kStageBytes;                 // STAGED: two staging tiles
+  const uint32_t bar_base = out_base + (STAGED ? 2 * Cfg::kOutBytes : 0);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  auto res_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::kStages + 5 + b); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = p.N / BN;
@@ -59,7 +64,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); mbar_init(res_bar(a), 1); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -133,6 +138,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         __syncwarp();
       }
     }
+  } else if constexpr (STAGED) {
+    // ================= epilogue (warps 2..9): staged in shared memory, TMA in / out (gemm_epilogue.cuh; never split-K) =================
+    extern __shared__ uint8_t smem_gen[];
+    uint8_t* sgen = smem_gen + (smem_base - smem_u32(smem_gen));
+    int it = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      const int tn = w % tiles_n, tm = w / tiles_n;
+      const int acc = it & 1;
+      const uint32_t tbar = tempty_bar(acc);
+      staged_epilogue_tile<BN>(p, &tmC, &tmC2, &tmR, sgen, smem_base, out_base, res_bar(0), tfull_bar(acc), (it >> 1) & 1,
+                               tmem_base + acc * BN, it, tn * BN, tm * BM, warp, lane, [&] { mbar_arrive(tbar); });
+    }
+    if (warp == 2 && lane == 0) bulk_wait0();
   } else {
     // ================= epilogue (warps 2..9) =================
     const int quad = warp & 3;
@@ -182,10 +200,10 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm_t(cudaStream_t stream, const GemmDesc& g) {
-  using Cfg = GemmCfg<BN>;
-  CUtensorMap tmA, tmB;
+template <int BN, bool A_MN, bool B_MN, bool STAGED>
+static int launch_gemm_t2(cudaStream_t stream, const GemmDesc& g, int add_mode, const __nv_bfloat16* add, int add_rows, int add_ld) {
+  using Cfg = GemmCfg<BN, STAGED>;
+  CUtensorMap tmA, tmB, tmC, tmC2, tmR;
   int rc;
   // K-major operand: tensor [rows = M or N, cols = K], box [BM or BN rows, 64 cols]
   // MN-major operand: tensor [rows = K, cols = M or N], box [64 rows, 64 cols]
@@ -195,6 +213,12 @@ static int launch_gemm_t(cudaStream_t stream, const GemmDesc& g) {
   if (!B_MN) rc = make_tmap_2d_bf16(&tmB, g.B, g.N, g.K, (uint64_t)g.ldb * 2, BN, BK);
   else rc = make_tmap_2d_bf16(&tmB, g.B, g.K, g.N, (uint64_t)g.ldb * 2, BK, 64);
   if (rc) return rc;
+  tmC = tmA; tmC2 = tmA; tmR = tmA;                      // placeholders when unused
+  if (STAGED) {
+    if ((rc = make_tmap_2d_bf16(&tmC, g.C, g.M, g.N, (uint64_t)g.ldc * 2, BM, 64))) return rc;
+    if (g.C2 && (rc = make_tmap_2d_bf16(&tmC2, g.C2, g.M, g.N, (uint64_t)g.ldc * 2, BM, 64))) return rc;
+    if (add_mode && (rc = make_tmap_2d_bf16(&tmR, add, add_rows, g.N, (uint64_t)add_ld * 2, BM, 64))) return rc;
+  }
   GemmParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K;
   const int KB = (g.K + BK - 1) / BK;
@@ -207,13 +231,23 @@ static int launch_gemm_t(cudaStream_t stream, const GemmDesc& g) {
   p.splits = (KB + p.kb_per_split - 1) / p.kb_per_split;
   p.epi = g.epi; p.C = g.C; p.C2 = g.C2; p.ldc = g.ldc; p.bias = g.bias; p.residual = g.residual; p.ldr = g.ldr;
   p.pos = g.pos; p.pos_period = g.pos_period > 0 ? g.pos_period : 1; p.out_scale = g.out_scale;
-  auto kern = gemm_kernel<BN, A_MN, B_MN>;
+  p.add_mode = STAGED ? add_mode : 0;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, STAGED>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (err != cudaSuccess) return check_cuda(err);
   const int work = tiles * p.splits;
   const int grid = min(work, num_sms());
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmC2, tmR, p);
   return check_cuda(cudaGetLastError());
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm_t(cudaStream_t stream, const GemmDesc& g) {
+  const __nv_bfloat16* add; int add_rows, add_ld;
+  const int mode = staged_epilogue_mode(g, &add, &add_rows, &add_ld);
+  // the staged epilogue pays off for the epilogue-bound token-dimension GEMMs with a small contraction; others keep the deeper ring
+  if (mode >= 0 && g.M >= 1024 && g.K <= 1536) return launch_gemm_t2<BN, A_MN, B_MN, true>(stream, g, mode, add, add_rows, add_ld);
+  return launch_gemm_t2<BN, A_MN, B_MN, false>(stream, g, 0, nullptr, 0, 0);
 }
 
 template <int BN>

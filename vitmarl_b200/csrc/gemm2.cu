@@ -162,97 +162,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (lane == 0) mbar_arrive_cluster(tempty_bar(acc) & kPeerMask);
     }
   } else {
-    // ================= epilogue (both CTAs; warps 2..9): staged in shared memory, TMA in / out =================
+    // ================= epilogue (both CTAs; warps 2..9): staged in shared memory, TMA in / out (gemm_epilogue.cuh) =================
     extern __shared__ uint8_t smem_gen[];
     uint8_t* sgen = smem_gen + (smem_base - smem_u32(smem_gen));          // generic pointer to the aligned base
-    const int quad = warp & 3;
-    const int chalf = (warp - 2) >> 2;
-    constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
-    const int trow = quad * 32 + lane;                                     // row within this CTA's tile
-    const uint32_t sw = (uint32_t)(trow & 7);
-    const bool has_add = p.add_mode != 0;                                  // 1 residual tile, 2 position-embedding tile (row 0)
-    const bool two_out = p.epi == EPI_BIAS_GELU && p.C2 != nullptr;
-    const bool elected = (warp == 2 && lane == 0);
     int it = 0;
     for (int w = cluster; w < num_work; w += num_clusters, ++it) {
       const int tn = w % tiles_n, tm = w / tiles_n;
       const int acc = it & 1;
-      const uint32_t acc_ph = (it >> 1) & 1;
-      const int buf = two_out ? 0 : (it & 1);
-      const uint32_t res_ph = two_out ? (it & 1) : ((it >> 1) & 1);
-      const int grow0 = tm * 2 * BM + (int)rank * BM;                      // first row of this CTA's tile
-      const uint32_t out0 = out_base + buf * Cfg::kOutBytes, out1 = out_base + Cfg::kOutBytes;
-      if (elected) {
-        // the staging tile(s) of this iteration must have been read by their previous TMA store
-        if (two_out) bulk_wait_read0(); else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        if (has_add) {                                                     // lands while the mainloop of this tile runs
-          mbar_arrive_expect_tx(res_bar(buf), Cfg::kOutBytes);
-          for (int kb = 0; kb < BN / 64; ++kb)
-            tma_load_2d(out0 + kb * (BM * 128), &tmR, tn * BN + kb * 64, p.add_mode == 1 ? grow0 : 0, res_bar(buf));
-        }
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      mbar_wait(tfull_bar(acc), acc_ph);
-      if (has_add) mbar_wait(res_bar(buf), res_ph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
-      uint8_t* o0 = sgen + (out0 - smem_base);
-      uint8_t* o1 = sgen + (out1 - smem_base);
-#pragma unroll 1
-      for (int c = chalf * kColsPerWarp; c < (chalf + 1) * kColsPerWarp; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c, r);
-        tmem_ld_wait();
-        if (c + 32 >= (chalf + 1) * kColsPerWarp) {                        // last read of the accumulator by this warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(tempty_bar(acc) & kPeerMask);
-        }
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + tn * BN + c + j));   // same address in every lane
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
-        }
-        const uint32_t tile_off = (uint32_t)((c >> 6) * (BM * 128) + trow * 128);
-        const uint32_t ch0 = (uint32_t)((c & 63) >> 3);
-        if (p.epi == EPI_BIAS_GELU) {
-          if (two_out) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(o1 + tile_off + (((ch0 + j) ^ sw) << 4)) =
-                  make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                             pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4* slot = reinterpret_cast<uint4*>(o0 + tile_off + (((ch0 + j) ^ sw) << 4));
-          if (has_add) {
-            const uint4 a = *slot;
-            v[8 * j + 0] += bf16_lo(a.x); v[8 * j + 1] += bf16_hi(a.x); v[8 * j + 2] += bf16_lo(a.y); v[8 * j + 3] += bf16_hi(a.y);
-            v[8 * j + 4] += bf16_lo(a.z); v[8 * j + 5] += bf16_hi(a.z); v[8 * j + 6] += bf16_lo(a.w); v[8 * j + 7] += bf16_hi(a.w);
-          }
-          *slot = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                             pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-        }
-      }
-      fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (elected) {
-        for (int kb = 0; kb < BN / 64; ++kb) tma_store_2d(&tmC, out0 + kb * (BM * 128), tn * BN + kb * 64, grow0);
-        if (two_out)
-          for (int kb = 0; kb < BN / 64; ++kb) tma_store_2d(&tmC2, out1 + kb * (BM * 128), tn * BN + kb * 64, grow0);
-        bulk_commit();
-      }
+      const uint32_t tbar = tempty_bar(acc) & kPeerMask;
+      staged_epilogue_tile<BN>(p, &tmC, &tmC2, &tmR, sgen, smem_base, out_base, res_bar(0), tfull_bar(acc), (it >> 1) & 1,
+                               tmem_base + acc * BN, it, tn * BN, tm * 2 * BM + (int)rank * BM, warp, lane,
+                               [&] { mbar_arrive_cluster(tbar); });
     }
-    if (elected) bulk_wait0();
+    if (warp == 2 && lane == 0) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -300,15 +222,11 @@ static int launch_gemm2_t(cudaStream_t stream, const GemmDesc& g, int add_mode, 
 }
 
 int launch_gemm2(cudaStream_t stream, const GemmDesc& g) {
-  // shared-memory-staged epilogue for bf16 outputs whose addend (if any) is available as a bf16 tile source
-  const bool bf16_out = g.epi == EPI_STORE_BF16 || g.epi == EPI_BIAS_GELU;
-  const bool aligned = (g.ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && (!g.C2 || (reinterpret_cast<uintptr_t>(g.C2) & 15) == 0);
-  if (bf16_out && aligned && !(g.pos && g.residual)) {
-    if (g.residual && (g.ldr % 8) == 0 && (reinterpret_cast<uintptr_t>(g.residual) & 15) == 0 && g.epi == EPI_STORE_BF16)
-      return launch_gemm2_t<true>(stream, g, 1, g.residual, g.M, g.ldr);
-    if (g.pos && g.pos_tile && g.epi == EPI_STORE_BF16) return launch_gemm2_t<true>(stream, g, 2, g.pos_tile, g2::BM, g.N);
-    if (!g.pos && !g.residual) return launch_gemm2_t<true>(stream, g, 0, nullptr, 0, 0);
-  }
+  const __nv_bfloat16* add; int add_rows, add_ld;
+  const int mode = staged_epilogue_mode(g, &add, &add_rows, &add_ld);
+  // small-K products are epilogue-bound (staged epilogue, 4-stage ring); large-K products are mainloop-bound and keep the
+  // 6-stage ring with the per-thread epilogue hidden behind the next tile's mainloop
+  if (mode >= 0 && g.K <= 1536) return launch_gemm2_t<true>(stream, g, mode, add, add_rows, add_ld);
   return launch_gemm2_t<false>(stream, g, 0, nullptr, 0, 0);
 }
 

@@ -20,7 +20,8 @@ struct GemmParams {
   const __nv_bfloat16* residual; int ldr;   // [M, N] bf16 or null
   const float* pos; int pos_period;         // [pos_period, N] fp32 (row % pos_period) or null
   float out_scale;
-  int add_mode;           // shared-memory-staged epilogue (gemm2): 0 no addend, 1 residual tile, 2 position-embedding tile
+  int add_mode;           // shared-memory-staged epilogue: 0 no addend tile, 1 residual tile (+=), 2 position-embedding tile (+=, row 0),
+                          // 3 pre-activation tile (*= gelu_tanh'(aux): EPI_MUL_GELU_GRAD)
 };
 
 
@@ -94,6 +95,133 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
       }
     }
   }
+}
+
+// ---- shared-memory-staged epilogue of one [128 x BN] bf16 output tile (8 epilogue warps = 256 threads, named barrier 1) ----
+// A tcgen05.ld hands every thread one ROW of the accumulator, so per-thread global loads / stores touch 32 different cache
+// lines per warp instruction (the residual, the pre-activation, the position embedding and the output all have that
+// shape) and the epilogue -- not the tensor pipe -- bounded the small-K projections of the ViT.  Here the addend tile is
+// TMA-loaded into a swizzled staging tile while the mainloop of the same tile runs, each thread combines its row segment
+// in place, and the tile (plus, for bias+GELU, a second tile with the pre-activation saved for backward) leaves through
+// TMA stores.  Staging tiles: BN/64 sub-tiles of [128 rows x 64 cols], 128B swizzle (chunk ^ (row & 7)).
+//   out_base : two staging tiles of 128*BN*2 bytes (alternating per tile; C and C2 when both are written)
+//   res_bar0 : two mbarriers (one per staging tile) for the addend loads
+template <int BN, typename ArriveEmpty>
+__device__ __forceinline__ void staged_epilogue_tile(const GemmParams& p, const CUtensorMap* tmC, const CUtensorMap* tmC2,
+                                                     const CUtensorMap* tmR, uint8_t* sgen, uint32_t smem_base, uint32_t out_base,
+                                                     uint32_t res_bar0, uint32_t tfull_bar, uint32_t acc_ph, uint32_t taddr_acc,
+                                                     int it, int col0, int grow0, int warp, int lane, ArriveEmpty arrive_empty) {
+  constexpr int kOutBytes = 128 * BN * 2;
+  constexpr int kColsPerWarp = BN / 2;
+  const int quad = warp & 3, chalf = (warp - 2) >> 2;
+  const int trow = quad * 32 + lane;
+  const uint32_t sw = (uint32_t)(trow & 7);
+  const bool has_add = p.add_mode != 0;
+  const bool two_out = p.epi == EPI_BIAS_GELU && p.C2 != nullptr;
+  const bool elected = (warp == 2 && lane == 0);
+  const int buf = two_out ? 0 : (it & 1);
+  const uint32_t res_ph = two_out ? (it & 1) : ((it >> 1) & 1);
+  const uint32_t out0 = out_base + buf * kOutBytes, out1 = out_base + kOutBytes;
+  const uint32_t res_bar = res_bar0 + 8u * buf;
+  if (elected) {
+    // the staging tile(s) of this iteration must have been read by their previous TMA store
+    if (two_out) bulk_wait_read0(); else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    if (has_add) {                                                         // lands while the mainloop of this tile runs
+      mbar_arrive_expect_tx(res_bar, kOutBytes);
+      for (int kb = 0; kb < BN / 64; ++kb) tma_load_2d(out0 + kb * (128 * 128), tmR, col0 + kb * 64, p.add_mode == 2 ? 0 : grow0, res_bar);
+    }
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  mbar_wait(tfull_bar, acc_ph);
+  if (has_add) mbar_wait(res_bar, res_ph);
+  tc_fence_after();
+  const uint32_t taddr = taddr_acc + ((uint32_t)(quad * 32) << 16);
+  uint8_t* o0 = sgen + (out0 - smem_base);
+  uint8_t* o1 = sgen + (out1 - smem_base);
+#pragma unroll 1
+  for (int c = chalf * kColsPerWarp; c < (chalf + 1) * kColsPerWarp; c += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + c, r);
+    tmem_ld_wait();
+    if (c + 32 >= (chalf + 1) * kColsPerWarp) {                            // last read of the accumulator by this warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) arrive_empty();
+    }
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c + j));   // same address in every lane
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+    const uint32_t tile_off = (uint32_t)((c >> 6) * (128 * 128) + trow * 128);
+    const uint32_t ch0 = (uint32_t)((c & 63) >> 3);
+    if (p.epi == EPI_BIAS_GELU) {
+      if (two_out) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(o1 + tile_off + (((ch0 + j) ^ sw) << 4)) =
+              make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                         pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4* slot = reinterpret_cast<uint4*>(o0 + tile_off + (((ch0 + j) ^ sw) << 4));
+      if (has_add) {
+        const uint4 a = *slot;
+        const float a8[8] = {bf16_lo(a.x), bf16_hi(a.x), bf16_lo(a.y), bf16_hi(a.y), bf16_lo(a.z), bf16_hi(a.z), bf16_lo(a.w), bf16_hi(a.w)};
+        if (p.add_mode == 3) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[8 * j + k] *= gelu_tanh_grad(a8[k]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[8 * j + k] += a8[k];
+        }
+      }
+      *slot = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                         pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    }
+  }
+  fence_proxy_async_smem();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (elected) {
+    for (int kb = 0; kb < BN / 64; ++kb) tma_store_2d(tmC, out0 + kb * (128 * 128), col0 + kb * 64, grow0);
+    if (two_out)
+      for (int kb = 0; kb < BN / 64; ++kb) tma_store_2d(tmC2, out1 + kb * (128 * 128), col0 + kb * 64, grow0);
+    bulk_commit();
+  }
+}
+
+// Can this GEMM use the staged epilogue?  Returns the addend mode (-1: no) and the addend tile source.
+inline int staged_epilogue_mode(const GemmDesc& g, const __nv_bfloat16** add, int* add_rows, int* add_ld) {
+  *add = nullptr; *add_rows = 0; *add_ld = 0;
+  const bool bf16_out = g.epi == EPI_STORE_BF16 || g.epi == EPI_BIAS_GELU || g.epi == EPI_MUL_GELU_GRAD;
+  const bool aligned = (g.ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && (!g.C2 || (reinterpret_cast<uintptr_t>(g.C2) & 15) == 0);
+  if (!bf16_out || !aligned || (g.pos && g.residual)) return -1;
+  const bool res_ok = g.residual && (g.ldr % 8) == 0 && (reinterpret_cast<uintptr_t>(g.residual) & 15) == 0;
+  if (g.epi == EPI_MUL_GELU_GRAD) {
+    if (!res_ok || g.pos) return -1;
+    *add = g.residual; *add_rows = g.M; *add_ld = g.ldr;
+    return 3;
+  }
+  if (g.residual) {
+    if (!res_ok || g.epi != EPI_STORE_BF16) return -1;
+    *add = g.residual; *add_rows = g.M; *add_ld = g.ldr;
+    return 1;
+  }
+  if (g.pos) {
+    if (!g.pos_tile || g.epi != EPI_STORE_BF16) return -1;
+    *add = g.pos_tile; *add_rows = 128; *add_ld = g.N;
+    return 2;
+  }
+  return 0;
 }
 
 }  // namespace vitmarl
