@@ -68,6 +68,7 @@ struct FusedAttn2Params {
   const float* bo;              // [D] folded output bias (bo + Wo . bv')
   float eps;
   long long* dbg;
+  int inplace;                  // out aliases x: the residual add is done by a TMA reduce-add store (x += delta), no residual load
   int flags;                    // tuning switches: bit 0 projection of head n+1 held back until S(n) has retired; bit 1 output projection
                                 // (and its weights) before the next tile's first QKV projection
 };
@@ -156,7 +157,10 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       for (int j = 0; j < nt; ++j) {
         if (j + 1 < nt) { mbar_wait_guard(bar(B_XFREE), j & 1); load_x(j + 1); }      // LayerNorm(j) has read the x buffer
         mbar_wait_guard(bar(B_OUTREADY), j & 1);
-        for (int kb = 0; kb < KB_X; ++kb) tma_store_2d(&tmOut, sbase + OFF_OC + kb * KBLK, kb * 64, tile_row(j));
+        for (int kb = 0; kb < KB_X; ++kb) {
+          if (p.inplace) tma_reduce_add_2d(&tmOut, sbase + OFF_OC + kb * KBLK, kb * 64, tile_row(j));
+          else tma_store_2d(&tmOut, sbase + OFF_OC + kb * KBLK, kb * 64, tile_row(j));
+        }
         bulk_commit();
         bulk_wait_read0();
         mbar_arrive(bar(B_OCFREE));                                                   // the staging tile may be overwritten
@@ -463,7 +467,7 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     auto final_epilogue = [&](int j) {
       const int grow = tile_row(j) + row;
       uint4 xr[8];
-      if (grow < p.M) {
+      if (!p.inplace && grow < p.M) {                       // (in place: x += delta by the TMA reduce-add store, nothing to load)
         const uint4* gx = reinterpret_cast<const uint4*>(p.x + (size_t)grow * D + part * 64);
 #pragma unroll
         for (int c = 0; c < 8; ++c) xr[c] = gx[c];
@@ -548,7 +552,7 @@ int launch_fused_attn2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat1
   if ((rc = make_tmap_2d_bf16(&tmOut, out, M, D, (uint64_t)D * 2, TM, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmWqkv, wqkvf, 3 * D, D, (uint64_t)D * 2, 64, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmWo, wo, D, D, (uint64_t)D * 2, D, 64))) return rc;
-  FusedAttn2Params p{M, x, reinterpret_cast<const uint32_t*>(bqp), bof, eps, g_fattn2_dbg, g_fattn2_flags};
+  FusedAttn2Params p{M, x, reinterpret_cast<const uint32_t*>(bqp), bof, eps, g_fattn2_dbg, out == x ? 1 : 0, g_fattn2_flags};
   cudaError_t e = cudaFuncSetAttribute(fused_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return check_cuda(e);
   const int tiles = (M + TM - 1) / TM;

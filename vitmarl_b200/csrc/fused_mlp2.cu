@@ -80,6 +80,7 @@ struct FusedMlp2Params {
   const float* b2;              // [D]
   float eps;
   long long* dbg;               // optional clock64 timeline of cluster 0 / leader (second tile); null in production
+  int inplace;                  // out aliases x: the residual add is done by a TMA reduce-add store (x += delta), no residual load
 };
 
 #define FM2_WAIT(acc, call) do { if (p.dbg) { const long long t__ = clock64(); call; if (j == 1) acc += clock64() - t__; } else { call; } } while (0)
@@ -154,7 +155,10 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       for (int j = 0; j < nt; ++j) {
         // the final epilogue has staged the output tile in the (dead) x buffer: store it, then reuse the buffer
         mbar_wait_guard(bar(B_OUTREADY), j & 1);
-        for (int kb = 0; kb < KB_X; ++kb) tma_store_2d(&tmOut, sbase + OFF_X + (j & 1) * X_BYTES + kb * KBLK, kb * 64, tile_row(j));
+        for (int kb = 0; kb < KB_X; ++kb) {
+          if (p.inplace) tma_reduce_add_2d(&tmOut, sbase + OFF_X + (j & 1) * X_BYTES + kb * KBLK, kb * 64, tile_row(j));
+          else tma_store_2d(&tmOut, sbase + OFF_X + (j & 1) * X_BYTES + kb * KBLK, kb * 64, tile_row(j));
+        }
         bulk_commit();
         if (j + 2 < nt) { bulk_wait_read0(); load_x(j + 2); }
       }
@@ -369,7 +373,7 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int g3 = 0; g3 < 3; ++g3) {
           uint4 xr[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) xr[i] = grow < p.M ? gx[g3 * 4 + i] : make_uint4(0u, 0u, 0u, 0u);
+          for (int i = 0; i < 4; ++i) xr[i] = (!p.inplace && grow < p.M) ? gx[g3 * 4 + i] : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int col = col0 + g3 * 32 + 8 * i, kb = col >> 6, c8 = (col & 63) >> 3;
@@ -424,7 +428,7 @@ int launch_fused_mlp2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16
   if ((rc = make_tmap_2d_bf16(&tmOut, out, M, D, (uint64_t)D * 2, TM, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmW1, w1f, HID, D, (uint64_t)D * 2, HC / 2, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmW2, w2h, fmlp2::D, HID, (uint64_t)HID * 2, fmlp2::D / 2, 64))) return rc;
-  FusedMlp2Params p{M, x, reinterpret_cast<const uint32_t*>(b1p), b2, eps, g_fmlp2_dbg};
+  FusedMlp2Params p{M, x, reinterpret_cast<const uint32_t*>(b1p), b2, eps, g_fmlp2_dbg, out == x ? 1 : 0};
   cudaError_t e = cudaFuncSetAttribute(fused_mlp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return check_cuda(e);
   const int pair_tiles = (M + 2 * TM - 1) / (2 * TM);

@@ -38,6 +38,14 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_
                : "memory");
 }
 
+// 2-D tile reduction smem -> global: global[tile] += smem[tile], element type from the tensor map (bf16: the add and its
+// rounding happen in L2).  `x += delta` of a residual stream updated in place needs no residual load at all.
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m), "r"(src_smem), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+
 // ---- UMMA descriptors -------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_128B, tile rows are 128 bytes (64 bf16), 8-row atoms of 1024 B.
 //   K-major  (rows = M/N index, 128 B of K per row):  LBO unused (=1), SBO = 1024 B between 8-row groups.
