@@ -265,9 +265,9 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": dom_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": dom_tf / peaks["bf16_tflops_sustained"],
                      # dram__bytes_read.sum + dram__bytes_write.sum per launch of fused_mlp2_kernel at this shape, from the
-                     # ncu --set full capture profiles/r01_fused_blocks_ncu_full_v3.md (algorithmic: 100.7 MB in + 100.7 MB out;
+                     # ncu --set full capture profiles/r01_fused_blocks_ncu_full_v4.md (algorithmic: 100.7 MB in + 100.7 MB out;
                      # part of the write-back is still in L2 when the kernel ends)
-                     "traffic": 143.8e6,
+                     "traffic": 145.0e6,
                      "kernel": "vitmarl::fused_mlp2_kernel (LN2+FC1+GELU+FC2+residual, CTA-pair tcgen05), 12 launches per step",
                      "flops_per_launch": mlp_flops, "avg_launch_us": mlp_us, "share_of_step": cat_ms[1] / steps_logged / (t_dev / K * 1e3),
                      "second_kernel": {"kernel": "vitmarl::fused_attn2_kernel (LN1+QKV+softmax+PV+proj+residual)", "flops_per_launch": attn_flops,
