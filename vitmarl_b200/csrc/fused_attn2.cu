@@ -256,43 +256,47 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     if (nt > 0) {
       constexpr uint32_t id_s = umma_idesc_bf16(TM, 128, false, false);
       constexpr uint32_t id_pv = umma_idesc_bf16(TM, 64, false, true);      // B = V_h, MN-major
+      const uint32_t la_q = umma_desc_lo(sbase + OFF_Q), lb_k = umma_desc_lo(sbase + OFF_K), lv = umma_desc_lo(sbase + OFF_V, 8192);
+      auto issue_s = [&](uint32_t m) {        // elected lane only: S = Q K^T (both images; the diagonal 64x64 blocks are used)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + COL_S, umma_desc_from_lo(la_q + 2 * k), umma_desc_from_lo(lb_k + 2 * k), id_s, k ? 1u : 0u);
+        umma_commit(bar(B_SFULL));
+        mbar_arrive(bar(B_SISSUED));
+      };
       uint32_t n = 0;
+      bool s_issued = false;                   // S(n) already went out back to back with P.V(n-1)
       for (int j = 0; j < nt; ++j) {
         for (int h = 0; h < NH; ++h, ++n) {
           const uint32_t ph = n & 1;
-          // ---- S = Q K^T (both images; the diagonal 64x64 blocks are used).  Issued after P.V of the previous head by the
-          //      same thread, so the in-order tensor pipe has finished reading P before S overwrites it ----
-          if (h == 0) mbar_wait_guard(bar(B_PROJEMPTY), (j & 1) ^ 1);      // previous tile's final epilogue drained cols 288..479
-          mbar_wait_guard(bar(B_QKREADY), ph);
-          tc_fence_after();
-          FA2_STAMP(100 + 4 * h);
-          {
-            const uint32_t la = umma_desc_lo(sbase + OFF_Q), lb = umma_desc_lo(sbase + OFF_K);
-            if (elect_one()) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + COL_S, umma_desc_from_lo(la + 2 * k), umma_desc_from_lo(lb + 2 * k), id_s, k ? 1u : 0u);
-              umma_commit(bar(B_SFULL));
-              mbar_arrive(bar(B_SISSUED));
-            }
+          // ---- S(n).  Issued after P.V(n-1) by the same thread, so the in-order tensor pipe has finished reading P before S
+          //      overwrites it ----
+          if (!s_issued) {
+            if (h == 0) mbar_wait_guard(bar(B_PROJEMPTY), (j & 1) ^ 1);    // previous tile's final epilogue drained cols 288..479
+            mbar_wait_guard(bar(B_QKREADY), ph);
+            tc_fence_after();
+            FA2_STAMP(100 + 4 * h);
+            if (elect_one()) issue_s(n);
             __syncwarp();
           }
-          // ---- O = P V  (P in tensor memory over the S columns, V an MN-major B operand) ----
-          // the barriers that complete early first: only one wait latency is left once the softmax arrives on PREADY
+          // ---- O = P V  (P in tensor memory over the S columns, V an MN-major B operand).  The barriers that complete early
+          //      first: only one wait latency is left once the softmax arrives on PREADY; if the next head's Q / K are already
+          //      in place, S(n+1) goes out in the same breath ----
           mbar_wait_guard(bar(B_VREADY), ph);
           if (n > 0) mbar_wait_guard(bar(B_OCREADY), (n - 1) & 1);          // previous O drained from TMEM
+          // (warp-uniform: the phase is complete as soon as any lane has observed it)
+          const bool next_ready = (h + 1 < NH) && __any_sync(0xffffffffu, mbar_try_wait(bar(B_QKREADY), ph ^ 1));
           mbar_wait_guard(bar(B_PREADY), ph);
           tc_fence_after();
           FA2_STAMP(102 + 4 * h);
-          {
-            const uint32_t lv = umma_desc_lo(sbase + OFF_V, 8192);
-            if (elect_one()) {
+          if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 8; ++k)                                    // 16 keys per step: P columns 8k.., V rows 16k.. (2048 B)
-                umma_bf16_ts(tmem_base + COL_O, tmem_base + COL_S + 8 * k, umma_desc_from_lo(lv + k * (2048 >> 4)), id_pv, k ? 1u : 0u);
-              umma_commit(bar(B_OFULL));
-            }
-            __syncwarp();
+            for (int k = 0; k < 8; ++k)                                      // 16 keys per step: P columns 8k.., V rows 16k.. (2048 B)
+              umma_bf16_ts(tmem_base + COL_O, tmem_base + COL_S + 8 * k, umma_desc_from_lo(lv + k * (2048 >> 4)), id_pv, k ? 1u : 0u);
+            umma_commit(bar(B_OFULL));
+            if (next_ready) issue_s(n + 1);
           }
+          __syncwarp();
+          s_issued = next_ready;
         }
       }
     }
@@ -313,27 +317,31 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         uint32_t sv[32];
         tmem_ld_32x32(tmem_base + tm_lane + COL_S + img * 64 + half * 32, sv);
         tmem_ld_wait();
-        // scores already carry 1/8 . log2(e) (folded into Wq / bq): p = 2^(s - max)
+        // scores already carry 1/8 . log2(e) (folded into Wq / bq).  Each thread exponentiates against the max of ITS 32 keys;
+        // the pair then exchanges (max, sum) once and rescales -- one barrier per head instead of two (the barrier also
+        // orders every S read of the pair before the in-place P writes)
         float mx = __uint_as_float(sv[0]);
 #pragma unroll
         for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
-        sm_part[row * 2 + half].x = mx;
-        asm volatile("bar.sync 2, 256;" ::: "memory");          // also orders every S read of the pair before the in-place P writes
-        mx = fmaxf(mx, sm_part[row * 2 + (half ^ 1)].x);
         float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e = ex2_approx(__uint_as_float(sv[i]) - mx);
+          sum += e;
+          sv[i] = __float_as_uint(e);
+        }
+        sm_part[row * 2 + half] = make_float2(mx, sum);
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const float2 other = sm_part[row * 2 + (half ^ 1)];
+        const float m = fmaxf(mx, other.x);
+        const float f = ex2_approx(mx - m);
+        if (half == 0) s_inv[ph * 128 + row] = 1.0f / (sum * f + other.y * ex2_approx(other.x - m));   // read by the O epilogue after OFULL
         uint32_t pw[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float e0 = ex2_approx(__uint_as_float(sv[2 * i]) - mx), e1 = ex2_approx(__uint_as_float(sv[2 * i + 1]) - mx);
-          sum += e0 + e1;
-          pw[i] = pack_bf16(e0, e1);
-        }
-        sm_part[row * 2 + half].y = sum;
+        for (int i = 0; i < 16; ++i) pw[i] = pack_bf16(__uint_as_float(sv[2 * i]) * f, __uint_as_float(sv[2 * i + 1]) * f);
         // P (unnormalised, bf16 pairs) over this row's S columns: keys of its own image, zeros for the other image's keys
         tmem_st_32x16(tmem_base + tm_lane + COL_S + img * 32 + half * 16, pw);
         tmem_st_32x16_fill(tmem_base + tm_lane + COL_S + (img ^ 1) * 32 + half * 16, 0u);
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        if (half == 0) s_inv[ph * 128 + row] = 1.0f / (sum + sm_part[row * 2 + 1].y);   // read by the O epilogue after OFULL
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
