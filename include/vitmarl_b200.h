@@ -120,6 +120,17 @@ int vitmarl_env_step(void* stream, int E, int N, int T, int M,
 int vitmarl_get_cancel_msgs(void* stream, int E, int N, int size, const int32_t* bookside, int agent_id, int side,
                             const int32_t* cancel_time, int32_t* out);
 
+/* Auto-reset of MARLEnv.step (marl_env.py:737-766) for the world-state leaves this library owns: where done[e] != 0, env e's
+ * books / trades are replaced by those of its data window window_index[e] (base_env.py:215-231, index_tree(init_states_array)),
+ * best_asks / best_bids [E,M,2] are tiled from the window's initial best ask / bid [n_windows,2] (marl_env.py:186-189) and
+ * mid_price = float32((best_bid + best_ask) / 2) (:190).  Environments that are not done are untouched (the reference builds a
+ * full reset state for every env and selects).  window_index is the caller's jax.random.randint draw (base_env.py:219-222);
+ * init_trades [n_windows,T,8] may be NULL (= all -1).  All buffers int32 device memory, 16-byte aligned trades. */
+int vitmarl_auto_reset(void* stream, int E, int N, int T, int M, int n_windows, const int32_t* done, const int32_t* window_index,
+                       const int32_t* init_asks, const int32_t* init_bids, const int32_t* init_trades,
+                       const int32_t* init_best_asks, const int32_t* init_best_bids, int32_t* asks, int32_t* bids,
+                       int32_t* trades, int32_t* best_asks, int32_t* best_bids, float* mid_price);
+
 /* Replaces job.get_agent_trades under vmap (JaxOrderBookArrays.py:824-831): rows of trades [E,T,8] that are executed
  * (price >= 0) and involve agent_id as passive or aggressive trader are kept, all others zeroed. */
 int vitmarl_get_agent_trades(void* stream, int E, int T, const int32_t* trades, int agent_id, int32_t* out);

@@ -435,3 +435,24 @@ def build_step_msgs(message_data, start, step_counter, n_data, cancel_msgs, acti
     data = get_data_messages(message_data, start, step_counter, n_data, end_time_s)
     combined = np.concatenate([np.asarray(cancel_msgs, dtype=np.int32).reshape(-1, 8), action, data], axis=0)
     return combined, _w32(int(order_id_counter) - Ma)
+
+
+def auto_reset(done, window, init_asks, init_bids, init_best_asks, init_best_bids, asks, bids, trades, best_asks, best_bids, mid,
+               init_trades=None):
+    """marl_env.py:737-766 (jax.lax.select(done, reset_state, stepped_state) per leaf) with the reset state of
+    base_env.py:215-231 (index_tree(init_states_array, idx_data_window)) and marl_env.py:186-190 (best bid / ask tiled over the
+    message slots, mid_price = float32((best_bid[0] + best_ask[0]) / 2) with x64 disabled).  Returns new copies."""
+    asks, bids, trades = np.array(asks, np.int32), np.array(bids, np.int32), np.array(trades, np.int32)
+    best_asks, best_bids, mid = np.array(best_asks, np.int32), np.array(best_bids, np.int32), np.array(mid, np.float32)
+    M = best_asks.shape[1]
+    for e in range(asks.shape[0]):
+        if not done[e]:
+            continue
+        w = int(window[e])
+        asks[e], bids[e] = init_asks[w], init_bids[w]
+        trades[e] = -1 if init_trades is None else init_trades[w]
+        best_asks[e] = np.tile(np.asarray(init_best_asks[w], np.int32)[None, :], (M, 1))
+        best_bids[e] = np.tile(np.asarray(init_best_bids[w], np.int32)[None, :], (M, 1))
+        ssum = (int(init_best_bids[w][0]) + int(init_best_asks[w][0]) + 2**31) % 2**32 - 2**31     # int32 wrap-around (XLA semantics)
+        mid[e] = np.float32(np.float32(ssum) / np.float32(2))
+    return asks, bids, trades, best_asks, best_bids, mid

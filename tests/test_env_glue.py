@@ -47,6 +47,45 @@ def test_build_step_msgs_known_answer():
     assert np.array_equal(O.get_data_messages(md, 9, 5, 3), md[7:10])
 
 
+def test_auto_reset_known_answer():
+    init_a = np.arange(2 * 3 * 6, dtype=np.int32).reshape(2, 3, 6)
+    init_b = -init_a
+    asks = np.full((3, 3, 6), 7, np.int32); bids = np.full((3, 3, 6), 8, np.int32)
+    trades = np.full((3, 2, 8), 9, np.int32)
+    ba = np.full((3, 4, 2), 1, np.int32); bb = np.full((3, 4, 2), 2, np.int32)
+    mid = np.array([1.5, 2.5, 3.5], np.float32)
+    out = O.auto_reset([0, 1, 0], [0, 1, 0], init_a, init_b, [[101, 5], [2200100, 7]], [[99, 6], [2199900, 8]], asks, bids, trades, ba, bb, mid)
+    a, b, t, oa, ob, m = out
+    assert (a[0] == 7).all() and (a[2] == 7).all() and np.array_equal(a[1], init_a[1]) and np.array_equal(b[1], init_b[1])
+    assert (t[1] == -1).all() and (t[0] == 9).all()
+    assert oa[1].tolist() == [[2200100, 7]] * 4 and ob[1].tolist() == [[2199900, 8]] * 4 and (oa[0] == 1).all()
+    assert m.tolist() == [1.5, 2200000.0, 3.5]
+
+
+@pytest.mark.gpu
+def test_auto_reset_cuda_parity():
+    import torch
+    from vitmarl_b200 import env as venv
+    rng = np.random.default_rng(11)
+    E, N, T, M, nW = 133, 100, 100, 13, 9
+    init_a = rng.integers(-1, 3_000_000, (nW, N, 6)).astype(np.int32); init_b = rng.integers(-1, 3_000_000, (nW, N, 6)).astype(np.int32)
+    init_t = rng.integers(-1, 50, (nW, T, 8)).astype(np.int32)
+    iba = rng.integers(-1, 2**31 - 1, (nW, 2)).astype(np.int32); ibb = rng.integers(-1, 2**31 - 1, (nW, 2)).astype(np.int32)
+    for use_trades in (True, False):
+        asks = rng.integers(-1, 99, (E, N, 6)).astype(np.int32); bids = rng.integers(-1, 99, (E, N, 6)).astype(np.int32)
+        trades = rng.integers(-1, 99, (E, T, 8)).astype(np.int32)
+        ba = rng.integers(-1, 99, (E, M, 2)).astype(np.int32); bb = rng.integers(-1, 99, (E, M, 2)).astype(np.int32)
+        mid = rng.random(E).astype(np.float32)
+        done = (rng.random(E) < 0.4).astype(np.int32); win = rng.integers(0, nW, E).astype(np.int32)
+        want = O.auto_reset(done, win, init_a, init_b, iba, ibb, asks, bids, trades, ba, bb, mid, init_t if use_trades else None)
+        dev = lambda x: torch.from_numpy(x).cuda()
+        st = venv.BookState(dev(asks), dev(bids), dev(trades), dev(ba), dev(bb), dev(mid))
+        venv.auto_reset(st, dev(done), dev(win), dev(init_a), dev(init_b), dev(iba), dev(ibb), dev(init_t) if use_trades else None)
+        got = (st.ask_raw_orders, st.bid_raw_orders, st.trades, st.best_asks, st.best_bids, st.mid_price)
+        for g, w in zip(got, want):
+            assert g.cpu().numpy().tobytes() == np.ascontiguousarray(w).tobytes()
+
+
 @pytest.mark.gpu
 def test_env_glue_cuda_parity():
     import torch

@@ -91,6 +91,42 @@ __global__ void step_msgs_kernel(const StepMsgParams p) {
   }
 }
 
+// ---- auto-reset (marl_env.py:737-766): where done[e], the world-state leaves of env e are replaced by the reset state of its
+// sampled data window (base_env.py:215-231 index_tree(init_states_array, idx); marl_env.py:186-208 best bid / ask tiled over the
+// message slots, mid = float32((best_bid + best_ask) / 2), trades of the loaded state).  One warp per environment; environments
+// that are not done are untouched (the reference materialises a full reset state for every env and selects).
+struct ResetParams {
+  int E, N, T, M;
+  const int32_t* done; const int32_t* window;
+  const int32_t* init_asks; const int32_t* init_bids; const int32_t* init_trades; const int32_t* init_best_asks; const int32_t* init_best_bids;
+  int32_t* asks; int32_t* bids; int32_t* trades; int32_t* best_asks; int32_t* best_bids; float* mid;
+};
+
+__global__ void __launch_bounds__(128) auto_reset_kernel(const ResetParams p) {
+  const int e = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (e >= p.E || p.done[e] == 0) return;
+  const size_t w = (size_t)p.window[e];
+  const int side_v = p.N * 6 / 2;                                   // int2 elements per book side (N * 6 is even)
+  const int2* sa = reinterpret_cast<const int2*>(p.init_asks + w * p.N * 6);
+  const int2* sb = reinterpret_cast<const int2*>(p.init_bids + w * p.N * 6);
+  int2* da = reinterpret_cast<int2*>(p.asks + (size_t)e * p.N * 6);
+  int2* db = reinterpret_cast<int2*>(p.bids + (size_t)e * p.N * 6);
+  for (int i = lane; i < side_v; i += 32) { da[i] = __ldg(sa + i); db[i] = __ldg(sb + i); }
+  int4* dt = reinterpret_cast<int4*>(p.trades + (size_t)e * p.T * 8);
+  if (p.init_trades) {
+    const int4* st = reinterpret_cast<const int4*>(p.init_trades + w * p.T * 8);
+    for (int i = lane; i < p.T * 2; i += 32) dt[i] = __ldg(st + i);
+  } else {
+    for (int i = lane; i < p.T * 2; i += 32) dt[i] = make_int4(-1, -1, -1, -1);
+  }
+  const int2 ba = __ldg(reinterpret_cast<const int2*>(p.init_best_asks + w * 2));
+  const int2 bb = __ldg(reinterpret_cast<const int2*>(p.init_best_bids + w * 2));
+  int2* oa = reinterpret_cast<int2*>(p.best_asks + (size_t)e * p.M * 2);
+  int2* ob = reinterpret_cast<int2*>(p.best_bids + (size_t)e * p.M * 2);
+  for (int i = lane; i < p.M; i += 32) { oa[i] = ba; ob[i] = bb; }
+  if (lane == 0 && p.mid) p.mid[e] = __int2float_rn(wadd(bb.x, ba.x)) / 2.0f;   // jnp.float32((best_bid[0] + best_ask[0]) / 2), x64 disabled
+}
+
 }  // namespace vitmarl
 
 using namespace vitmarl;
@@ -129,5 +165,25 @@ extern "C" int vitmarl_build_step_msgs(void* stream, int E, int n_total, int n_d
   const size_t total = (size_t)E * (Mc + Ma + n_data);
   const int grid = (int)((total + 255) / 256 < (size_t)num_sms() * 8 ? (total + 255) / 256 : (size_t)num_sms() * 8);
   step_msgs_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_cuda(cudaGetLastError());
+}
+
+extern "C" int vitmarl_auto_reset(void* stream, int E, int N, int T, int M, int n_windows, const int32_t* done, const int32_t* window_index,
+                                  const int32_t* init_asks, const int32_t* init_bids, const int32_t* init_trades,
+                                  const int32_t* init_best_asks, const int32_t* init_best_bids, int32_t* asks, int32_t* bids,
+                                  int32_t* trades, int32_t* best_asks, int32_t* best_bids, float* mid_price) {
+  if (E == 0) return VITMARL_OK;
+  if (E < 0 || N < 1 || T < 0 || M < 0 || n_windows < 1 || !done || !window_index || !init_asks || !init_bids || !init_best_asks ||
+      !init_best_bids || !asks || !bids || !trades || !best_asks || !best_bids)
+    return VITMARL_EINVAL;
+  if ((N * 6) % 2) return VITMARL_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(trades) | reinterpret_cast<uintptr_t>(init_trades)) & 15) return VITMARL_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(asks) | reinterpret_cast<uintptr_t>(bids) | reinterpret_cast<uintptr_t>(init_asks) |
+       reinterpret_cast<uintptr_t>(init_bids) | reinterpret_cast<uintptr_t>(best_asks) | reinterpret_cast<uintptr_t>(best_bids) |
+       reinterpret_cast<uintptr_t>(init_best_asks) | reinterpret_cast<uintptr_t>(init_best_bids)) & 7)
+    return VITMARL_EINVAL;
+  ResetParams p{E, N, T, M, done, window_index, init_asks, init_bids, init_trades, init_best_asks, init_best_bids,
+                asks, bids, trades, best_asks, best_bids, mid_price};
+  auto_reset_kernel<<<(E + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return check_cuda(cudaGetLastError());
 }

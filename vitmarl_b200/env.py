@@ -13,7 +13,7 @@ from . import _capi
 from .config import World_EnvironmentConfig
 from .jaxob import _chk, _ptr, _stream, get_best_bid_and_ask_inclQuants
 
-__all__ = ["BookState", "StepOutput", "reset", "step", "build_step_msgs"]
+__all__ = ["BookState", "StepOutput", "reset", "step", "build_step_msgs", "auto_reset"]
 
 
 @dataclasses.dataclass
@@ -95,3 +95,25 @@ def build_step_msgs(message_data: torch.Tensor, start_index: torch.Tensor, step_
                                              _ptr(cm), _ptr(am), _ptr(pm), _ptr(oc), _ptr(out), _ptr(newc))
     _capi.check(rc)
     return out, newc
+
+
+def auto_reset(state: BookState, done: torch.Tensor, window_index: torch.Tensor, init_asks: torch.Tensor, init_bids: torch.Tensor,
+               init_best_asks: torch.Tensor, init_best_bids: torch.Tensor, init_trades: Optional[torch.Tensor] = None) -> BookState:
+    """Auto-reset of ``MARLEnv.step`` (``marl_env.py:737-766``) for the world-state leaves in :class:`BookState`, in place:
+    environments with ``done`` take the books / trades of their sampled data window (``base_env.py:215-231``), the tiled
+    initial best bid / ask and the initial mid price (``marl_env.py:186-190``); the others are untouched.
+    ``window_index`` is the caller's ``jax.random.randint`` draw."""
+    asks, bids = _chk(state.ask_raw_orders, "asks", 6), _chk(state.bid_raw_orders, "bids", 6)
+    E, N, _ = asks.shape
+    T, M = state.trades.shape[1], state.best_asks.shape[1]
+    i32 = lambda t: None if t is None else t.to(torch.int32).contiguous()
+    d, w = i32(done), i32(window_index)
+    ia, ib, it = _chk(init_asks, "init_asks", 6), _chk(init_bids, "init_bids", 6), i32(init_trades)
+    iba, ibb = i32(init_best_asks), i32(init_best_bids)
+    if ia.shape[1] != N or ib.shape != ia.shape or iba.shape != (ia.shape[0], 2) or ibb.shape != iba.shape:
+        raise _capi.VitmarlError(_capi.EINVAL, "auto_reset: init state shapes")
+    rc = _capi.lib().vitmarl_auto_reset(_stream(), E, N, T, M, ia.shape[0], _ptr(d), _ptr(w), _ptr(ia), _ptr(ib), _ptr(it), _ptr(iba),
+                                        _ptr(ibb), _ptr(asks), _ptr(bids), _ptr(state.trades), _ptr(state.best_asks),
+                                        _ptr(state.best_bids), _ptr(state.mid_price))
+    _capi.check(rc)
+    return state
