@@ -163,14 +163,7 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
       "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
-// the same 32-bit word to 32 consecutive columns of the thread's lane (zero fill)
-__device__ __forceinline__ void tmem_st_32x32_fill(uint32_t taddr, uint32_t v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
-      "r"(v)
-      : "memory");
-}
+// the same 32-bit word to 16 consecutive columns of the thread's lane (zero fill)
 __device__ __forceinline__ void tmem_st_32x16_fill(uint32_t taddr, uint32_t v) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(v)
@@ -231,39 +224,7 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
-// wait with acquire at cluster scope (barriers that receive arrivals from the peer CTA) and a watchdog: a protocol bug
-// traps after ~1 s instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0, polls = 0;
-  long long t0 = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if ((++polls & 1023u) == 0) {
-      const long long t = clock64();
-      if (t0 == 0) t0 = t;
-      else if (t - t0 > 4000000000LL) __trap();
-    }
-  }
-}
-// CTA-scope wait with the same watchdog
-__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {   // non-blocking poll (no hardware suspend)
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
+// mbarrier wait with a watchdog: a protocol bug traps after ~2 s instead of hanging the GPU
 // try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires) instead
 // of spinning through the ~100-cycle default time-out -- the polling loops of 20+ waiting warps were ~20-30 % of the
 // fused kernels' issued instructions, taken from the issue slots of the warps that work
