@@ -36,6 +36,8 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("cfg,B", [(vit.ViTConfig(64, 64, 2, 8, 192, 0, 3, 768), 6),
+                                   (vit.VIT_PARITY, 1),      # half an attention tile, a quarter of an MLP pair tile
+                                   (vit.VIT_PARITY, 3),
                                    (vit.VIT_PARITY, 16),
                                    (vit.ViTConfig(64, 64, 2, 8, 192, 12, 3, 768), 33),
                                    # > 148 attention tiles / > 74 MLP pair tiles: every CTA of the persistent fused kernels loops
