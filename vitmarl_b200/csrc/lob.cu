@@ -9,11 +9,12 @@
 //
 // B200 design (not a translation of the XLA program, which runs ~40 small fused loops over
 // [100,6] arrays per message and, under vmap, executes all five switch branches):
-//   * a warp owns one environment for the whole step; both book sides live in REGISTERS
-//     (row r = j*32 + lane, RPL = ceil(N/32) rows per lane, 6 fields x 2 sides);
-//   * book sides / trades are moved with the TMA engine as 1-D bulk copies
-//     (cp.async.bulk global<->shared + mbarrier), one instruction per 2.4 KB side, so the
-//     LSU only sees the AoS<->register transposition in shared memory;
+//   * a warp owns one environment for the whole step; book sides / trades are moved with the TMA
+//     engine as 1-D bulk copies (cp.async.bulk global<->shared + mbarrier), one instruction per
+//     2.4 KB side, and the AoS slab in shared memory stays the master copy of the side: a message
+//     touches one row (a few STS by the lane that owns it) and nothing is transposed on the way out;
+//   * price / quantity / order id of every row are cached in REGISTERS (row r = j*32 + lane,
+//     RPL = ceil(N/32) rows per lane) because every search and reduction runs over them;
 //   * messages are read as coalesced 32-byte rows (one message per lane, 2x LDG.128) and
 //     broadcast with SHFL; per-message best bid/ask are kept in lane registers and written
 //     as coalesced 8-byte rows per 32 messages;
@@ -28,6 +29,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "../../include/vitmarl_b200.h"
@@ -57,52 +59,55 @@ struct LobParams {
   int bulk_ok;            // 1: TMA bulk copies usable (16-byte aligned, N even)
 };
 
-// ---------------------------------------------------------------- one book side in registers
+// ---------------------------------------------------------------- one book side: registers + shared memory
+// The AoS slab [N][6] the TMA engine loaded stays the MASTER copy of the side for the whole step (it is also what
+// the TMA store sends back, so nothing is transposed on the way out); price / quantity / order id -- the fields the
+// searches and reductions run over -- are cached in registers (row r = j*32 + lane).  Row r of the slab is only ever
+// touched by lane r & 31, so the two copies stay coherent without any intra-warp synchronisation.
 template <int RPL>
 struct Side {
-  int p[RPL], q[RPL], oid[RPL], tid[RPL], ts[RPL], tns[RPL];
+  int p[RPL], q[RPL], oid[RPL];
+  int32_t* sm;   // [N][6] master copy in shared memory
   int best;      // bids: max(price) | asks: min(price, -1 -> MAXINT)   (over existing rows)
   int vol;       // volume at the reported best price (Q10 semantics)
-  bool tidy;     // every row is either all -1 or has no -1 field and qty > 0.  While this holds (the normal
-                 // state) an empty row <=> price == -1, only the touched row can need wiping and the cached
-                 // best price / volume can be updated incrementally; otherwise the literal full-array forms run.
+  bool tidy;     // every row is either all -1 or has no -1 field, qty > 0 and time_s != MAXINT.  While this holds
+                 // (the normal state) an empty row <=> price == -1, only the touched row can need wiping, the row
+                 // picked by the price-time priority search sits at the cached best price, and the cached best
+                 // price / volume can be updated incrementally; otherwise the literal full-array forms run.
 };
 
 // rows r = j*32 + lane exist for r < N; RPL = ceil(N/32), so only the last j can hold phantom rows
 #define VM_EX(j) ((j) < RPL - 1 || (j) * 32 + lane < N)
 
+__device__ __forceinline__ void sm_store_row(int32_t* sm, int r, int a, int b, int c, int d, int e, int f) {
+  int2* row = reinterpret_cast<int2*>(sm + r * 6);
+  row[0] = make_int2(a, b); row[1] = make_int2(c, d); row[2] = make_int2(e, f);
+}
+
+// row j of this lane (must exist) -> all -1, in both copies
 template <int RPL>
-__device__ __forceinline__ void wipe_row(Side<RPL>& s, int j) {
-  s.p[j] = -1; s.q[j] = -1; s.oid[j] = -1; s.tid[j] = -1; s.ts[j] = -1; s.tns[j] = -1;
+__device__ __forceinline__ void wipe_row(Side<RPL>& s, int j, int lane) {
+  s.p[j] = -1; s.q[j] = -1; s.oid[j] = -1;
+  sm_store_row(s.sm, j * 32 + lane, -1, -1, -1, -1, -1, -1);
 }
 
 // JOBA:85-90 on the whole side (literal form)
 template <int RPL>
-__device__ __forceinline__ void wipe_all(Side<RPL>& s) {
+__device__ __forceinline__ void wipe_all(Side<RPL>& s, int N, int lane) {
 #pragma unroll
   for (int j = 0; j < RPL; ++j)
-    if (s.q[j] <= 0) wipe_row(s, j);
+    if (VM_EX(j) && s.q[j] <= 0) wipe_row(s, j, lane);
 }
 
-// After modifying row `idx`: JOBA:85-90.  Fast path touches only that row.
+// first row index (ascending) whose predicate holds, -1 if none: one REDUX.MIN over per-lane candidates
 template <int RPL>
-__device__ __forceinline__ void wipe_after(Side<RPL>& s, int idx, int lane) {
-  if (!s.tidy) { wipe_all(s); return; }
+__device__ __forceinline__ int first_index(const bool (&pred)[RPL], int lane) {
+  int cand = MAXINT;
 #pragma unroll
-  for (int j = 0; j < RPL; ++j)
-    if (j * 32 + lane == idx && s.q[j] <= 0) wipe_row(s, j);
-}
-
-// first row index (ascending) whose predicate holds, -1 if none
-template <int RPL>
-__device__ __forceinline__ int first_index(const bool (&pred)[RPL]) {
-  int idx = -1;
-#pragma unroll
-  for (int j = RPL - 1; j >= 0; --j) {
-    unsigned b = __ballot_sync(FULL, pred[j]);
-    if (b) idx = j * 32 + __ffs(b) - 1;
-  }
-  return idx;
+  for (int j = RPL - 1; j >= 0; --j)
+    if (pred[j]) cand = j * 32 + lane;
+  cand = __reduce_min_sync(FULL, cand);
+  return cand == MAXINT ? -1 : cand;
 }
 
 // JOBA:846-865 + :833-844 -> cached (best, vol) of one side
@@ -129,91 +134,123 @@ __device__ __forceinline__ int best_price_out(const Side<RPL>& s) {
   return (!IS_BID && s.best == MAXINT) ? -1 : s.best;
 }
 
-// JOBA:240-267 literal (Q9)
+// JOBA:240-267 literal (Q9).  time_s / time_ns come from the shared-memory copy, and only for the rows that can win.
 template <int RPL, bool IS_BID>
 __device__ __forceinline__ int top_index(const Side<RPL>& s, int N, int lane) {
   const int best = s.best;  // == maxPrice (bids) / minPrice incl. MAXINT (asks)
-  int t[RPL];
+  int t[RPL], u[RPL];
   int ms = MAXINT;
 #pragma unroll
   for (int j = 0; j < RPL; ++j) {
-    bool ex = VM_EX(j);
-    t[j] = (s.p[j] == best) ? s.ts[j] : MAXINT;
-    if (ex) ms = min(ms, t[j]);
+    t[j] = MAXINT; u[j] = MAXINT;
+    if (VM_EX(j)) {
+      if (s.p[j] == best) {
+        const int2 tt = *reinterpret_cast<const int2*>(s.sm + (j * 32 + lane) * 6 + 4);
+        t[j] = tt.x; u[j] = tt.y;
+      }
+      ms = min(ms, t[j]);
+    }
   }
   ms = __reduce_min_sync(FULL, ms);
+  if (ms == MAXINT) {
+    // no row at `best` with time_s < MAXINT: every row ties on the first key, so time_ns of EVERY row competes
+#pragma unroll
+    for (int j = 0; j < RPL; ++j)
+      if (VM_EX(j)) u[j] = s.sm[(j * 32 + lane) * 6 + 5];
+  } else {
+#pragma unroll
+    for (int j = 0; j < RPL; ++j)
+      if (t[j] != ms) u[j] = MAXINT;
+  }
   int mn = MAXINT;
 #pragma unroll
-  for (int j = 0; j < RPL; ++j) {
-    bool ex = VM_EX(j);
-    t[j] = (t[j] == ms) ? s.tns[j] : MAXINT;
-    if (ex) mn = min(mn, t[j]);
-  }
+  for (int j = 0; j < RPL; ++j)
+    if (VM_EX(j)) mn = min(mn, u[j]);
   mn = __reduce_min_sync(FULL, mn);
   bool pred[RPL];
 #pragma unroll
-  for (int j = 0; j < RPL; ++j) pred[j] = VM_EX(j) && (t[j] == mn);
-  int idx = first_index<RPL>(pred);
+  for (int j = 0; j < RPL; ++j) pred[j] = VM_EX(j) && (u[j] == mn);
+  int idx = first_index<RPL>(pred, lane);
   return idx < 0 ? N - 1 : idx;
 }
 
-// broadcast one field of row `idx` to the warp
-template <int RPL>
-__device__ __forceinline__ int row_field(const int (&f)[RPL], int idx) {
-  // (selected per lane, not by the uniform idx>>5: the latter is turned into a dynamically
-  //  indexed load by the compiler, which demotes the register arrays to local memory)
-  const int lane = threadIdx.x & 31;
-  int v = 0;
-#pragma unroll
-  for (int j = 0; j < RPL; ++j)
-    if (j * 32 + lane == idx) v = f[j];
-  return __shfl_sync(FULL, v, idx & 31);
-}
+// the fields of one message that the book operations use (warp-uniform)
+struct Msg { int side, qty, price, oid, tid, ts, tns; bool clean; };
 
-struct Msg { int type, side, qty, price, oid, tid, ts, tns; };
+// trades slab [T][8] in shared memory + where the next fill goes (Q6)
+struct TradeLog {
+  int32_t* tr;
+  int next;       // fresh log (all -1 at step start, marl_env.py:377): rows [0,next) are taken, [next,T) are all -1
+  bool literal;   // caller-supplied trades: search column 4 for every fill
+};
+
+__device__ __forceinline__ int trade_slot(const TradeLog& tl, int T, int lane) {
+  if (!tl.literal) return tl.next < T ? tl.next : T - 1;
+  // first free trade slot: column 4 == -1 (Q6); none -> last row
+  int e = -1;
+  for (int base = 0; base < T && e < 0; base += 32) {
+    int r = base + lane;
+    bool free_ = (r < T) && (tl.tr[r * 8 + 4] == -1);
+    unsigned b = __ballot_sync(FULL, free_);
+    if (b) e = base + __ffs(b) - 1;
+  }
+  return e < 0 ? T - 1 : e;
+}
 
 // JOBA:171-330 : match the incoming order against `book` (Q6, Q7, Q11)
 template <int RPL, bool IS_BID_BOOK>
-__device__ __forceinline__ int match_against(Side<RPL>& book, const Msg& m, int32_t* tr, int N, int T, int lane) {
+__device__ __forceinline__ int match_against(Side<RPL>& book, const Msg& m, TradeLog& tl, int N, int T, int lane) {
   int qtm = m.qty;
   // exact quick reject: if no existing row can satisfy the price condition the loop body never runs
   bool possible = IS_BID_BOOK ? (book.best >= m.price) : (book.best <= m.price);
   if (!(possible && qtm > 0)) return qtm;
-  bool modified = false;
   for (;;) {
-    int top = top_index<RPL, IS_BID_BOOK>(book, N, lane);
-    int tp = row_field<RPL>(book.p, top);
-    bool cross = IS_BID_BOOK ? (tp >= m.price) : (tp <= m.price);
-    if (!(cross && qtm > 0 && tp != -1)) break;
-    int q_top = row_field<RPL>(book.q, top);
-    int o_top = row_field<RPL>(book.oid, top);
-    int t_top = row_field<RPL>(book.tid, top);
-    int d = wsub(q_top, qtm);
-    int newq = d > 0 ? d : 0;
-    qtm = wsub(qtm, q_top);
-    // first free trade slot: column 4 == -1 (Q6); none -> last row
-    int e = -1;
-    for (int base = 0; base < T && e < 0; base += 32) {
-      int r = base + lane;
-      bool free_ = (r < T) && (tr[r * 8 + 4] == -1);
-      unsigned b = __ballot_sync(FULL, free_);
-      if (b) e = base + __ffs(b) - 1;
+    // tidy side with a best price: the row the priority search returns sits AT the cached best price, so the loop
+    // condition is known before searching
+    const bool fastok = book.tidy && (IS_BID_BOOK || book.best != MAXINT);
+    int tp = book.best;
+    if (fastok) {
+      const bool cross = IS_BID_BOOK ? (tp >= m.price) : (tp <= m.price);
+      if (!(cross && qtm > 0 && tp != -1)) break;
     }
-    if (e < 0) e = T - 1;
-    if (lane == 0) {
-      int4* dst = reinterpret_cast<int4*>(tr + e * 8);
-      dst[0] = make_int4(tp, wmul(wsub(0, m.side), wsub(q_top, newq)), o_top, m.oid);
-      dst[1] = make_int4(m.ts, m.tns, t_top, m.tid);
+    const int top = top_index<RPL, IS_BID_BOOK>(book, N, lane);
+    const int src = top & 31;
+    int2 pq = make_int2(0, 0), ot = make_int2(0, 0);
+    if (lane == src) {
+      const int2* row = reinterpret_cast<const int2*>(book.sm + top * 6);
+      pq = row[0]; ot = row[1];
     }
-    __syncwarp();
+    if (!fastok) {
+      tp = __shfl_sync(FULL, pq.x, src);
+      const bool cross = IS_BID_BOOK ? (tp >= m.price) : (tp <= m.price);
+      if (!(cross && qtm > 0 && tp != -1)) break;
+    }
+    const int q_top = __shfl_sync(FULL, pq.y, src);
+    const int d = wsub(q_top, qtm);
+    const int newq = d > 0 ? d : 0;
+    const int filled = wsub(q_top, newq);
+    const int e = trade_slot(tl, T, lane);
+    const bool gone = book.tidy && newq <= 0;
+    if (lane == src) {
+      int4* dst = reinterpret_cast<int4*>(tl.tr + e * 8);
+      dst[0] = make_int4(pq.x, wmul(wsub(0, m.side), filled), ot.x, m.oid);
+      dst[1] = make_int4(m.ts, m.tns, ot.y, m.tid);
+      if (gone) sm_store_row(book.sm, top, -1, -1, -1, -1, -1, -1);
+      else book.sm[top * 6 + 1] = newq;
+    }
+    if (tl.literal) __syncwarp();
+    else if (m.ts != -1 && tl.next < T) tl.next += 1;
 #pragma unroll
     for (int j = 0; j < RPL; ++j)
-      if (j * 32 + lane == top) book.q[j] = newq;
-    wipe_after(book, top, lane);
-    refresh_best<RPL, IS_BID_BOOK>(book, N, lane);
-    modified = true;
+      if (j * 32 + lane == top) {
+        book.q[j] = newq;
+        if (gone) { book.p[j] = -1; book.q[j] = -1; book.oid[j] = -1; }
+      }
+    if (!book.tidy) wipe_all(book, N, lane);
+    qtm = wsub(qtm, q_top);
+    if (fastok && newq > 0) book.vol = wsub(book.vol, filled);   // the row stays at the best price
+    else refresh_best<RPL, IS_BID_BOOK>(book, N, lane);
   }
-  (void)modified;
   return qtm;
 }
 
@@ -221,25 +258,25 @@ __device__ __forceinline__ int match_against(Side<RPL>& book, const Msg& m, int3
 template <int RPL, bool IS_BID>
 __device__ __forceinline__ void add_order(Side<RPL>& s, const Msg& m, int qrem, int N, int lane) {
   const int qn = qrem > 0 ? qrem : 0;
-  const bool msg_clean = !(m.price == -1 || m.oid == -1 || m.tid == -1 || m.ts == -1 || m.tns == -1);
   bool pred[RPL];
   if (s.tidy) {
     // ---- fast path: empty row <=> price == -1 (phantom rows r >= N also hold -1: caught by idx >= N) ----
 #pragma unroll
     for (int j = 0; j < RPL; ++j) pred[j] = s.p[j] == -1;
-    int idx = first_index<RPL>(pred);
+    int idx = first_index<RPL>(pred, lane);
     const bool found = idx >= 0 && idx < N;
     if (!found) idx = N - 1;                                   // Q2: full side -> last row overwritten
     const bool alive = qn > 0;                                 // write + wipe merged: a zero-quantity row ends up all -1
-    const int wp = alive ? m.price : -1, wq = alive ? qn : -1, wo = alive ? m.oid : -1, wt = alive ? m.tid : -1,
-              ws = alive ? m.ts : -1, wn = alive ? m.tns : -1;
+    const int wp = alive ? m.price : -1, wq = alive ? qn : -1, wo = alive ? m.oid : -1;
+    if (lane == (idx & 31))
+      sm_store_row(s.sm, idx, wp, wq, wo, alive ? m.tid : -1, alive ? m.ts : -1, alive ? m.tns : -1);
 #pragma unroll
     for (int j = 0; j < RPL; ++j)
-      if (j * 32 + lane == idx) { s.p[j] = wp; s.q[j] = wq; s.oid[j] = wo; s.tid[j] = wt; s.ts[j] = ws; s.tns[j] = wn; }
-    if (alive && !msg_clean) s.tidy = false;                   // a resting row with a -1 field
+      if (j * 32 + lane == idx) { s.p[j] = wp; s.q[j] = wq; s.oid[j] = wo; }
+    if (alive && !m.clean) s.tidy = false;                     // a resting row with a -1 field (or time_s == MAXINT)
     // cached best: the overwritten row was empty, so nothing changes unless the new order rests at / inside the best
     const bool side_nonempty = IS_BID ? (s.best != -1) : (s.best != MAXINT);
-    if (found && msg_clean && side_nonempty) {
+    if (found && m.clean && side_nonempty) {
       if (alive) {
         const bool better = IS_BID ? (m.price > s.best) : (m.price < s.best);
         if (better) { s.best = m.price; s.vol = qn; }
@@ -250,18 +287,23 @@ __device__ __forceinline__ void add_order(Side<RPL>& s, const Msg& m, int qrem, 
     refresh_best<RPL, IS_BID>(s, N, lane);
     return;
   }
-  // ---- literal path ----
+  // ---- literal path: "empty" = any field equals -1 (Q1) ----
 #pragma unroll
-  for (int j = 0; j < RPL; ++j)
-    pred[j] = VM_EX(j) && (s.p[j] == -1 || s.q[j] == -1 || s.oid[j] == -1 || s.tid[j] == -1 || s.ts[j] == -1 || s.tns[j] == -1);
-  int idx = first_index<RPL>(pred);
-  if (idx < 0) idx = N - 1;
-#pragma unroll
-  for (int j = 0; j < RPL; ++j)
-    if (j * 32 + lane == idx) {
-      s.p[j] = m.price; s.q[j] = qn; s.oid[j] = m.oid; s.tid[j] = m.tid; s.ts[j] = m.ts; s.tns[j] = m.tns;
+  for (int j = 0; j < RPL; ++j) {
+    pred[j] = false;
+    if (VM_EX(j)) {
+      const int2* row = reinterpret_cast<const int2*>(s.sm + (j * 32 + lane) * 6);
+      const int2 b = row[1], c = row[2];
+      pred[j] = s.p[j] == -1 || s.q[j] == -1 || b.x == -1 || b.y == -1 || c.x == -1 || c.y == -1;
     }
-  wipe_all(s);
+  }
+  int idx = first_index<RPL>(pred, lane);
+  if (idx < 0) idx = N - 1;
+  if (lane == (idx & 31)) sm_store_row(s.sm, idx, m.price, qn, m.oid, m.tid, m.ts, m.tns);
+#pragma unroll
+  for (int j = 0; j < RPL; ++j)
+    if (j * 32 + lane == idx) { s.p[j] = m.price; s.q[j] = qn; s.oid[j] = m.oid; }
+  wipe_all(s, N, lane);
   refresh_best<RPL, IS_BID>(s, N, lane);
 }
 
@@ -271,84 +313,99 @@ __device__ __forceinline__ void cancel_order(Side<RPL>& s, const Msg& m, int ini
   bool pred[RPL];
 #pragma unroll
   for (int j = 0; j < RPL; ++j) pred[j] = s.oid[j] == m.oid;       // phantom rows (oid -1) sit above every real row
-  int idx = first_index<RPL>(pred);
+  int idx = first_index<RPL>(pred, lane);
   if (idx < 0 || idx >= N) {
 #pragma unroll
     for (int j = 0; j < RPL; ++j) pred[j] = (s.p[j] == m.price) && (s.oid[j] <= init_id) && (s.q[j] >= m.qty);
-    idx = first_index<RPL>(pred);
+    idx = first_index<RPL>(pred, lane);
   }
   if (idx < 0 || idx >= N) idx = N - 1;                               // Q5
-  int rp = 0;                                                          // price of the touched row (before the update)
-  bool odd = false;
+  const int src = idx & 31;
+  int rp = 0, nq = 0;                                                  // price of the touched row, its new quantity
+  if (lane == src) {
+    const int2 pq = *reinterpret_cast<const int2*>(s.sm + idx * 6);
+    rp = pq.x;
+    nq = wsub(pq.y, m.qty);
+    if (s.tidy && nq <= 0) sm_store_row(s.sm, idx, -1, -1, -1, -1, -1, -1);
+    else s.sm[idx * 6 + 1] = nq;
+  }
+  rp = __shfl_sync(FULL, rp, src);
+  nq = __shfl_sync(FULL, nq, src);
+  const bool gone = s.tidy && nq <= 0;
 #pragma unroll
   for (int j = 0; j < RPL; ++j)
     if (j * 32 + lane == idx) {
-      rp = s.p[j];
-      s.q[j] = wsub(s.q[j], m.qty);
-      if (s.p[j] == -1 && s.q[j] > 0) odd = true;                     // an empty row that acquired a positive quantity
-      if (s.tidy && s.q[j] <= 0) wipe_row(s, j);
+      s.q[j] = nq;
+      if (gone) { s.p[j] = -1; s.q[j] = -1; s.oid[j] = -1; }
     }
-  if (!s.tidy) wipe_all(s);
-  else if (m.qty < 0 && __any_sync(FULL, odd)) s.tidy = false;
-  rp = __shfl_sync(FULL, rp, idx & 31);
+  if (!s.tidy) wipe_all(s, N, lane);
+  else if (rp == -1 && nq > 0) s.tidy = false;                        // an empty row that acquired a positive quantity
   // the cached best only changes when the touched row sat at the best price (or the side had no best)
   const int bp = best_price_out<RPL, IS_BID>(s);
-  if (!s.tidy || rp == bp || bp == -1 || m.qty < 0) refresh_best<RPL, IS_BID>(s, N, lane);
+  if (s.tidy && m.qty >= 0 && bp != -1) {
+    if (rp != bp) return;
+    if (nq > 0) { s.vol = wsub(s.vol, m.qty); return; }               // partial cancel at the best price
+  }
+  refresh_best<RPL, IS_BID>(s, N, lane);
 }
 
-// JOBA:617-661
-template <int RPL>
-__device__ __forceinline__ void process_message(Side<RPL>& asks, Side<RPL>& bids, const Msg& m, int32_t* tr,
-                                                int N, int T, int init_id, int lane) {
-  const int s = m.side, t = m.type;
+// JOBA:617-661, per lane on ITS message (the dispatch index is then broadcast with the message):
+//   bits 0-2: branch, bit 3: message rests cleanly (no -1 field among price/oid/tid/ts/tns, ts != MAXINT)
+__device__ __forceinline__ int decode_message(const int4& m0, const int4& m1) {
+  const int t = m0.x, s = m0.y;
   int idx = (((s == 1 && t == 1) || (s == -1 && t == 4)) ? 1 : 0) + ((s == -1 && (t == 2 || t == 3)) ? 2 : 0) +
             ((s == 1 && (t == 2 || t == 3)) ? 3 : 0) + ((s == 0 && t == 0) ? 4 : 0);
-  if (idx == 0) {          // ask_lim :417-453 (also every (type, side) outside the table, Q8)
-    int q = match_against<RPL, true>(bids, m, tr, N, T, lane);
-    add_order<RPL, false>(asks, m, q, N, lane);
-  } else if (idx == 1) {   // bid_lim :356-391
-    int q = match_against<RPL, false>(asks, m, tr, N, T, lane);
-    add_order<RPL, true>(bids, m, q, N, lane);
-  } else if (idx == 2) {   // ask_cancel :455-478
-    cancel_order<RPL, false>(asks, m, init_id, N, lane);
-  } else if (idx == 3) {   // bid_cancel :392-415
-    cancel_order<RPL, true>(bids, m, init_id, N, lane);
-  }                        // 4: doNothing :334-355
+  const bool clean = !(m0.w == -1 || m1.x == -1 || m1.y == -1 || m1.z == -1 || m1.w == -1) && m1.z != MAXINT;
+  return idx | (clean ? 8 : 0);
 }
 
-// ---------------------------------------------------------------- staging <-> registers
+// one message (held by lane i as m0/m1, decoded as code) applied to the book
 template <int RPL>
-__device__ __forceinline__ void regs_from_smem(Side<RPL>& s, const int32_t* sm, int N, int lane) {
+__device__ __forceinline__ void process_message(Side<RPL>& asks, Side<RPL>& bids, const int4& m0, const int4& m1, int code,
+                                                int i, TradeLog& tl, int N, int T, int init_id, int lane) {
+  const int c = __shfl_sync(FULL, code, i);
+  const int idx = c & 7;
+  if (idx == 4) return;    // doNothing :334-355
+  Msg m;
+  m.qty = __shfl_sync(FULL, m0.z, i); m.price = __shfl_sync(FULL, m0.w, i); m.oid = __shfl_sync(FULL, m1.x, i);
+  if (idx >= 2) {          // ask_cancel :455-478 / bid_cancel :392-415
+    if (idx == 2) cancel_order<RPL, false>(asks, m, init_id, N, lane);
+    else          cancel_order<RPL, true>(bids, m, init_id, N, lane);
+    return;
+  }
+  m.side = __shfl_sync(FULL, m0.y, i);
+  m.tid = __shfl_sync(FULL, m1.y, i); m.ts = __shfl_sync(FULL, m1.z, i); m.tns = __shfl_sync(FULL, m1.w, i);
+  m.clean = (c & 8) != 0;
+  if (idx == 0) {          // ask_lim :417-453 (also every (type, side) outside the table, Q8)
+    int q = match_against<RPL, true>(bids, m, tl, N, T, lane);
+    add_order<RPL, false>(asks, m, q, N, lane);
+  } else {                 // bid_lim :356-391
+    int q = match_against<RPL, false>(asks, m, tl, N, T, lane);
+    add_order<RPL, true>(bids, m, q, N, lane);
+  }
+}
+
+// ---------------------------------------------------------------- staging -> registers
+template <int RPL>
+__device__ __forceinline__ void regs_from_smem(Side<RPL>& s, int32_t* sm, int N, int lane) {
   bool tidy = true;
+  s.sm = sm;
 #pragma unroll
   for (int j = 0; j < RPL; ++j) {
     int r = j * 32 + lane;
+    s.p[j] = -1; s.q[j] = -1; s.oid[j] = -1;
     if (VM_EX(j)) {
       const int2* row = reinterpret_cast<const int2*>(sm + r * 6);
       int2 a = row[0], b = row[1], c = row[2];
-      s.p[j] = a.x; s.q[j] = a.y; s.oid[j] = b.x; s.tid[j] = b.y; s.ts[j] = c.x; s.tns[j] = c.y;
-      const bool all = (a.x & a.y & b.x & b.y & c.x & c.y) == -1;
-      const bool none = a.x != -1 && a.y != -1 && b.x != -1 && b.y != -1 && c.x != -1 && c.y != -1;
-      if (!(all || (none && a.y > 0))) tidy = false;
-    } else {
-      wipe_row(s, j);
+      s.p[j] = a.x; s.q[j] = a.y; s.oid[j] = b.x;
+      // -1 is the largest unsigned value: min == -1 <=> all fields are -1, max == -1 <=> some field is -1
+      const unsigned lo = __vimin3_u32(__vimin3_u32(a.x, a.y, b.x), __vimin3_u32(b.y, c.x, c.y), 0xffffffffu);
+      const unsigned hi = __vimax3_u32(__vimax3_u32(a.x, a.y, b.x), __vimax3_u32(b.y, c.x, c.y), 0u);
+      const bool all = lo == 0xffffffffu, none = hi != 0xffffffffu;
+      if (!(all || (none && a.y > 0 && c.x != MAXINT))) tidy = false;
     }
   }
   s.tidy = __all_sync(FULL, tidy);
-}
-
-template <int RPL>
-__device__ __forceinline__ void regs_to_smem(const Side<RPL>& s, int32_t* sm, int N, int lane) {
-#pragma unroll
-  for (int j = 0; j < RPL; ++j) {
-    int r = j * 32 + lane;
-    if (VM_EX(j)) {
-      int2* row = reinterpret_cast<int2*>(sm + r * 6);
-      row[0] = make_int2(s.p[j], s.q[j]);
-      row[1] = make_int2(s.oid[j], s.tid[j]);
-      row[2] = make_int2(s.ts[j], s.tns[j]);
-    }
-  }
 }
 
 __device__ __forceinline__ void warp_copy_g2s(int32_t* dst, const int32_t* src, int n, int lane) {
@@ -513,8 +570,8 @@ __device__ __forceinline__ void render_env(const Side<RPL>& asks, const Side<RPL
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int RPL>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, RPL <= 4 ? 5 : (RPL <= 6 ? 3 : 2)) lob_kernel(const LobParams P) {
+template <int RPL, int MINB>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) lob_kernel(const LobParams P) {
   extern __shared__ __align__(16) int32_t smem[];
   __shared__ __align__(8) uint64_t bars[kWarpsPerCta];
 
@@ -576,19 +633,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RPL <= 4 ? 5 : (RPL <= 6 ? 
     const int keep0 = M - P.n_keep;   // first message index whose best bid/ask is reported
     int carry_a = -1, carry_b = -1;   // ffill carries across blocks
     int last_a = 0, last_b = 0;
+    TradeLog tl;
+    tl.tr = sm_tr; tl.next = 0; tl.literal = P.trades_in != nullptr;
     for (int base = 0; base < M; base += 32) {
       int4 m0 = nm0, m1 = nm1;
       int nb = base + 32 + lane;
       if (nb < M) { nm0 = ld_nc_v4(g_msgs + 2 * nb); nm1 = ld_nc_v4(g_msgs + 2 * nb + 1); }
       int oa_p = -1, oa_v = 0, ob_p = -1, ob_v = 0;   // this lane's message outputs
       const int cnt = min(32, M - base);
+      const int code = decode_message(m0, m1);        // every lane decodes its own message once
       for (int i = 0; i < cnt; ++i) {
-        Msg m;
-        m.type = __shfl_sync(FULL, m0.x, i); m.side = __shfl_sync(FULL, m0.y, i);
-        m.qty = __shfl_sync(FULL, m0.z, i);  m.price = __shfl_sync(FULL, m0.w, i);
-        m.oid = __shfl_sync(FULL, m1.x, i);  m.tid = __shfl_sync(FULL, m1.y, i);
-        m.ts = __shfl_sync(FULL, m1.z, i);   m.tns = __shfl_sync(FULL, m1.w, i);
-        process_message<RPL>(asks, bids, m, sm_tr, N, T, P.init_id, lane);
+        process_message<RPL>(asks, bids, m0, m1, code, i, tl, N, T, P.init_id, lane);
         if (lane == i) {
           oa_p = best_price_out<RPL, false>(asks); oa_v = asks.vol;
           ob_p = best_price_out<RPL, true>(bids);  ob_v = bids.vol;
@@ -624,9 +679,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RPL <= 4 ? 5 : (RPL <= 6 ? 
       have_mid = true;
       if (lane == 0 && P.mid_out) P.mid_out[e] = mid;
     }
-    // ---- store: registers -> shared (AoS) -> TMA bulk stores ------------------------------
-    regs_to_smem<RPL>(asks, sm_asks, N, lane);
-    regs_to_smem<RPL>(bids, sm_bids, N, lane);
+    // ---- store: the shared-memory slabs are already up to date -> TMA bulk stores ---------
     if (P.bulk_ok) {
       fence_proxy_async_smem();
       __syncwarp();
@@ -697,21 +750,22 @@ static int launch_lob(cudaStream_t stream, LobParams& P) {
   const size_t smem = (size_t)kWarpsPerCta * (2 * P.N * 6 + (P.do_step ? P.T * 8 : 0)) * sizeof(int32_t);
   const dim3 grid((P.E + kWarpsPerCta - 1) / kWarpsPerCta), block(kWarpsPerCta * 32);
   cudaError_t err = cudaSuccess;
-#define VM_LAUNCH(R)                                                                                      \
+#define VM_LAUNCH(R, B)                                                                                   \
   do {                                                                                                    \
-    if (smem > 48 * 1024) err = cudaFuncSetAttribute(lob_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(lob_kernel<R>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);  \
-    if (err == cudaSuccess) lob_kernel<R><<<grid, block, smem, stream>>>(P);                              \
+    if (smem > 48 * 1024) err = cudaFuncSetAttribute(lob_kernel<R, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(lob_kernel<R, B>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);  \
+    if (err == cudaSuccess) lob_kernel<R, B><<<grid, block, smem, stream>>>(P);                           \
   } while (0)
+  static const int minb = [] { const char* v = getenv("VITMARL_LOB_MINB"); return v ? atoi(v) : 5; }();
   switch (rpl) {
-    case 1: VM_LAUNCH(1); break;
-    case 2: VM_LAUNCH(2); break;
-    case 3: VM_LAUNCH(3); break;
-    case 4: VM_LAUNCH(4); break;
-    case 5: VM_LAUNCH(5); break;
-    case 6: VM_LAUNCH(6); break;
-    case 7: VM_LAUNCH(7); break;
-    default: VM_LAUNCH(8); break;
+    case 1: VM_LAUNCH(1, 5); break;
+    case 2: VM_LAUNCH(2, 5); break;
+    case 3: VM_LAUNCH(3, 5); break;
+    case 4: if (minb == 7) VM_LAUNCH(4, 7); else if (minb == 6) VM_LAUNCH(4, 6); else VM_LAUNCH(4, 5); break;
+    case 5: VM_LAUNCH(5, 3); break;
+    case 6: VM_LAUNCH(6, 3); break;
+    case 7: VM_LAUNCH(7, 2); break;
+    default: VM_LAUNCH(8, 2); break;
   }
 #undef VM_LAUNCH
   if (err == cudaSuccess) err = cudaGetLastError();
