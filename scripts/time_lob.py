@@ -32,6 +32,9 @@ def run(E, M, N=100, fused=False, image=False, iters=20):
           f"alg {byts/t/1e9:.0f} GB/s = {byts/t/1e9/HBM:.3f} of HBM peak")
 
 if __name__ == "__main__":
+    if "--one" in sys.argv:     # --one E M [N]: a single configuration (used under ncu)
+        a = [int(x) for x in sys.argv[sys.argv.index("--one") + 1:]]
+        run(a[0], a[1], N=a[2] if len(a) > 2 else 100, iters=2); sys.exit(0)
     if "--quick" in sys.argv:
         run(4096, 13, iters=2); run(4096, 13, fused=True, image=True, iters=2); run(16384, 100, iters=2); sys.exit(0)
     run(4096, 13); run(4096, 13, fused=True); run(4096, 13, fused=True, image=True)

@@ -64,16 +64,22 @@ struct LobParams {
 // the TMA store sends back, so nothing is transposed on the way out); price / quantity / order id -- the fields the
 // searches and reductions run over -- are cached in registers (row r = j*32 + lane).  Row r of the slab is only ever
 // touched by lane r & 31, so the two copies stay coherent without any intra-warp synchronisation.
+//
+// TWO implementations of the message semantics live in this file:
+//   * the FAST path (register cache, templates) assumes both sides are TIDY: every row is either all -1, or has no
+//     -1 field, qty > 0 and price / time_s / time_ns != MAXINT.  Then an empty row <=> price == -1, only the touched
+//     row can need wiping, the row the price-time priority search returns sits at the cached best price, and the
+//     cached best price / volume can be updated incrementally.  Normal LOBSTER-style data never leaves this state.
+//   * the LITERAL path (slow_* below) restates JOBA line by line on the shared-memory slabs.  A warp switches to it,
+//     for the rest of its step, the moment a side is not tidy at load time or a message could break tidiness.
+// Keeping the literal forms out of the hot loop matters: the loop is instruction-FETCH bound (20 warps per SM at
+// different program counters; 32 KB L1.5 instruction cache), and the literal branches were a third of its code.
 template <int RPL>
 struct Side {
   int p[RPL], q[RPL], oid[RPL];
   int32_t* sm;   // [N][6] master copy in shared memory
   int best;      // bids: max(price) | asks: min(price, -1 -> MAXINT)   (over existing rows)
   int vol;       // volume at the reported best price (Q10 semantics)
-  bool tidy;     // every row is either all -1 or has no -1 field, qty > 0 and time_s != MAXINT.  While this holds
-                 // (the normal state) an empty row <=> price == -1, only the touched row can need wiping, the row
-                 // picked by the price-time priority search sits at the cached best price, and the cached best
-                 // price / volume can be updated incrementally; otherwise the literal full-array forms run.
 };
 
 // rows r = j*32 + lane exist for r < N; RPL = ceil(N/32), so only the last j can hold phantom rows
@@ -82,21 +88,6 @@ struct Side {
 __device__ __forceinline__ void sm_store_row(int32_t* sm, int r, int a, int b, int c, int d, int e, int f) {
   int2* row = reinterpret_cast<int2*>(sm + r * 6);
   row[0] = make_int2(a, b); row[1] = make_int2(c, d); row[2] = make_int2(e, f);
-}
-
-// row j of this lane (must exist) -> all -1, in both copies
-template <int RPL>
-__device__ __forceinline__ void wipe_row(Side<RPL>& s, int j, int lane) {
-  s.p[j] = -1; s.q[j] = -1; s.oid[j] = -1;
-  sm_store_row(s.sm, j * 32 + lane, -1, -1, -1, -1, -1, -1);
-}
-
-// JOBA:85-90 on the whole side (literal form)
-template <int RPL>
-__device__ __forceinline__ void wipe_all(Side<RPL>& s, int N, int lane) {
-#pragma unroll
-  for (int j = 0; j < RPL; ++j)
-    if (VM_EX(j) && s.q[j] <= 0) wipe_row(s, j, lane);
 }
 
 // first row index (ascending) whose predicate holds, -1 if none: one REDUX.MIN over per-lane candidates
@@ -134,182 +125,113 @@ __device__ __forceinline__ int best_price_out(const Side<RPL>& s) {
   return (!IS_BID && s.best == MAXINT) ? -1 : s.best;
 }
 
-// JOBA:240-267 literal (Q9).  time_s / time_ns come from the shared-memory copy, and only for the rows that can win.
-template <int RPL, bool IS_BID>
-__device__ __forceinline__ int top_index(const Side<RPL>& s, int N, int lane) {
-  const int best = s.best;  // == maxPrice (bids) / minPrice incl. MAXINT (asks)
+// JOBA:240-267 on a tidy side whose best price exists (best != -1 / MAXINT): among the rows at the best price the
+// earliest (time_s, time_ns), ties -> lowest index.  Times come from the shared-memory copy, only for candidate rows.
+template <int RPL>
+__device__ __forceinline__ int top_index(const Side<RPL>& s, int lane) {
+  const int best = s.best;
   int t[RPL], u[RPL];
   int ms = MAXINT;
 #pragma unroll
   for (int j = 0; j < RPL; ++j) {
     t[j] = MAXINT; u[j] = MAXINT;
-    if (VM_EX(j)) {
-      if (s.p[j] == best) {
-        const int2 tt = *reinterpret_cast<const int2*>(s.sm + (j * 32 + lane) * 6 + 4);
-        t[j] = tt.x; u[j] = tt.y;
-      }
-      ms = min(ms, t[j]);
+    if (s.p[j] == best) {    // phantom rows hold -1 and never match
+      const int2 tt = *reinterpret_cast<const int2*>(s.sm + (j * 32 + lane) * 6 + 4);
+      t[j] = tt.x; u[j] = tt.y;
     }
+    ms = min(ms, t[j]);
   }
   ms = __reduce_min_sync(FULL, ms);
-  if (ms == MAXINT) {
-    // no row at `best` with time_s < MAXINT: every row ties on the first key, so time_ns of EVERY row competes
-#pragma unroll
-    for (int j = 0; j < RPL; ++j)
-      if (VM_EX(j)) u[j] = s.sm[(j * 32 + lane) * 6 + 5];
-  } else {
-#pragma unroll
-    for (int j = 0; j < RPL; ++j)
-      if (t[j] != ms) u[j] = MAXINT;
-  }
   int mn = MAXINT;
 #pragma unroll
-  for (int j = 0; j < RPL; ++j)
-    if (VM_EX(j)) mn = min(mn, u[j]);
-  mn = __reduce_min_sync(FULL, mn);
+  for (int j = 0; j < RPL; ++j) {
+    if (t[j] != ms) u[j] = MAXINT;
+    mn = min(mn, u[j]);
+  }
+  mn = __reduce_min_sync(FULL, mn);   // < MAXINT: tidy rows have time_ns != MAXINT
   bool pred[RPL];
 #pragma unroll
-  for (int j = 0; j < RPL; ++j) pred[j] = VM_EX(j) && (u[j] == mn);
-  int idx = first_index<RPL>(pred, lane);
-  return idx < 0 ? N - 1 : idx;
+  for (int j = 0; j < RPL; ++j) pred[j] = u[j] == mn;
+  return first_index<RPL>(pred, lane);
 }
 
 // the fields of one message that the book operations use (warp-uniform)
-struct Msg { int side, qty, price, oid, tid, ts, tns; bool clean; };
+struct Msg { int side, qty, price, oid, tid, ts, tns; };
 
-// trades slab [T][8] in shared memory + where the next fill goes (Q6)
-struct TradeLog {
-  int32_t* tr;
-  int next;       // fresh log (all -1 at step start, marl_env.py:377): rows [0,next) are taken, [next,T) are all -1
-  bool literal;   // caller-supplied trades: search column 4 for every fill
-};
-
-__device__ __forceinline__ int trade_slot(const TradeLog& tl, int T, int lane) {
-  if (!tl.literal) return tl.next < T ? tl.next : T - 1;
-  // first free trade slot: column 4 == -1 (Q6); none -> last row
-  int e = -1;
-  for (int base = 0; base < T && e < 0; base += 32) {
-    int r = base + lane;
-    bool free_ = (r < T) && (tl.tr[r * 8 + 4] == -1);
-    unsigned b = __ballot_sync(FULL, free_);
-    if (b) e = base + __ffs(b) - 1;
-  }
-  return e < 0 ? T - 1 : e;
-}
-
-// JOBA:171-330 : match the incoming order against `book` (Q6, Q7, Q11)
+// JOBA:171-330 : match the incoming order against `book` (Q6, Q7, Q11).  Fresh trade log: rows [0,tr_next) are
+// taken, rows [tr_next,T) have column 4 == -1, so the first free slot (Q6) is a counter.
 template <int RPL, bool IS_BID_BOOK>
-__device__ __forceinline__ int match_against(Side<RPL>& book, const Msg& m, TradeLog& tl, int N, int T, int lane) {
+__device__ __forceinline__ int match_against(Side<RPL>& book, const Msg& m, int32_t* tr, int& tr_next, int N, int T, int lane) {
   int qtm = m.qty;
-  // exact quick reject: if no existing row can satisfy the price condition the loop body never runs
-  bool possible = IS_BID_BOOK ? (book.best >= m.price) : (book.best <= m.price);
-  if (!(possible && qtm > 0)) return qtm;
   for (;;) {
-    // tidy side with a best price: the row the priority search returns sits AT the cached best price, so the loop
-    // condition is known before searching
-    const bool fastok = book.tidy && (IS_BID_BOOK || book.best != MAXINT);
-    int tp = book.best;
-    if (fastok) {
-      const bool cross = IS_BID_BOOK ? (tp >= m.price) : (tp <= m.price);
-      if (!(cross && qtm > 0 && tp != -1)) break;
-    }
-    const int top = top_index<RPL, IS_BID_BOOK>(book, N, lane);
+    // the row the priority search returns sits AT the cached best price: the loop condition is known before searching
+    const int tp = book.best;
+    const bool cross = IS_BID_BOOK ? (tp >= m.price) : (tp <= m.price);   // empty ask side: MAXINT <= price never holds
+    if (!(cross && qtm > 0 && tp != -1)) break;
+    const int top = top_index<RPL>(book, lane);
     const int src = top & 31;
     int2 pq = make_int2(0, 0), ot = make_int2(0, 0);
     if (lane == src) {
       const int2* row = reinterpret_cast<const int2*>(book.sm + top * 6);
       pq = row[0]; ot = row[1];
     }
-    if (!fastok) {
-      tp = __shfl_sync(FULL, pq.x, src);
-      const bool cross = IS_BID_BOOK ? (tp >= m.price) : (tp <= m.price);
-      if (!(cross && qtm > 0 && tp != -1)) break;
-    }
     const int q_top = __shfl_sync(FULL, pq.y, src);
     const int d = wsub(q_top, qtm);
     const int newq = d > 0 ? d : 0;
     const int filled = wsub(q_top, newq);
-    const int e = trade_slot(tl, T, lane);
-    const bool gone = book.tidy && newq <= 0;
+    const int e = tr_next < T ? tr_next : T - 1;
     if (lane == src) {
-      int4* dst = reinterpret_cast<int4*>(tl.tr + e * 8);
+      int4* dst = reinterpret_cast<int4*>(tr + e * 8);
       dst[0] = make_int4(pq.x, wmul(wsub(0, m.side), filled), ot.x, m.oid);
       dst[1] = make_int4(m.ts, m.tns, ot.y, m.tid);
-      if (gone) sm_store_row(book.sm, top, -1, -1, -1, -1, -1, -1);
+      if (newq <= 0) sm_store_row(book.sm, top, -1, -1, -1, -1, -1, -1);
       else book.sm[top * 6 + 1] = newq;
     }
-    if (tl.literal) __syncwarp();
-    else if (m.ts != -1 && tl.next < T) tl.next += 1;
+    if (tr_next < T) tr_next += 1;       // m.ts != -1 on this path, so the slot is taken for good
 #pragma unroll
     for (int j = 0; j < RPL; ++j)
       if (j * 32 + lane == top) {
         book.q[j] = newq;
-        if (gone) { book.p[j] = -1; book.q[j] = -1; book.oid[j] = -1; }
+        if (newq <= 0) { book.p[j] = -1; book.q[j] = -1; book.oid[j] = -1; }
       }
-    if (!book.tidy) wipe_all(book, N, lane);
     qtm = wsub(qtm, q_top);
-    if (fastok && newq > 0) book.vol = wsub(book.vol, filled);   // the row stays at the best price
+    if (newq > 0) book.vol = wsub(book.vol, filled);   // the row stays at the best price
     else refresh_best<RPL, IS_BID_BOOK>(book, N, lane);
   }
   return qtm;
 }
 
-// JOBA:62-83 (Q1, Q2, Q3)
+// JOBA:62-83 (Q2, Q3) on a tidy side: empty row <=> price == -1.  Returns true when (best, vol) must be recomputed.
 template <int RPL, bool IS_BID>
-__device__ __forceinline__ void add_order(Side<RPL>& s, const Msg& m, int qrem, int N, int lane) {
+__device__ __forceinline__ bool add_order(Side<RPL>& s, const Msg& m, int qrem, int N, int lane) {
   const int qn = qrem > 0 ? qrem : 0;
   bool pred[RPL];
-  if (s.tidy) {
-    // ---- fast path: empty row <=> price == -1 (phantom rows r >= N also hold -1: caught by idx >= N) ----
 #pragma unroll
-    for (int j = 0; j < RPL; ++j) pred[j] = s.p[j] == -1;
-    int idx = first_index<RPL>(pred, lane);
-    const bool found = idx >= 0 && idx < N;
-    if (!found) idx = N - 1;                                   // Q2: full side -> last row overwritten
-    const bool alive = qn > 0;                                 // write + wipe merged: a zero-quantity row ends up all -1
-    const int wp = alive ? m.price : -1, wq = alive ? qn : -1, wo = alive ? m.oid : -1;
-    if (lane == (idx & 31))
-      sm_store_row(s.sm, idx, wp, wq, wo, alive ? m.tid : -1, alive ? m.ts : -1, alive ? m.tns : -1);
-#pragma unroll
-    for (int j = 0; j < RPL; ++j)
-      if (j * 32 + lane == idx) { s.p[j] = wp; s.q[j] = wq; s.oid[j] = wo; }
-    if (alive && !m.clean) s.tidy = false;                     // a resting row with a -1 field (or time_s == MAXINT)
-    // cached best: the overwritten row was empty, so nothing changes unless the new order rests at / inside the best
-    const bool side_nonempty = IS_BID ? (s.best != -1) : (s.best != MAXINT);
-    if (found && m.clean && side_nonempty) {
-      if (alive) {
-        const bool better = IS_BID ? (m.price > s.best) : (m.price < s.best);
-        if (better) { s.best = m.price; s.vol = qn; }
-        else if (m.price == s.best) s.vol = wadd(s.vol, qn);
-      }
-      return;
-    }
-    refresh_best<RPL, IS_BID>(s, N, lane);
-    return;
-  }
-  // ---- literal path: "empty" = any field equals -1 (Q1) ----
-#pragma unroll
-  for (int j = 0; j < RPL; ++j) {
-    pred[j] = false;
-    if (VM_EX(j)) {
-      const int2* row = reinterpret_cast<const int2*>(s.sm + (j * 32 + lane) * 6);
-      const int2 b = row[1], c = row[2];
-      pred[j] = s.p[j] == -1 || s.q[j] == -1 || b.x == -1 || b.y == -1 || c.x == -1 || c.y == -1;
-    }
-  }
+  for (int j = 0; j < RPL; ++j) pred[j] = s.p[j] == -1;      // phantom rows r >= N also hold -1: caught by idx >= N
   int idx = first_index<RPL>(pred, lane);
-  if (idx < 0) idx = N - 1;
-  if (lane == (idx & 31)) sm_store_row(s.sm, idx, m.price, qn, m.oid, m.tid, m.ts, m.tns);
+  const bool found = idx >= 0 && idx < N;
+  if (!found) idx = N - 1;                                   // Q2: full side -> last row overwritten
+  const bool alive = qn > 0;                                 // write + wipe merged: a zero-quantity row ends up all -1
+  const int wp = alive ? m.price : -1, wq = alive ? qn : -1, wo = alive ? m.oid : -1;
+  if (lane == (idx & 31))
+    sm_store_row(s.sm, idx, wp, wq, wo, alive ? m.tid : -1, alive ? m.ts : -1, alive ? m.tns : -1);
 #pragma unroll
   for (int j = 0; j < RPL; ++j)
-    if (j * 32 + lane == idx) { s.p[j] = m.price; s.q[j] = qn; s.oid[j] = m.oid; }
-  wipe_all(s, N, lane);
-  refresh_best<RPL, IS_BID>(s, N, lane);
+    if (j * 32 + lane == idx) { s.p[j] = wp; s.q[j] = wq; s.oid[j] = wo; }
+  // cached best: the overwritten row was empty, so nothing changes unless the new order rests at / inside the best
+  const bool side_nonempty = IS_BID ? (s.best != -1) : (s.best != MAXINT);
+  if (!(found && side_nonempty)) return true;
+  if (alive) {
+    const bool better = IS_BID ? (m.price > s.best) : (m.price < s.best);
+    if (better) { s.best = m.price; s.vol = qn; }
+    else if (m.price == s.best) s.vol = wadd(s.vol, qn);
+  }
+  return false;
 }
 
-// JOBA:93-138 (Q4, Q5)
+// JOBA:93-138 (Q4, Q5) on a tidy side with msg.qty >= 0.  Returns true when (best, vol) must be recomputed.
 template <int RPL, bool IS_BID>
-__device__ __forceinline__ void cancel_order(Side<RPL>& s, const Msg& m, int init_id, int N, int lane) {
+__device__ __forceinline__ bool cancel_order(Side<RPL>& s, const Msg& m, int init_id, int N, int lane) {
   bool pred[RPL];
 #pragma unroll
   for (int j = 0; j < RPL; ++j) pred[j] = s.oid[j] == m.oid;       // phantom rows (oid -1) sit above every real row
@@ -326,68 +248,184 @@ __device__ __forceinline__ void cancel_order(Side<RPL>& s, const Msg& m, int ini
     const int2 pq = *reinterpret_cast<const int2*>(s.sm + idx * 6);
     rp = pq.x;
     nq = wsub(pq.y, m.qty);
-    if (s.tidy && nq <= 0) sm_store_row(s.sm, idx, -1, -1, -1, -1, -1, -1);
+    if (nq <= 0) sm_store_row(s.sm, idx, -1, -1, -1, -1, -1, -1);
     else s.sm[idx * 6 + 1] = nq;
   }
   rp = __shfl_sync(FULL, rp, src);
   nq = __shfl_sync(FULL, nq, src);
-  const bool gone = s.tidy && nq <= 0;
 #pragma unroll
   for (int j = 0; j < RPL; ++j)
     if (j * 32 + lane == idx) {
       s.q[j] = nq;
-      if (gone) { s.p[j] = -1; s.q[j] = -1; s.oid[j] = -1; }
+      if (nq <= 0) { s.p[j] = -1; s.q[j] = -1; s.oid[j] = -1; }
     }
-  if (!s.tidy) wipe_all(s, N, lane);
-  else if (rp == -1 && nq > 0) s.tidy = false;                        // an empty row that acquired a positive quantity
   // the cached best only changes when the touched row sat at the best price (or the side had no best)
   const int bp = best_price_out<RPL, IS_BID>(s);
-  if (s.tidy && m.qty >= 0 && bp != -1) {
-    if (rp != bp) return;
-    if (nq > 0) { s.vol = wsub(s.vol, m.qty); return; }               // partial cancel at the best price
-  }
-  refresh_best<RPL, IS_BID>(s, N, lane);
+  if (bp == -1) return true;
+  if (rp != bp) return false;
+  if (nq > 0) { s.vol = wsub(s.vol, m.qty); return false; }            // partial cancel at the best price
+  return true;
 }
 
-// JOBA:617-661, per lane on ITS message (the dispatch index is then broadcast with the message):
-//   bits 0-2: branch, bit 3: message rests cleanly (no -1 field among price/oid/tid/ts/tns, ts != MAXINT)
+// JOBA:617-661, per lane on ITS message (the code is then broadcast with the message):
+//   bits 0-2: branch; bit 3: the fast path may process it -- a limit order whose row would rest cleanly (no -1 among
+//   price/oid/tid/ts/tns, price/ts/tns != MAXINT), a cancel with qty >= 0, or a no-op.
 __device__ __forceinline__ int decode_message(const int4& m0, const int4& m1) {
   const int t = m0.x, s = m0.y;
-  int idx = (((s == 1 && t == 1) || (s == -1 && t == 4)) ? 1 : 0) + ((s == -1 && (t == 2 || t == 3)) ? 2 : 0) +
-            ((s == 1 && (t == 2 || t == 3)) ? 3 : 0) + ((s == 0 && t == 0) ? 4 : 0);
-  const bool clean = !(m0.w == -1 || m1.x == -1 || m1.y == -1 || m1.z == -1 || m1.w == -1) && m1.z != MAXINT;
-  return idx | (clean ? 8 : 0);
+  const int idx = (((s == 1 && t == 1) || (s == -1 && t == 4)) ? 1 : 0) + ((s == -1 && (t == 2 || t == 3)) ? 2 : 0) +
+                  ((s == 1 && (t == 2 || t == 3)) ? 3 : 0) + ((s == 0 && t == 0) ? 4 : 0);
+  const bool clean = !(m0.w == -1 || m1.x == -1 || m1.y == -1 || m1.z == -1 || m1.w == -1) &&
+                     m0.w != MAXINT && m1.z != MAXINT && m1.w != MAXINT;
+  const bool fast = idx == 4 || (idx <= 1 ? clean : m0.z >= 0);
+  return idx | (fast ? 8 : 0);
 }
 
-// one message (held by lane i as m0/m1, decoded as code) applied to the book
+// one message (held by lane i as m0/m1; idx = its branch) applied to a tidy book
 template <int RPL>
-__device__ __forceinline__ void process_message(Side<RPL>& asks, Side<RPL>& bids, const int4& m0, const int4& m1, int code,
-                                                int i, TradeLog& tl, int N, int T, int init_id, int lane) {
-  const int c = __shfl_sync(FULL, code, i);
-  const int idx = c & 7;
+__device__ __forceinline__ void process_message(Side<RPL>& asks, Side<RPL>& bids, const int4& m0, const int4& m1, int idx,
+                                                int i, int32_t* tr, int& tr_next, int N, int T, int init_id, int lane) {
   if (idx == 4) return;    // doNothing :334-355
   Msg m;
   m.qty = __shfl_sync(FULL, m0.z, i); m.price = __shfl_sync(FULL, m0.w, i); m.oid = __shfl_sync(FULL, m1.x, i);
+  bool ra = false, rb = false;   // (best, vol) of asks / bids to be recomputed
   if (idx >= 2) {          // ask_cancel :455-478 / bid_cancel :392-415
-    if (idx == 2) cancel_order<RPL, false>(asks, m, init_id, N, lane);
-    else          cancel_order<RPL, true>(bids, m, init_id, N, lane);
+    if (idx == 2) ra = cancel_order<RPL, false>(asks, m, init_id, N, lane);
+    else          rb = cancel_order<RPL, true>(bids, m, init_id, N, lane);
+  } else {
+    m.tid = __shfl_sync(FULL, m1.y, i); m.ts = __shfl_sync(FULL, m1.z, i); m.tns = __shfl_sync(FULL, m1.w, i);
+    if (idx == 0) {        // ask_lim :417-453 (also every (type, side) outside the table, Q8)
+      int q = m.qty;
+      if (bids.best >= m.price && q > 0) {   // exact quick reject: otherwise the match loop body never runs
+        m.side = __shfl_sync(FULL, m0.y, i);
+        q = match_against<RPL, true>(bids, m, tr, tr_next, N, T, lane);
+      }
+      ra = add_order<RPL, false>(asks, m, q, N, lane);
+    } else {               // bid_lim :356-391
+      int q = m.qty;
+      if (asks.best <= m.price && q > 0) {
+        m.side = __shfl_sync(FULL, m0.y, i);
+        q = match_against<RPL, false>(asks, m, tr, tr_next, N, T, lane);
+      }
+      rb = add_order<RPL, true>(bids, m, q, N, lane);
+    }
+  }
+  if (ra) refresh_best<RPL, false>(asks, N, lane);
+  if (rb) refresh_best<RPL, true>(bids, N, lane);
+}
+
+// ---------------------------------------------------------------- literal path (any book, any message)
+// JOBA restated on the shared-memory slabs, warp-cooperative, side chosen at run time; every lane returns the same
+// values.  Used when a side is not tidy, a message could break tidiness, or the caller supplies a trade log whose
+// free rows are not a suffix.  Cross-lane visibility of the single-lane writes comes from __syncwarp().
+template <class F>
+__device__ __forceinline__ int slow_first(int n, int lane, F pred) {
+  for (int base = 0; base < n; base += 32) {
+    const int r = base + lane;
+    const unsigned b = __ballot_sync(FULL, r < n && pred(r));
+    if (b) return base + __ffs(b) - 1;
+  }
+  return -1;
+}
+
+// JOBA:85-90
+__device__ __noinline__ void slow_wipe(int32_t* s, int N, int lane) {
+  __syncwarp();
+  for (int r = lane; r < N; r += 32)
+    if (s[r * 6 + 1] <= 0) sm_store_row(s, r, -1, -1, -1, -1, -1, -1);
+  __syncwarp();
+}
+
+// JOBA:846-865, :833-844 -> raw best (MAXINT for an empty ask side) and the volume at the reported price
+__device__ __noinline__ int2 slow_best(const int32_t* s, int N, bool is_bid, int lane) {
+  int m = is_bid ? (int)0x80000000 : MAXINT;
+  for (int r = lane; r < N; r += 32) {
+    const int p = s[r * 6];
+    m = is_bid ? max(m, p) : min(m, p == -1 ? MAXINT : p);
+  }
+  m = is_bid ? __reduce_max_sync(FULL, m) : __reduce_min_sync(FULL, m);
+  const int bp = (!is_bid && m == MAXINT) ? -1 : m;
+  int v = 0;
+  for (int r = lane; r < N; r += 32)
+    if (s[r * 6] == bp) v = wadd(v, s[r * 6 + 1]);
+  return make_int2(m, __reduce_add_sync(FULL, v));
+}
+
+// JOBA:240-267 (Q9)
+__device__ __noinline__ int slow_top(const int32_t* s, int N, int best, int lane) {
+  int ms = MAXINT;
+  for (int r = lane; r < N; r += 32) ms = min(ms, s[r * 6] == best ? s[r * 6 + 4] : MAXINT);
+  ms = __reduce_min_sync(FULL, ms);
+  int mn = MAXINT;
+  for (int r = lane; r < N; r += 32) {
+    const int t = s[r * 6] == best ? s[r * 6 + 4] : MAXINT;
+    mn = min(mn, t == ms ? s[r * 6 + 5] : MAXINT);
+  }
+  mn = __reduce_min_sync(FULL, mn);
+  const int idx = slow_first(N, lane, [&](int r) {
+    const int t = s[r * 6] == best ? s[r * 6 + 4] : MAXINT;
+    return (t == ms ? s[r * 6 + 5] : MAXINT) == mn;
+  });
+  return idx < 0 ? N - 1 : idx;
+}
+
+// JOBA:617-661 for one message given as its eight raw fields
+__device__ __noinline__ void slow_message(int32_t* asks, int32_t* bids, int32_t* tr, int N, int T, int init_id,
+                                          int4 a, int4 b, int lane) {
+  const int t = a.x, sd = a.y, qty = a.z, price = a.w, oid = b.x, tid = b.y, ts = b.z, tns = b.w;
+  const int idx = (((sd == 1 && t == 1) || (sd == -1 && t == 4)) ? 1 : 0) + ((sd == -1 && (t == 2 || t == 3)) ? 2 : 0) +
+                  ((sd == 1 && (t == 2 || t == 3)) ? 3 : 0) + ((sd == 0 && t == 0) ? 4 : 0);
+  if (idx == 4) return;
+  const bool own_is_bid = (idx & 1) != 0;
+  int32_t* own = own_is_bid ? bids : asks;
+  int32_t* opp = own_is_bid ? asks : bids;
+  __syncwarp();
+  if (idx >= 2) {   // cancel_order :93-138 (Q4, Q5)
+    int i = slow_first(N, lane, [&](int r) { return own[r * 6 + 2] == oid; });
+    if (i < 0) i = slow_first(N, lane, [&](int r) { return own[r * 6] == price && own[r * 6 + 2] <= init_id && own[r * 6 + 1] >= qty; });
+    if (i < 0) i = N - 1;
+    if (lane == 0) own[i * 6 + 1] = wsub(own[i * 6 + 1], qty);
+    slow_wipe(own, N, lane);
     return;
   }
-  m.side = __shfl_sync(FULL, m0.y, i);
-  m.tid = __shfl_sync(FULL, m1.y, i); m.ts = __shfl_sync(FULL, m1.z, i); m.tns = __shfl_sync(FULL, m1.w, i);
-  m.clean = (c & 8) != 0;
-  if (idx == 0) {          // ask_lim :417-453 (also every (type, side) outside the table, Q8)
-    int q = match_against<RPL, true>(bids, m, tl, N, T, lane);
-    add_order<RPL, false>(asks, m, q, N, lane);
-  } else {                 // bid_lim :356-391
-    int q = match_against<RPL, false>(asks, m, tl, N, T, lane);
-    add_order<RPL, true>(bids, m, q, N, lane);
+  // match against the opposite side :171-330 (Q6, Q7, Q11)
+  const bool book_is_bid = !own_is_bid;
+  int qtm = qty;
+  for (;;) {
+    const int best = slow_best(opp, N, book_is_bid, lane).x;
+    const int top = slow_top(opp, N, best, lane);
+    const int tp = opp[top * 6];
+    const bool cross = book_is_bid ? (tp >= price) : (tp <= price);
+    if (!(cross && qtm > 0 && tp != -1)) break;
+    const int q_top = opp[top * 6 + 1], o_top = opp[top * 6 + 2], t_top = opp[top * 6 + 3];
+    const int d = wsub(q_top, qtm);
+    const int newq = d > 0 ? d : 0;
+    int e = slow_first(T, lane, [&](int r) { return tr[r * 8 + 4] == -1; });
+    if (e < 0) e = T - 1;
+    __syncwarp();
+    if (lane == 0) {
+      int4* dst = reinterpret_cast<int4*>(tr + e * 8);
+      dst[0] = make_int4(tp, wmul(wsub(0, sd), wsub(q_top, newq)), o_top, oid);
+      dst[1] = make_int4(ts, tns, t_top, tid);
+      opp[top * 6 + 1] = newq;
+    }
+    slow_wipe(opp, N, lane);
+    qtm = wsub(qtm, q_top);
   }
+  // add_order :62-83 (Q1, Q2, Q3)
+  int i = slow_first(N, lane, [&](int r) {
+    const int32_t* w = own + r * 6;
+    return w[0] == -1 || w[1] == -1 || w[2] == -1 || w[3] == -1 || w[4] == -1 || w[5] == -1;
+  });
+  if (i < 0) i = N - 1;
+  __syncwarp();
+  if (lane == 0) sm_store_row(own, i, price, qtm > 0 ? qtm : 0, oid, tid, ts, tns);
+  slow_wipe(own, N, lane);
 }
 
 // ---------------------------------------------------------------- staging -> registers
+// Returns (warp-uniform) whether the side is tidy.
 template <int RPL>
-__device__ __forceinline__ void regs_from_smem(Side<RPL>& s, int32_t* sm, int N, int lane) {
+__device__ __forceinline__ bool regs_from_smem(Side<RPL>& s, int32_t* sm, int N, int lane) {
   bool tidy = true;
   s.sm = sm;
 #pragma unroll
@@ -402,10 +440,10 @@ __device__ __forceinline__ void regs_from_smem(Side<RPL>& s, int32_t* sm, int N,
       const unsigned lo = __vimin3_u32(__vimin3_u32(a.x, a.y, b.x), __vimin3_u32(b.y, c.x, c.y), 0xffffffffu);
       const unsigned hi = __vimax3_u32(__vimax3_u32(a.x, a.y, b.x), __vimax3_u32(b.y, c.x, c.y), 0u);
       const bool all = lo == 0xffffffffu, none = hi != 0xffffffffu;
-      if (!(all || (none && a.y > 0 && c.x != MAXINT))) tidy = false;
+      if (!(all || (none && a.y > 0 && a.x != MAXINT && c.x != MAXINT && c.y != MAXINT))) tidy = false;
     }
   }
-  s.tidy = __all_sync(FULL, tidy);
+  return __all_sync(FULL, tidy);
 }
 
 __device__ __forceinline__ void warp_copy_g2s(int32_t* dst, const int32_t* src, int n, int lane) {
@@ -614,64 +652,103 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) lob_kernel(const LobP
     for (int i = lane; i < trade_words / 4; i += 32) t4[i] = make_int4(-1, -1, -1, -1);
   }
   const int4* g_msgs = reinterpret_cast<const int4*>(P.msgs + (size_t)e * M * 8);
-  int4 nm0 = make_int4(0, 0, 0, 0), nm1 = nm0;
-  if (P.do_step && lane < M) { nm0 = ld_nc_v4(g_msgs + 2 * lane); nm1 = ld_nc_v4(g_msgs + 2 * lane + 1); }
+  int4 m0 = make_int4(0, 0, 0, 0), m1 = m0;   // this lane's message of the current block of 32
+  if (P.do_step && lane < M) { m0 = ld_nc_v4(g_msgs + 2 * lane); m1 = ld_nc_v4(g_msgs + 2 * lane + 1); }
 
   if (P.bulk_ok) mbar_wait(bar, 0);
   __syncwarp();
 
   Side<RPL> asks, bids;
-  regs_from_smem<RPL>(asks, sm_asks, N, lane);
-  regs_from_smem<RPL>(bids, sm_bids, N, lane);
-  refresh_best<RPL, false>(asks, N, lane);
-  refresh_best<RPL, true>(bids, N, lane);
-
   float mid = 0.f;
   bool have_mid = false;
+#pragma unroll 1
+  for (int pass = 0;; ++pass) {   // pass 1 only re-reads the register cache after the literal path ran
+  const bool tidy_a = regs_from_smem<RPL>(asks, sm_asks, N, lane);
+  const bool tidy_b = regs_from_smem<RPL>(bids, sm_bids, N, lane);
+  refresh_best<RPL, false>(asks, N, lane);
+  refresh_best<RPL, true>(bids, N, lane);
+  if (pass == 1) break;
+  bool slow = !(tidy_a && tidy_b);   // this warp runs the literal path (from some message on)
+
   if (P.do_step) {
-    // ---- message loop: blocks of 32 messages, one per lane, next block prefetched --------
+    // ---- message loop: blocks of 32 messages, one per lane -------------------------------
     const int keep0 = M - P.n_keep;   // first message index whose best bid/ask is reported
     int carry_a = -1, carry_b = -1;   // ffill carries across blocks
     int last_a = 0, last_b = 0;
-    TradeLog tl;
-    tl.tr = sm_tr; tl.next = 0; tl.literal = P.trades_in != nullptr;
-    for (int base = 0; base < M; base += 32) {
-      int4 m0 = nm0, m1 = nm1;
-      int nb = base + 32 + lane;
-      if (nb < M) { nm0 = ld_nc_v4(g_msgs + 2 * nb); nm1 = ld_nc_v4(g_msgs + 2 * nb + 1); }
-      int oa_p = -1, oa_v = 0, ob_p = -1, ob_v = 0;   // this lane's message outputs
+    int tr_next = 0;                  // fast path: first free trade row (fresh log: everything is free)
+    if (P.trades_in) {
+      // a caller-supplied log is usable by the fast path when its free rows (column 4 == -1, Q6) are a suffix
+      int ff = slow_first(T, lane, [&](int r) { return sm_tr[r * 8 + 4] == -1; });
+      if (ff < 0) ff = T;
+      bool ok = true;
+      for (int r = ff + lane; r < T; r += 32) ok = ok && sm_tr[r * 8 + 4] == -1;
+      if (!__all_sync(FULL, ok)) slow = true;
+      tr_next = ff;
+    }
+    // per-lane outputs of the current block of 32 messages
+    int oa_p = -1, oa_v = 0, ob_p = -1, ob_v = 0;
+    // block epilogue: forward fill, output rows, next block of messages
+    auto finish_block = [&](int base, int cnt) {
+        const int gi = base + lane;   // global message index of this lane
+        if (P.do_ffill) {
+          // marl_env.py:685-711 on both tracks
+          if (gi == 0) {
+            if (oa_p == -1) { oa_p = P.last_ask_price[e]; oa_v = 0; }
+            if (ob_p == -1) { ob_p = P.last_bid_price[e]; ob_v = 0; }
+          }
+          if (oa_p == -1) oa_v = 0;
+          if (ob_p == -1) ob_v = 0;
+          unsigned lower = (lane == 31) ? FULL : ((2u << lane) - 1u);
+          unsigned va = __ballot_sync(FULL, lane < cnt && oa_p != -1) & lower;
+          unsigned vb = __ballot_sync(FULL, lane < cnt && ob_p != -1) & lower;
+          int sa = __shfl_sync(FULL, oa_p, va ? 31 - __clz(va) : 0);
+          int sb = __shfl_sync(FULL, ob_p, vb ? 31 - __clz(vb) : 0);
+          oa_p = va ? sa : carry_a;
+          ob_p = vb ? sb : carry_b;
+          carry_a = __shfl_sync(FULL, oa_p, cnt - 1);
+          carry_b = __shfl_sync(FULL, ob_p, cnt - 1);
+          last_a = carry_a; last_b = carry_b;
+        }
+        if (lane < cnt && gi >= keep0) {
+          if (P.best_asks) reinterpret_cast<int2*>(P.best_asks + (size_t)e * P.n_keep * 2)[gi - keep0] = make_int2(oa_p, oa_v);
+          if (P.best_bids) reinterpret_cast<int2*>(P.best_bids + (size_t)e * P.n_keep * 2)[gi - keep0] = make_int2(ob_p, ob_v);
+        }
+        const int nb = gi + 32;   // next block (not prefetched: 8 registers matter more than one exposed load per 32 messages)
+        if (nb < M) { m0 = ld_nc_v4(g_msgs + 2 * nb); m1 = ld_nc_v4(g_msgs + 2 * nb + 1); }
+      oa_p = -1; oa_v = 0; ob_p = -1; ob_v = 0;
+    };
+    int base = 0, i = 0;
+    // ---- fast path: tidy book, register cache ----
+    for (; base < M && !slow; base += 32) {
       const int cnt = min(32, M - base);
       const int code = decode_message(m0, m1);        // every lane decodes its own message once
-      for (int i = 0; i < cnt; ++i) {
-        process_message<RPL>(asks, bids, m0, m1, code, i, tl, N, T, P.init_id, lane);
+      for (i = 0; i < cnt; ++i) {
+        const int c = __shfl_sync(FULL, code, i);
+        if (!(c & 8)) { slow = true; break; }         // could break tidiness: literal path from here to the end of the step
+        process_message<RPL>(asks, bids, m0, m1, c & 7, i, sm_tr, tr_next, N, T, P.init_id, lane);
         if (lane == i) {
           oa_p = best_price_out<RPL, false>(asks); oa_v = asks.vol;
           ob_p = best_price_out<RPL, true>(bids);  ob_v = bids.vol;
         }
       }
-      const int gi = base + lane;   // global message index of this lane
-      if (P.do_ffill) {
-        // marl_env.py:685-711 on both tracks
-        if (gi == 0) {
-          if (oa_p == -1) { oa_p = P.last_ask_price[e]; oa_v = 0; }
-          if (ob_p == -1) { ob_p = P.last_bid_price[e]; ob_v = 0; }
+      if (slow) break;
+      finish_block(base, cnt);
+    }
+    // ---- literal path on the shared-memory slabs (the register cache is dead from here on) ----
+    if (slow) {
+      if (base >= M) i = 0;
+      for (; base < M; base += 32) {
+        const int cnt = min(32, M - base);
+        for (; i < cnt; ++i) {
+          __syncwarp();
+          const int4 ma = make_int4(__shfl_sync(FULL, m0.x, i), __shfl_sync(FULL, m0.y, i), __shfl_sync(FULL, m0.z, i), __shfl_sync(FULL, m0.w, i));
+          const int4 mb = make_int4(__shfl_sync(FULL, m1.x, i), __shfl_sync(FULL, m1.y, i), __shfl_sync(FULL, m1.z, i), __shfl_sync(FULL, m1.w, i));
+          slow_message(sm_asks, sm_bids, sm_tr, N, T, P.init_id, ma, mb, lane);
+          const int2 ba = slow_best(sm_asks, N, false, lane), bb = slow_best(sm_bids, N, true, lane);
+          if (lane == i) { oa_p = ba.x == MAXINT ? -1 : ba.x; oa_v = ba.y; ob_p = bb.x; ob_v = bb.y; }
         }
-        if (oa_p == -1) oa_v = 0;
-        if (ob_p == -1) ob_v = 0;
-        unsigned lower = (lane == 31) ? FULL : ((2u << lane) - 1u);
-        unsigned va = __ballot_sync(FULL, lane < cnt && oa_p != -1) & lower;
-        unsigned vb = __ballot_sync(FULL, lane < cnt && ob_p != -1) & lower;
-        int sa = __shfl_sync(FULL, oa_p, va ? 31 - __clz(va) : 0);
-        int sb = __shfl_sync(FULL, ob_p, vb ? 31 - __clz(vb) : 0);
-        oa_p = va ? sa : carry_a;
-        ob_p = vb ? sb : carry_b;
-        carry_a = __shfl_sync(FULL, oa_p, cnt - 1);
-        carry_b = __shfl_sync(FULL, ob_p, cnt - 1);
-        last_a = carry_a; last_b = carry_b;
-      }
-      if (lane < cnt && gi >= keep0) {
-        if (P.best_asks) reinterpret_cast<int2*>(P.best_asks + (size_t)e * P.n_keep * 2)[gi - keep0] = make_int2(oa_p, oa_v);
-        if (P.best_bids) reinterpret_cast<int2*>(P.best_bids + (size_t)e * P.n_keep * 2)[gi - keep0] = make_int2(ob_p, ob_v);
+        finish_block(base, cnt);
+        i = 0;
       }
     }
     if (P.do_ffill) {
@@ -698,6 +775,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) lob_kernel(const LobP
   } else if (P.mid_in) {
     mid = P.mid_in[e];
     have_mid = true;
+  }
+  if (!(slow && P.do_step && P.do_render)) break;
   }
 
   if (!P.do_step && (P.best_asks || P.best_bids)) {   // get_best_bid_and_ask_inclQuants
