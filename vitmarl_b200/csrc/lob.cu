@@ -29,7 +29,6 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "../../include/vitmarl_b200.h"
@@ -423,33 +422,43 @@ __device__ __noinline__ void slow_message(int32_t* asks, int32_t* bids, int32_t*
 }
 
 // ---------------------------------------------------------------- staging -> registers
-// Returns (warp-uniform) whether the side is tidy.
 template <int RPL>
-__device__ __forceinline__ bool regs_from_smem(Side<RPL>& s, int32_t* sm, int N, int lane) {
-  bool tidy = true;
+__device__ __forceinline__ void regs_from_smem(Side<RPL>& s, int32_t* sm, int N, int lane) {
   s.sm = sm;
 #pragma unroll
   for (int j = 0; j < RPL; ++j) {
-    int r = j * 32 + lane;
     s.p[j] = -1; s.q[j] = -1; s.oid[j] = -1;
     if (VM_EX(j)) {
-      const int2* row = reinterpret_cast<const int2*>(sm + r * 6);
-      int2 a = row[0], b = row[1], c = row[2];
-      s.p[j] = a.x; s.q[j] = a.y; s.oid[j] = b.x;
-      // -1 is the largest unsigned value: min == -1 <=> all fields are -1, max == -1 <=> some field is -1
-      const unsigned lo = __vimin3_u32(__vimin3_u32(a.x, a.y, b.x), __vimin3_u32(b.y, c.x, c.y), 0xffffffffu);
-      const unsigned hi = __vimax3_u32(__vimax3_u32(a.x, a.y, b.x), __vimax3_u32(b.y, c.x, c.y), 0u);
-      const bool all = lo == 0xffffffffu, none = hi != 0xffffffffu;
-      if (!(all || (none && a.y > 0 && a.x != MAXINT && c.x != MAXINT && c.y != MAXINT))) tidy = false;
+      const int32_t* row = sm + (j * 32 + lane) * 6;
+      const int2 a = *reinterpret_cast<const int2*>(row);
+      s.p[j] = a.x; s.q[j] = a.y; s.oid[j] = row[2];
     }
+  }
+}
+
+// Are the `rows` rows of a [rows][6] slab (both sides are contiguous) tidy?  A rolled loop: this runs once per
+// environment and its code size counts against the instruction cache the message loop lives in.
+__device__ __forceinline__ bool slab_is_tidy(const int32_t* sm, int rows, int lane) {
+  bool tidy = true;
+#pragma unroll 1
+  for (int r = lane; r < rows; r += 32) {
+    const int2* row = reinterpret_cast<const int2*>(sm + r * 6);
+    const int2 a = row[0], b = row[1], c = row[2];
+    // -1 is the largest unsigned value: min == -1 <=> all fields are -1, max == -1 <=> some field is -1
+    const unsigned lo = __vimin3_u32(__vimin3_u32(a.x, a.y, b.x), __vimin3_u32(b.y, c.x, c.y), 0xffffffffu);
+    const unsigned hi = __vimax3_u32(__vimax3_u32(a.x, a.y, b.x), __vimax3_u32(b.y, c.x, c.y), 0u);
+    const bool all = lo == 0xffffffffu, none = hi != 0xffffffffu;
+    if (!(all || (none && a.y > 0 && a.x != MAXINT && c.x != MAXINT && c.y != MAXINT))) tidy = false;
   }
   return __all_sync(FULL, tidy);
 }
 
 __device__ __forceinline__ void warp_copy_g2s(int32_t* dst, const int32_t* src, int n, int lane) {
+#pragma unroll 1
   for (int i = lane; i < n; i += 32) dst[i] = src[i];
 }
 __device__ __forceinline__ void warp_copy_s2g(int32_t* dst, const int32_t* src, int n, int lane) {
+#pragma unroll 1
   for (int i = lane; i < n; i += 32) dst[i] = src[i];
 }
 
@@ -663,12 +672,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) lob_kernel(const LobP
   bool have_mid = false;
 #pragma unroll 1
   for (int pass = 0;; ++pass) {   // pass 1 only re-reads the register cache after the literal path ran
-  const bool tidy_a = regs_from_smem<RPL>(asks, sm_asks, N, lane);
-  const bool tidy_b = regs_from_smem<RPL>(bids, sm_bids, N, lane);
+  regs_from_smem<RPL>(asks, sm_asks, N, lane);
+  regs_from_smem<RPL>(bids, sm_bids, N, lane);
   refresh_best<RPL, false>(asks, N, lane);
   refresh_best<RPL, true>(bids, N, lane);
   if (pass == 1) break;
-  bool slow = !(tidy_a && tidy_b);   // this warp runs the literal path (from some message on)
+  bool slow = P.do_step && !slab_is_tidy(sm_asks, 2 * N, lane);   // this warp runs the literal path (from some message on)
 
   if (P.do_step) {
     // ---- message loop: blocks of 32 messages, one per lane -------------------------------
@@ -835,12 +844,13 @@ static int launch_lob(cudaStream_t stream, LobParams& P) {
     if (err == cudaSuccess) err = cudaFuncSetAttribute(lob_kernel<R, B>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);  \
     if (err == cudaSuccess) lob_kernel<R, B><<<grid, block, smem, stream>>>(P);                           \
   } while (0)
-  static const int minb = [] { const char* v = getenv("VITMARL_LOB_MINB"); return v ? atoi(v) : 5; }();
+  // MINB (resident CTAs per SM the register budget is sized for): 5 x 4 warps at 96 registers measured fastest for
+  // N <= 128; 6 or 7 CTAs (80 / 72 registers) are slower although nothing spills inside the message loop.
   switch (rpl) {
     case 1: VM_LAUNCH(1, 5); break;
     case 2: VM_LAUNCH(2, 5); break;
     case 3: VM_LAUNCH(3, 5); break;
-    case 4: if (minb == 7) VM_LAUNCH(4, 7); else if (minb == 6) VM_LAUNCH(4, 6); else VM_LAUNCH(4, 5); break;
+    case 4: VM_LAUNCH(4, 5); break;
     case 5: VM_LAUNCH(5, 3); break;
     case 6: VM_LAUNCH(6, 3); break;
     case 7: VM_LAUNCH(7, 2); break;
