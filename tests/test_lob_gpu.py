@@ -77,6 +77,24 @@ def test_fuzz_step(c_oracle, seed, N, T, M):
     _check_step(c_oracle, asks, bids, trades, msgs[:, :0], 0, T)      # M = 0: pure copy
 
 
+@pytest.mark.parametrize("seed,N,T,M", [(20, 5, 3, 40), (21, 12, 4, 70), (22, 33, 8, 50), (23, 64, 100, 33),
+                                        (24, 100, 100, 64), (25, 101, 7, 45), (26, 200, 16, 64), (27, 256, 5, 20),
+                                        (28, 1, 1, 9), (29, 100, 6, 100)])
+def test_fuzz_step_tidy_books(c_oracle, seed, N, T, M):
+    """Same adversarial value ranges on WELL-FORMED books: the register fast path of the kernel (price-time priority
+    with colliding prices / times / ids, Q2 full sides, Q4/Q5 cancels, trade-log overflow, prefix trade logs) and
+    the hand-over to the literal path in the middle of a step."""
+    rng = np.random.default_rng(seed)
+    for fill in (0.3, 0.9):
+        asks, bids, trades, msgs = fuzz_case(rng, 97, N, T, M, fill=fill, tidy=True)
+        _check_step(c_oracle, asks, bids, trades, msgs, M, T)
+        _check_step(c_oracle, asks, bids, None, msgs, min(5, M), T)
+        # limit orders and non-negative cancels only: no environment ever leaves the fast path
+        calm = msgs.copy()
+        calm[..., 2] = np.abs(calm[..., 2])
+        _check_step(c_oracle, asks, bids, None, calm, M, T)
+
+
 def test_book_depth_sweep_and_large_m(c_oracle):
     """BASELINE configs[2] shapes at oracle-sized E: capacity 10..100, M = 100 and 113."""
     for N in (10, 20, 50, 100):

@@ -17,9 +17,15 @@ def lobster_to_msg(row):
     return np.array([ty, d, int(sz), int(pr), int(oid), int(oid), int(s), ns], dtype=np.int32)
 
 
-def fuzz_case(rng, E, N, T, M, fill=0.6, weird=0.15):
+def fuzz_case(rng, E, N, T, M, fill=0.6, weird=0.15, tidy=False):
     """Adversarial small-range books + messages: collisions of ids / prices / times, -1 fields,
-    negative quantities, unknown (type, side) pairs, full books and full trade logs."""
+    negative quantities, unknown (type, side) pairs, full books and full trade logs.
+    tidy=True keeps the collisions but makes every resting row well formed (no -1 field, qty > 0), every limit
+    message restable and the pre-filled trade rows a prefix: the state the CUDA kernel's register fast path
+    handles (a cancel with a negative quantity still shows up now and then and sends an environment to the
+    literal path in the middle of its step)."""
+    if tidy:
+        weird = 0.0
     asks = np.full((E, N, 6), -1, dtype=np.int32)
     bids = np.full((E, N, 6), -1, dtype=np.int32)
     for side, lo, hi in ((asks, 105, 112), (bids, 98, 106)):
@@ -30,6 +36,9 @@ def fuzz_case(rng, E, N, T, M, fill=0.6, weird=0.15):
         side[..., 3] = rng.integers(-4, 4, size=(E, N))
         side[..., 4] = rng.integers(0, 4, size=(E, N))
         side[..., 5] = rng.integers(0, 4, size=(E, N))
+        if tidy:
+            side[..., 2] = np.where(side[..., 2] == -1, -2, side[..., 2])
+            side[..., 3] = np.where(side[..., 3] == -1, -3, side[..., 3])
         side[~live] = -1
         # some dirty rows: qty <= 0 but not wiped, partial -1 fields
         dirty = rng.random((E, N)) < weird * 0.3
@@ -52,8 +61,16 @@ def fuzz_case(rng, E, N, T, M, fill=0.6, weird=0.15):
     z = rng.random((E, M)) < 0.05
     msgs[z] = 0                                   # all-zero rows are no-ops (JOBA:653)
     trades = np.full((E, T, 8), -1, dtype=np.int32)
-    pre = rng.random((E, T)) < 0.3
-    trades[pre] = rng.integers(-1, 5, size=(int(pre.sum()), 8))
+    if tidy:
+        msgs[..., 4] = np.where(msgs[..., 4] == -1, -2, msgs[..., 4])
+        msgs[..., 5] = np.where(msgs[..., 5] == -1, -3, msgs[..., 5])
+        msgs[z] = 0
+        pre = np.arange(T)[None, :] < rng.integers(0, T + 1, size=(E, 1))
+        trades[pre] = rng.integers(-1, 5, size=(int(pre.sum()), 8))
+        trades[..., 4] = np.where(pre, np.abs(trades[..., 4]), -1)
+    else:
+        pre = rng.random((E, T)) < 0.3
+        trades[pre] = rng.integers(-1, 5, size=(int(pre.sum()), 8))
     return asks, bids, trades, msgs
 
 
