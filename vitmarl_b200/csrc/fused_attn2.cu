@@ -117,6 +117,9 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(bar(B_TMEMSLOT)));
+  // PDL: everything above (and the weight ring of W_TMA, which only reads parameters) overlaps the tail of the
+  // previous kernel; the residual stream is touched only after it has completed.
+  if (warp != W_TMA) { griddep_wait(); griddep_launch_dependents(); }
 
   if (warp == W_TMA) {
     // =============================== weight ring (in MMA issue order) ===============================
@@ -564,8 +567,13 @@ int launch_fused_attn2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat1
   cudaError_t e = cudaFuncSetAttribute(fused_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return check_cuda(e);
   const int tiles = (M + TM - 1) / TM;
-  fused_attn2_kernel<<<min(tiles, num_sms()), THREADS, SMEM_BYTES, stream>>>(tmX, tmWqkv, tmWo, tmOut, p);
-  return check_cuda(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(min(tiles, num_sms())); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return check_cuda(cudaLaunchKernelEx(&cfg, fused_attn2_kernel, tmX, tmWqkv, tmWo, tmOut, p));
 }
 
 }  // namespace vitmarl

@@ -141,6 +141,9 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(bar(B_TMEMSLOT)));
+  // PDL: everything above (and the weight rings of warps 2 / 3, which only read parameters) overlaps the tail of the
+  // previous kernel; the residual stream is touched only after it has completed.
+  if (warp != 2 && warp != 3) { griddep_wait(); griddep_launch_dependents(); }
 
   if (warp == 0) {
     // =============================== x tiles in, output tiles out ===============================
@@ -433,8 +436,13 @@ int launch_fused_mlp2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16
   if (e != cudaSuccess) return check_cuda(e);
   const int pair_tiles = (M + 2 * TM - 1) / (2 * TM);
   const int clusters = min(pair_tiles, num_sms() / 2);
-  fused_mlp2_kernel<<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(tmX, tmW1, tmW2, tmOut, p);
-  return check_cuda(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return check_cuda(cudaLaunchKernelEx(&cfg, fused_mlp2_kernel, tmX, tmW1, tmW2, tmOut, p));
 }
 
 }  // namespace vitmarl

@@ -80,6 +80,15 @@ __device__ __forceinline__ uint64_t umma_desc_from_lo(uint32_t lo, uint32_t sbo_
 }
 // One lane of a converged warp (warp-uniform predicate: the compiler emits a plain predicated instruction stream instead
 // of the per-active-thread loop it generates under `if (lane == 0)`).
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while the previous kernel of
+// the stream is still running; griddep_wait() blocks the calling thread until that kernel has completed and its
+// writes are visible (it returns at once for a normal launch).  Discipline used here: every thread that touches
+// memory the previous kernel reads or writes waits first, and a kernel lets ITS dependent go only after its own
+// wait, so a kernel never overlaps anything older than its immediate predecessor.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));

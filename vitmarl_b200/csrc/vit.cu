@@ -447,9 +447,13 @@ extern "C" int vitmarl_debug_fused_mlp_timeline(long long* device_buf) {
   return VITMARL_OK;
 }
 
-// Tuning switches of the fused kernels (debug / experiments; 0 = defaults).
+// Tuning switches of the fused kernels (debug / experiments).  Bits 0-7: fused_attn2 flags (default 4);
+// bit 8: launch the fused block kernels WITHOUT programmatic dependent launch.
+static bool g_pdl = true;
+namespace vitmarl { bool pdl_enabled() { return g_pdl; } }
 extern "C" int vitmarl_debug_set_flags(int flags) {
   fused_attn2_set_flags(flags & 0xff);
+  g_pdl = (flags & 0x100) == 0;
   return VITMARL_OK;
 }
 

@@ -87,6 +87,7 @@ int launch_fused_attn2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat1
 bool fused_attn2_supported(int D, int heads, int tokens);
 void fused_attn2_set_debug(long long* buf);
 void fused_attn2_set_flags(int flags);
+bool pdl_enabled();                  // programmatic dependent launch of the fused block kernels (default on)
 
 // parameter folding: Wf = scale * W . diag(gamma) (bf16 [N,K]), bias_out = bias + W . beta (fp32 or bf16 [N]); null = identity
 struct FoldJob {
