@@ -135,6 +135,16 @@ int vitmarl_auto_reset(void* stream, int E, int N, int T, int M, int n_windows, 
  * (price >= 0) and involve agent_id as passive or aggressive trader are kept, all others zeroed. */
 int vitmarl_get_agent_trades(void* stream, int E, int T, const int32_t* trades, int agent_id, int32_t* out);
 
+/* The per-step trade reductions of the reward functions, fused in one pass over trades [E,T,8] (int32 wrap-around
+ * arithmetic, as XLA): out [E,8] = [sum qty, sum |qty|, c_rl, buyQuant, sellQuant, TradedVolume, inventory_delta,
+ * sum |qty| of the other executed trades] of the rows get_agent_trades keeps for agent_id, where
+ *   sum qty        = agent_trades[:,1].sum()                                  (vision_env.py:2076-2077, before jnp.abs)
+ *   sum |qty|      = jnp.abs(agentTrades[:,1]).sum()                          (vision_env.py:2163)
+ *   c_rl           = (agentTrades[:,0] // tick_size * |agentTrades[:,1]|).sum() (vision_env.py:2191)
+ *   buy/sellQuant, TradedVolume = buy + sell, inventory_delta = buy - sell     (mm_env.py:1917-1933)
+ * trades and out 16-byte aligned device memory. */
+int vitmarl_agent_trade_stats(void* stream, int E, int T, const int32_t* trades, int agent_id, int tick_size, int32_t* out);
+
 /* Message assembly of MARLEnv.step_env (marl_env.py:272-344): combined[e] = [cancel_msgs[e]; action_msgs[e] with
  * order ids renumbered to order_id_counter[e] - arange(Ma) and rows permuted by perm[e] (jax.random.permutation
  * indices computed by the caller; NULL = no shuffle); data messages] where the data messages are

@@ -410,6 +410,28 @@ def get_agent_trades(trades, agent_id) -> np.ndarray:
     return np.where(mask2[:, None], executed, 0).astype(np.int32)
 
 
+def agent_trade_stats(trades, agent_id, tick_size) -> np.ndarray:
+    """The trade reductions the reward functions take of one environment's trades [T,8], int32 wrap-around like XLA:
+    vision_env.py:2076-2077 (signed sum), :2156-2163 (agentQuant), :2191 (c_rl); mm_env.py:1906-1933 (buyQuant,
+    sellQuant, TradedVolume, inventory_delta); last entry: sum |qty| of otherTrades (mm_env.py:1914)."""
+    trades = np.asarray(trades, dtype=np.int32)
+    executed = np.where((trades[:, 0] >= 0)[:, None], trades, 0).astype(np.int32)
+    mask2 = (agent_id == executed[:, 6]) | (agent_id == executed[:, 7])
+    agent = np.where(mask2[:, None], executed, 0).astype(np.int32)
+    other = np.where(mask2[:, None], 0, executed).astype(np.int32)
+    with np.errstate(over="ignore"):
+        absq = np.abs(agent[:, 1])                       # int32: abs(INT_MIN) stays INT_MIN, as jnp.abs
+        mask_buy = ((agent[:, 1] >= 0) & (agent_id == agent[:, 6])) | ((agent[:, 1] < 0) & (agent_id == agent[:, 7]))
+        mask_sell = ((agent[:, 1] < 0) & (agent_id == agent[:, 6])) | ((agent[:, 1] >= 0) & (agent_id == agent[:, 7]))
+        buy = np.where(mask_buy, absq, 0).astype(np.int32).sum(dtype=np.int32)
+        sell = np.where(mask_sell, absq, 0).astype(np.int32).sum(dtype=np.int32)
+        out = np.array([agent[:, 1].sum(dtype=np.int32), absq.sum(dtype=np.int32),
+                        ((agent[:, 0] // np.int32(tick_size)) * absq).astype(np.int32).sum(dtype=np.int32),
+                        buy, sell, np.int32(buy + sell), np.int32(buy - sell),
+                        np.abs(other[:, 1]).sum(dtype=np.int32)], dtype=np.int32)
+    return out
+
+
 def get_data_messages(message_data, start, step_counter, n_data_msg_per_step, end_time_s=None) -> np.ndarray:
     """base_env.py:341-371 (`_get_data_messages`); lax.dynamic_slice_in_dim clamps the start index.
     end_time_s is given for ep_type == 'fixed_time' only."""

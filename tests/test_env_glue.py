@@ -23,6 +23,18 @@ def test_get_cancel_msgs_known_answer():
     assert O.getCancelMsgs(b, -100, 1, -1, 1, 2).tolist() == [[2, -1, 7, 101, 11, -100, 1, 2]]
 
 
+def test_agent_trade_stats_known_answer():
+    """Two agent trades (one passive buy of 5 @ 2 200 100, one aggressive sell of 3 @ 2 200 300), one foreign trade, one empty row."""
+    t = np.full((4, 8), -1, np.int32)
+    t[0] = [2200100, 5, 11, 12, 34200, 1, -100, 7]       # qty >= 0 and agent passive -> agent BUYS 5
+    t[1] = [2200300, 3, 13, 14, 34200, 2, 8, -100]       # qty >= 0 and agent aggressive -> agent SELLS 3
+    t[2] = [2200200, -4, 15, 16, 34200, 3, 8, 9]         # others
+    s = O.agent_trade_stats(t, -100, 100)
+    assert s.tolist() == [8, 8, 22001 * 5 + 22003 * 3, 5, 3, 8, 2, 4]
+    assert O.agent_trade_stats(t, -1, 100).tolist() == [0, 0, 0, 0, 0, 0, 0, 12]   # the empty row never counts, even for id -1
+    assert np.array_equal(O.get_agent_trades(t, -100)[:, 1], [5, 3, 0, 0])
+
+
 def test_get_agent_trades_known_answer():
     t = np.full((4, 8), -1, np.int32)
     t[0] = [100, 5, 1, 2, 3, 4, -100, 9]
@@ -103,6 +115,14 @@ def test_env_glue_cuda_parity():
         got = jaxob.get_agent_trades(torch.from_numpy(trades).cuda(), agent).cpu().numpy()
         want = np.stack([O.get_agent_trades(trades[e], agent) for e in range(E)])
         assert np.array_equal(got, want)
+    big = trades.copy()
+    big[:, :, 0] = rng.integers(-1, 2_300_000, (E, T))
+    big[:, :, 1] = rng.integers(-2**31, 2**31 - 1, (E, T), dtype=np.int64).astype(np.int32) * (rng.random((E, T)) < 0.1) + rng.integers(-500, 500, (E, T))
+    for tr_, tick in ((trades, 1), (big, 100)):
+        for agent in (-1, 0, 2):
+            got = jaxob.agent_trade_stats(torch.from_numpy(tr_).cuda(), agent, tick).cpu().numpy()
+            want = np.stack([O.agent_trade_stats(tr_[e], agent, tick) for e in range(E)])
+            assert np.array_equal(got, want)
     n_total, n_data, Mc, Ma = 500, 7, 5, 12
     md = rng.integers(-5, 50000, (n_total, 8)).astype(np.int32)
     md[:, 6] = np.sort(rng.integers(34200, 34300, n_total))

@@ -127,6 +127,42 @@ __global__ void __launch_bounds__(128) auto_reset_kernel(const ResetParams p) {
   if (lane == 0 && p.mid) p.mid[e] = __int2float_rn(wadd(bb.x, ba.x)) / 2.0f;   // jnp.float32((best_bid[0] + best_ask[0]) / 2), x64 disabled
 }
 
+// ---------------------------------------------------------------- per-step trade reductions of the reward functions
+// vision_env.py:2076-2078 (signed executed quantity), :2156-2163 (agentQuant), :2191 (c_rl = sum(price // tick * |qty|)),
+// mm_env.py:1906-1936 (_extract_agent_trade_stats: buyQuant / sellQuant / TradedVolume / inventory_delta).
+// One warp per environment; int32 wrap-around arithmetic like XLA; out[e] = 8 int32:
+//   [sum qty, sum |qty|, c_rl, buyQuant, sellQuant, TradedVolume, inventory_delta, sum |qty| of the OTHER executed trades]
+__global__ void __launch_bounds__(128) trade_stats_kernel(int E, int T, const int4* __restrict__ trades, int agent_id, int tick, int4* __restrict__ out) {
+  const int e = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (e >= E) return;
+  const int4* tr = trades + (size_t)e * T * 2;
+  unsigned s_q = 0, s_abs = 0, s_rev = 0, s_buy = 0, s_sell = 0, s_other = 0;
+  for (int r = lane; r < T; r += 32) {
+    const int4 a = __ldg(tr + 2 * r), b = __ldg(tr + 2 * r + 1);   // [price, qty, pass_oid, agr_oid], [t_s, t_ns, pass_tid, agr_tid]
+    const bool executed = a.x >= 0;
+    const int price = executed ? a.x : 0, qty = executed ? a.y : 0, ptid = executed ? b.z : 0, atid = executed ? b.w : 0;
+    const bool mine = agent_id == ptid || agent_id == atid;        // evaluated on the zeroed row, as the reference does
+    const unsigned aq = qty < 0 ? 0u - (unsigned)qty : (unsigned)qty;   // jnp.abs wraps for INT_MIN
+    if (mine) {
+      s_q += (unsigned)qty;
+      s_abs += aq;
+      s_rev += (unsigned)(price / tick) * aq;                      // price >= 0 here: floor division == C division
+      const bool buy = (qty >= 0 && agent_id == ptid) || (qty < 0 && agent_id == atid);
+      const bool sell = (qty < 0 && agent_id == ptid) || (qty >= 0 && agent_id == atid);
+      if (buy) s_buy += aq;
+      if (sell) s_sell += aq;
+    } else {
+      s_other += aq;
+    }
+  }
+  s_q = __reduce_add_sync(0xffffffffu, s_q); s_abs = __reduce_add_sync(0xffffffffu, s_abs); s_rev = __reduce_add_sync(0xffffffffu, s_rev);
+  s_buy = __reduce_add_sync(0xffffffffu, s_buy); s_sell = __reduce_add_sync(0xffffffffu, s_sell); s_other = __reduce_add_sync(0xffffffffu, s_other);
+  if (lane == 0) {
+    out[2 * e] = make_int4((int)s_q, (int)s_abs, (int)s_rev, (int)s_buy);
+    out[2 * e + 1] = make_int4((int)s_sell, (int)(s_buy + s_sell), (int)(s_buy - s_sell), (int)s_other);
+  }
+}
+
 }  // namespace vitmarl
 
 using namespace vitmarl;
@@ -146,6 +182,14 @@ extern "C" int vitmarl_get_agent_trades(void* stream, int E, int T, const int32_
   const int grid = (int)((rows + 255) / 256 < (size_t)num_sms() * 8 ? (rows + 255) / 256 : (size_t)num_sms() * 8);
   agent_trades_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, reinterpret_cast<const int4*>(trades), agent_id,
                                                                            reinterpret_cast<int4*>(out));
+  return check_cuda(cudaGetLastError());
+}
+
+extern "C" int vitmarl_agent_trade_stats(void* stream, int E, int T, const int32_t* trades, int agent_id, int tick_size, int32_t* out) {
+  if (E == 0) return VITMARL_OK;
+  if (E < 0 || T < 0 || tick_size < 1 || !trades || !out || ((reinterpret_cast<uintptr_t>(trades) | reinterpret_cast<uintptr_t>(out)) & 15)) return VITMARL_EINVAL;
+  trade_stats_kernel<<<(E + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(E, T, reinterpret_cast<const int4*>(trades), agent_id, tick_size,
+                                                                               reinterpret_cast<int4*>(out));
   return check_cuda(cudaGetLastError());
 }
 

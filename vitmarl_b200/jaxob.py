@@ -23,7 +23,7 @@ from .config import JAXLOB_Configuration
 
 __all__ = ["init_orderside", "init_msgs_from_l2", "scan_through_entire_array",
            "scan_through_entire_array_save_bidask", "get_best_bid_and_ask_inclQuants",
-           "get_L2_state", "get_vision_L2_state", "getCancelMsgs", "get_agent_trades"]
+           "get_L2_state", "get_vision_L2_state", "getCancelMsgs", "get_agent_trades", "agent_trade_stats"]
 
 
 def _stream() -> int:
@@ -156,6 +156,17 @@ def getCancelMsgs(bookside, agentID: int, size: int, side: int, cancel_time: tor
     ct = cancel_time.to(torch.int32).contiguous()
     out = torch.empty((E, size, 8), dtype=torch.int32, device=book.device)
     _capi.check(_capi.lib().vitmarl_get_cancel_msgs(_stream(), E, N, size, _ptr(book), int(agentID), int(side), _ptr(ct), _ptr(out)))
+    return out
+
+
+def agent_trade_stats(trades, agent_id: int, tick_size: int) -> torch.Tensor:
+    """The trade reductions of the reward functions in one pass (vision_env.py:2076-2078, 2156-2163, 2191;
+    mm_env.py:1906-1936): trades [E,T,8] -> int32 [E,8] = [sum qty, sum |qty|, c_rl, buyQuant, sellQuant, TradedVolume,
+    inventory_delta, sum |qty| of the other executed trades]."""
+    tr = _chk(trades, "trades", 8)
+    E, T, _ = tr.shape
+    out = torch.empty((E, 8), dtype=torch.int32, device=tr.device)
+    _capi.check(_capi.lib().vitmarl_agent_trade_stats(_stream(), E, T, _ptr(tr), int(agent_id), int(tick_size), _ptr(out)))
     return out
 
 
