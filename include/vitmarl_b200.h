@@ -135,6 +135,13 @@ int vitmarl_auto_reset(void* stream, int E, int N, int T, int M, int n_windows, 
  * (price >= 0) and involve agent_id as passive or aggressive trader are kept, all others zeroed. */
 int vitmarl_get_agent_trades(void* stream, int E, int T, const int32_t* trades, int agent_id, int32_t* out);
 
+/* Replaces `_filter_messages` under vmap (vision_env.py:622-684; the same text in mm_env.py:509-571 and exec_env.py:611-673):
+ * cancellations are netted against new orders at the same non-zero price -- the t-th matching action row is paired with the
+ * t-th matching cancel row, both lose rel = (c_qty >= a_qty) * a_qty, and action rows left with quantity 0 become all-zero
+ * dummy messages.  action_msgs / cnl_msgs / outputs [E,n,8] int32, n <= 32, 16-byte aligned; outputs may alias the inputs. */
+int vitmarl_filter_messages(void* stream, int E, int n, const int32_t* action_msgs, const int32_t* cnl_msgs,
+                            int32_t* action_out, int32_t* cnl_out);
+
 /* The per-step trade reductions of the reward functions, fused in one pass over trades [E,T,8] (int32 wrap-around
  * arithmetic, as XLA): out [E,8] = [sum qty, sum |qty|, c_rl, buyQuant, sellQuant, TradedVolume, inventory_delta,
  * sum |qty| of the other executed trades] of the rows get_agent_trades keeps for agent_id, where

@@ -410,6 +410,40 @@ def get_agent_trades(trades, agent_id) -> np.ndarray:
     return np.where(mask2[:, None], executed, 0).astype(np.int32)
 
 
+def filter_messages(action_msgs, cnl_msgs):
+    """`_filter_messages` (vision_env.py:622-684; the same text in mm_env.py:509-571 and exec_env.py:611-673), literal:
+    cancellations are netted against new orders at the same price.  jnp.where(mask, size=n, fill_value=-1) = ascending
+    indices padded with -1; rank_rev(mask) = stable descending rank; int32 arithmetic."""
+    action_msgs = np.array(action_msgs, dtype=np.int32)
+    cnl_msgs = np.array(cnl_msgs, dtype=np.int32)
+    n = action_msgs.shape[0]
+    assert cnl_msgs.shape[0] == n, "(c >= a) * a needs as many cancel rows as action rows"
+
+    def argsort_rev(arr):
+        return (arr.shape[0] - 1 - np.argsort(arr[::-1], kind="stable"))[::-1]
+
+    def rank_rev(arr):
+        return np.argsort(argsort_rev(arr), kind="stable")
+
+    def where_size(mask):
+        idx = np.flatnonzero(mask)
+        return np.concatenate([idx, np.full(n - idx.size, -1, dtype=np.int64)])
+
+    pa, pc = action_msgs[:, 3], cnl_msgs[:, 3]
+    res = (pc[None, :] == pa[:, None]) & (pa[:, None] != 0)
+    a_mask, c_mask = res.any(axis=1), res.any(axis=0)
+    a_i = where_size(a_mask)
+    a = np.where(a_i == -1, 0, action_msgs[a_i][:, 2]).astype(np.int32)
+    c_i = where_size(c_mask)
+    c = np.where(c_i == -1, 0, cnl_msgs[c_i][:, 2]).astype(np.int32)
+    rel = ((c >= a) * a).astype(np.int32)
+    with np.errstate(over="ignore"):
+        action_msgs[:, 2] = action_msgs[:, 2] - rel[rank_rev(a_mask)]
+        action_msgs = np.where((action_msgs[:, 2] == 0)[:, None], 0, action_msgs).astype(np.int32)
+        cnl_msgs[:, 2] = cnl_msgs[:, 2] - rel[rank_rev(c_mask)]
+    return action_msgs, cnl_msgs
+
+
 def agent_trade_stats(trades, agent_id, tick_size) -> np.ndarray:
     """The trade reductions the reward functions take of one environment's trades [T,8], int32 wrap-around like XLA:
     vision_env.py:2076-2077 (signed sum), :2156-2163 (agentQuant), :2191 (c_rl); mm_env.py:1906-1933 (buyQuant,

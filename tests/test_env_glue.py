@@ -23,6 +23,29 @@ def test_get_cancel_msgs_known_answer():
     assert O.getCancelMsgs(b, -100, 1, -1, 1, 2).tolist() == [[2, -1, 7, 101, 11, -100, 1, 2]]
 
 
+def test_filter_messages_known_answers():
+    """The docstring example of the reference (at one level, 3 cancels & 1 action -> 2 cancels, 0 actions), the 'new order
+    larger than the old one' case (nothing is netted), and the pairing quirk: the t-th matching action is netted against
+    the t-th matching cancellation BY POSITION, whatever their prices."""
+    def rows(kind, specs):
+        m = np.zeros((4, 8), np.int32)
+        for i, (q, p) in enumerate(specs):
+            m[i] = [kind, 1, q, p, -150 - i, -100, 34200, 0]
+        return m
+    ao, co = O.filter_messages(rows(1, [(10, 2200100)]), rows(2, [(10, 2200100)] * 3))
+    assert (ao == 0).all() and co[:, 2].tolist() == [0, 10, 10, 0]
+    ao, co = O.filter_messages(rows(1, [(10, 2200100)]), rows(2, [(5, 2200100)]))
+    assert ao[0, 2] == 10 and co[0, 2] == 5                      # 10 > 5: the old order is cancelled in full, the new one placed in full
+    a = rows(1, [(10, 2200100), (10, 2200300)])
+    c = rows(2, [(10, 2200100), (10, 2200100), (10, 2200100), (5, 2200300)])
+    ao, co = O.filter_messages(a, c)
+    assert (ao == 0).all() and co[:, 2].tolist() == [0, 0, 10, 5]   # action 1 @ 2200300 was paired with cancel 1 @ 2200100
+    # price 0 never matches; the inputs are not modified
+    z = np.zeros((2, 8), np.int32); z[:, 2] = 7
+    ao, co = O.filter_messages(z, z)
+    assert np.array_equal(ao, z) and np.array_equal(co, z) and (z[:, 2] == 7).all()
+
+
 def test_agent_trade_stats_known_answer():
     """Two agent trades (one passive buy of 5 @ 2 200 100, one aggressive sell of 3 @ 2 200 300), one foreign trade, one empty row."""
     t = np.full((4, 8), -1, np.int32)
@@ -115,6 +138,14 @@ def test_env_glue_cuda_parity():
         got = jaxob.get_agent_trades(torch.from_numpy(trades).cuda(), agent).cpu().numpy()
         want = np.stack([O.get_agent_trades(trades[e], agent) for e in range(E)])
         assert np.array_equal(got, want)
+    for n in (1, 4, 8, 13):
+        am = rng.integers(-2, 4, (E, n, 8)).astype(np.int32)
+        cm = rng.integers(-2, 4, (E, n, 8)).astype(np.int32)
+        am[..., 3] = rng.integers(0, 4, (E, n)); cm[..., 3] = rng.integers(0, 4, (E, n))      # few price levels: many matches
+        ga, gc = jaxob.filter_messages(torch.from_numpy(am).cuda(), torch.from_numpy(cm).cuda())
+        for e in range(E):
+            wa, wc = O.filter_messages(am[e], cm[e])
+            assert np.array_equal(ga[e].cpu().numpy(), wa) and np.array_equal(gc[e].cpu().numpy(), wc), (n, e)
     big = trades.copy()
     big[:, :, 0] = rng.integers(-1, 2_300_000, (E, T))
     big[:, :, 1] = rng.integers(-2**31, 2**31 - 1, (E, T), dtype=np.int64).astype(np.int32) * (rng.random((E, T)) < 0.1) + rng.integers(-500, 500, (E, T))

@@ -57,6 +57,7 @@ SIGNATURES = {
     "vitmarl_get_cancel_msgs": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "vitmarl_get_agent_trades": (_I, [_P, _I, _I, _P, _I, _P]),
     "vitmarl_agent_trade_stats": (_I, [_P, _I, _I, _P, _I, _I, _P]),
+    "vitmarl_filter_messages": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "vitmarl_auto_reset": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vitmarl_build_step_msgs": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vitmarl_env_step": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,

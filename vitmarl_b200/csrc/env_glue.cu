@@ -163,6 +163,53 @@ __global__ void __launch_bounds__(128) trade_stats_kernel(int E, int T, const in
   }
 }
 
+// ---------------------------------------------------------------- _filter_messages (vision_env.py:622-684 = mm_env.py:509-571)
+// One thread per environment, n <= 32 action rows and as many cancel rows.  Closed forms of the reference's index
+// gymnastics: where(mask, size=n, fill=-1) lists the set rows in ascending order; rank_rev(mask)[i] = (#set before i) for
+// a set row and (#set + #unset before i) for an unset one; rel[t] = (c[t] >= a[t]) * a[t] pairs the t-th matching action
+// with the t-th matching cancellation (0 quantities past the end of either list).
+constexpr int kMaxFilterRows = 32;
+__global__ void __launch_bounds__(128) filter_msgs_kernel(int E, int n, const int32_t* __restrict__ action_in, const int32_t* __restrict__ cnl_in,
+                                                          int32_t* __restrict__ action_out, int32_t* __restrict__ cnl_out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int4* ain = reinterpret_cast<const int4*>(action_in) + (size_t)e * n * 2;
+  const int4* cin = reinterpret_cast<const int4*>(cnl_in) + (size_t)e * n * 2;
+  int pa[kMaxFilterRows], qa[kMaxFilterRows], pc[kMaxFilterRows], qc[kMaxFilterRows];
+  for (int i = 0; i < n; ++i) { const int4 a = ain[2 * i], c = cin[2 * i]; qa[i] = a.z; pa[i] = a.w; qc[i] = c.z; pc[i] = c.w; }
+  unsigned am = 0, cm = 0;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j)
+      if (pc[j] == pa[i] && pa[i] != 0) { am |= 1u << i; cm |= 1u << j; }
+  int a[kMaxFilterRows], c[kMaxFilterRows];       // quantities of the matching rows in order, 0-padded
+  int ka = 0, kc = 0;
+  for (int i = 0; i < n; ++i) { a[i] = 0; c[i] = 0; }
+  for (int i = 0; i < n; ++i) { if (am >> i & 1) a[ka++] = qa[i]; if (cm >> i & 1) c[kc++] = qc[i]; }
+  int rel[kMaxFilterRows];
+  for (int t = 0; t < n; ++t) rel[t] = c[t] >= a[t] ? a[t] : 0;
+  int4* aout = reinterpret_cast<int4*>(action_out) + (size_t)e * n * 2;
+  int4* cout_ = reinterpret_cast<int4*>(cnl_out) + (size_t)e * n * 2;
+  int sa = 0, ua = 0, sc = 0, uc = 0;              // set / unset rows seen so far
+  for (int i = 0; i < n; ++i) {
+    int4 r0 = ain[2 * i], r1 = ain[2 * i + 1];
+    const bool set = am >> i & 1;
+    const int rk = set ? sa : ka + ua;
+    if (set) ++sa; else ++ua;
+    r0.z = wsub(r0.z, rel[rk]);
+    if (r0.z == 0) { r0 = make_int4(0, 0, 0, 0); r1 = r0; }   // actions netted to zero become dummy messages
+    aout[2 * i] = r0; aout[2 * i + 1] = r1;
+  }
+  for (int j = 0; j < n; ++j) {
+    int4 r0 = cin[2 * j];
+    const int4 r1 = cin[2 * j + 1];
+    const bool set = cm >> j & 1;
+    const int rk = set ? sc : kc + uc;
+    if (set) ++sc; else ++uc;
+    r0.z = wsub(r0.z, rel[rk]);
+    cout_[2 * j] = r0; cout_[2 * j + 1] = r1;
+  }
+}
+
 }  // namespace vitmarl
 
 using namespace vitmarl;
@@ -182,6 +229,16 @@ extern "C" int vitmarl_get_agent_trades(void* stream, int E, int T, const int32_
   const int grid = (int)((rows + 255) / 256 < (size_t)num_sms() * 8 ? (rows + 255) / 256 : (size_t)num_sms() * 8);
   agent_trades_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, reinterpret_cast<const int4*>(trades), agent_id,
                                                                            reinterpret_cast<int4*>(out));
+  return check_cuda(cudaGetLastError());
+}
+
+extern "C" int vitmarl_filter_messages(void* stream, int E, int n, const int32_t* action_msgs, const int32_t* cnl_msgs,
+                                       int32_t* action_out, int32_t* cnl_out) {
+  if (E == 0 || n == 0) return VITMARL_OK;
+  if (E < 0 || n < 0 || n > kMaxFilterRows || !action_msgs || !cnl_msgs || !action_out || !cnl_out) return VITMARL_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(action_msgs) | reinterpret_cast<uintptr_t>(cnl_msgs) | reinterpret_cast<uintptr_t>(action_out) |
+       reinterpret_cast<uintptr_t>(cnl_out)) & 15) return VITMARL_EINVAL;
+  filter_msgs_kernel<<<(E + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(E, n, action_msgs, cnl_msgs, action_out, cnl_out);
   return check_cuda(cudaGetLastError());
 }
 

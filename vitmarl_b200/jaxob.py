@@ -23,7 +23,7 @@ from .config import JAXLOB_Configuration
 
 __all__ = ["init_orderside", "init_msgs_from_l2", "scan_through_entire_array",
            "scan_through_entire_array_save_bidask", "get_best_bid_and_ask_inclQuants",
-           "get_L2_state", "get_vision_L2_state", "getCancelMsgs", "get_agent_trades", "agent_trade_stats"]
+           "get_L2_state", "get_vision_L2_state", "getCancelMsgs", "get_agent_trades", "agent_trade_stats", "filter_messages"]
 
 
 def _stream() -> int:
@@ -157,6 +157,18 @@ def getCancelMsgs(bookside, agentID: int, size: int, side: int, cancel_time: tor
     out = torch.empty((E, size, 8), dtype=torch.int32, device=book.device)
     _capi.check(_capi.lib().vitmarl_get_cancel_msgs(_stream(), E, N, size, _ptr(book), int(agentID), int(side), _ptr(ct), _ptr(out)))
     return out
+
+
+def filter_messages(action_msgs, cnl_msgs):
+    """`_filter_messages` batched (vision_env.py:622-684, mm_env.py:509-571): [E,n,8] x [E,n,8] -> (action_msgs, cnl_msgs)."""
+    am = _chk(action_msgs, "action_msgs", 8)
+    cm = _chk(cnl_msgs, "cnl_msgs", 8)
+    if am.shape != cm.shape:
+        raise ValueError("filter_messages: action and cancel messages must have the same shape")
+    E, n, _ = am.shape
+    ao, co = torch.empty_like(am), torch.empty_like(cm)
+    _capi.check(_capi.lib().vitmarl_filter_messages(_stream(), E, n, _ptr(am), _ptr(cm), _ptr(ao), _ptr(co)))
+    return ao, co
 
 
 def agent_trade_stats(trades, agent_id: int, tick_size: int) -> torch.Tensor:
