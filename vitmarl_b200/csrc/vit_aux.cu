@@ -119,11 +119,32 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     g[2 * i] = a.x; g[2 * i + 1] = a.y;
     dg[2 * i] = dg[2 * i + 1] = db[2 * i] = db[2 * i + 1] = 0.f;
   }
-  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
+  // The three row streams (x, dy, residual gradient) of the NEXT row are requested before the current row is reduced:
+  // with ~100 registers only 16 warps fit an SM, so each warp keeps two rows (36 x 128 B) in flight.
+  const int row0 = blockIdx.x * wpb + (threadIdx.x >> 5), stride = gridDim.x * wpb;
+  uint32_t nx[NP], nd[NP], na[NP];
+  auto fetch = [&](int row) {
+    if (row < M) {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        nx[i] = __ldg(reinterpret_cast<const uint32_t*>(x + (size_t)row * D) + lane + 32 * i);
+        nd[i] = __ldg(reinterpret_cast<const uint32_t*>(dy + (size_t)row * D) + lane + 32 * i);
+        na[i] = dx_add ? __ldg(reinterpret_cast<const uint32_t*>(dx_add + (size_t)row * D) + lane + 32 * i) : 0u;
+      }
+    }
+  };
+  fetch(row0);
+  for (int row = row0; row < M; row += stride) {
     float v[2 * NP], d[2 * NP];
-    load_row<NP>(x + (size_t)row * D, lane, v);
-    load_row<NP>(dy + (size_t)row * D, lane, d);
+    uint32_t a[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      v[2 * i] = bf16_lo(nx[i]); v[2 * i + 1] = bf16_hi(nx[i]);
+      d[2 * i] = bf16_lo(nd[i]); d[2 * i + 1] = bf16_hi(nd[i]);
+      a[i] = na[i];
+    }
     const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + row);
+    fetch(row + stride);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < 2 * NP; ++i) {
@@ -136,13 +157,10 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     }
     s1 = warp_sum(s1) / D;
     s2 = warp_sum(s2) / D;
-    float a[2 * NP];
-    if (dx_add) load_row<NP>(dx_add + (size_t)row * D, lane, a);
     uint32_t* out = reinterpret_cast<uint32_t*>(dx + (size_t)row * D);
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-      float r0 = st.y * (d[2 * i] - s1 - v[2 * i] * s2), r1 = st.y * (d[2 * i + 1] - s1 - v[2 * i + 1] * s2);
-      if (dx_add) { r0 += a[2 * i]; r1 += a[2 * i + 1]; }
+      const float r0 = st.y * (d[2 * i] - s1 - v[2 * i] * s2) + bf16_lo(a[i]), r1 = st.y * (d[2 * i + 1] - s1 - v[2 * i + 1] * s2) + bf16_hi(a[i]);
       out[lane + 32 * i] = pack_bf16(r0, r1);
     }
   }
