@@ -46,6 +46,14 @@ errs.append(run(4096, 192, 576, b_mn=True))                 # dX = dY . W
 errs.append(run(192, 192, 8192, epi=3, a_mn=True, b_mn=True))   # dW = dY^T X (split-K, atomics)
 errs.append(run(768, 192, 16384, epi=3, a_mn=True, b_mn=True))
 errs.append(run(256, 128, 512, a_mn=True))
+# CTA-pair kernel with MN-major operands
+errs.append(run(4096, 384, 1536, b_mn=True, res=True))          # staged epilogue, 1.5-block B halves
+errs.append(run(5000, 384, 3072, b_mn=True, bias=True))         # per-thread epilogue, ragged M
+errs.append(run(1536, 384, 32768, epi=3, a_mn=True, b_mn=True)) # dW, 6 x 2 pair tiles, split-K
+errs.append(run(1152, 384, 16384, epi=3, a_mn=True, b_mn=True)) # dW, last pair tile half empty
+errs.append(run(2048, 192, 200 * 64, epi=3, a_mn=True, b_mn=True))
+errs.append(run(384, 1536, 20000, epi=3, a_mn=True, b_mn=True))  # 256 x 384 work items, operands swapped + transposed output
+errs.append(run(1280, 768, 9984, epi=3, a_mn=True, b_mn=True))   # two 384-column work items per row block
 assert max(errs) < 1e-2, max(errs)
 # throughput
 for (M, N, K) in ((262144, 576, 192), (262144, 768, 192), (262144, 192, 768)):

@@ -261,6 +261,10 @@ static int launch_gemm_bn(cudaStream_t stream, const GemmDesc& g) {
 int launch_gemm(cudaStream_t stream, const GemmDesc& g) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0 || !g.A || !g.B || !g.C) { set_last_error("gemm: bad arguments"); return VITMARL_EINVAL; }
   if (g.N % 64 || g.K % 8 || g.lda % 8 || g.ldb % 8 || (g.a_mn_major && g.M % 64)) { set_last_error("gemm: unsupported shape"); return VITMARL_EINVAL; }
+  if (gemm_2cta_enabled() && g.a_mn_major && g.b_mn_major && g.epi == EPI_ATOMIC_F32) {
+    const int rc = launch_gemm2_dw(stream, g);
+    if (rc != 1) return rc;                              // 1: not a shape for the 256 x 384 weight-gradient kernel
+  }
   if (gemm2_supported(g)) return launch_gemm2(stream, g);
   if (g.N % 192 == 0) return launch_gemm_bn<192>(stream, g);
   if (g.N % 128 == 0) return launch_gemm_bn<128>(stream, g);

@@ -29,8 +29,16 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
   if (p.epi == EPI_ATOMIC_F32) {
     if (row_ok) {
       float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col;
+      if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {      // 32 consecutive floats of one row: 16-byte vector reductions
 #pragma unroll
-      for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]) * p.out_scale);
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j]) * p.out_scale),
+                       "f"(__uint_as_float(r[j + 1]) * p.out_scale), "f"(__uint_as_float(r[j + 2]) * p.out_scale),
+                       "f"(__uint_as_float(r[j + 3]) * p.out_scale) : "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]) * p.out_scale);
+      }
     }
   } else {
     float v[32];

@@ -37,6 +37,9 @@ int launch_gemm(cudaStream_t stream, const GemmDesc& g);
 bool gemm2_supported(const GemmDesc& g);
 int launch_gemm2(cudaStream_t stream, const GemmDesc& g);
 void gemm_set_2cta(bool on);
+bool gemm_2cta_enabled();
+// dW-shaped products (MN x MN, split-K, fp32 red.add) on CTA pairs with 256 x 384 work items; returns 1 when the shape is not handled
+int launch_gemm2_dw(cudaStream_t stream, const GemmDesc& g);
 
 // x[B,H,W,C] bf16 -> patches [B*T, P*P*C] bf16, token t = py*(W/P)+px, feature (ph, pw, c)
 int launch_patchify(cudaStream_t s, const __nv_bfloat16* x, __nv_bfloat16* out, int B, int H, int W, int C, int P);
