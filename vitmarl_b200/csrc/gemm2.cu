@@ -267,7 +267,7 @@ int launch_gemm2(cudaStream_t stream, const GemmDesc& g) {
   const int mode = staged_epilogue_mode(g, &add, &add_rows, &add_ld);
   // small-K products are epilogue-bound (staged epilogue, 4-stage ring); large-K products are mainloop-bound and keep the
   // 6-stage ring with the per-thread epilogue hidden behind the next tile's mainloop
-  const bool staged = mode >= 0 && g.K <= 1536;
+  const bool staged = mode >= 0 && g.K <= 1536;   // (also measured for the dX shapes at D = 384: the deeper ring does not beat it)
   if (g.b_mn_major) {
     if (staged) return launch_gemm2_t<true, false, true>(stream, g, mode, add, add_rows, add_ld);
     return launch_gemm2_t<false, false, true>(stream, g, 0, nullptr, 0, 0);
