@@ -260,7 +260,7 @@ def run_ours(args):
         "config": {"workload": "configs[1]: 2-agent MAPPO step shape (MM+EXE), 4096 envs/GPU, M=13 msgs/step, N=T=100, "
                                "64x64x2 LOB raster, ViT-Tiny/8 (D192 L12 h3) forward",
                    "envs_per_gpu": E, "msgs_per_step": M, "image": "64x64x2 bf16", "vit": "tiny/8 D192 L12",
-                   "l2": "per-step working set ~300 MB (residual stream 100 MB + patches 67 MB + raster 67 MB + books/trades 35 MB + weights) > 126 MB L2; no flush needed",
+                   "l2": "per-step working set ~215 MB (residual stream 100 MB + raster written as the patch matrix 67 MB + books/trades 35 MB + weights 11 MB) > 126 MB L2; no flush needed",
                    "parallelism": f"env-sharded x{world}, no data-path collective"},
         "roofline": {"bound": "tensor", "achieved": dom_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": dom_tf / peaks["bf16_tflops_sustained"],

@@ -77,6 +77,11 @@ int vitmarl_lob_best_bid_ask(void* stream, int E, int N, const int32_t* asks, co
 #define VITMARL_IMG_NONE 0
 #define VITMARL_IMG_U8 1   /* uint8 {0,1}          */
 #define VITMARL_IMG_BF16 2 /* bfloat16 {0.0,1.0}   */
+/* bfloat16 raster written directly as the ViT's patch matrix [E, (H/p)*(W/p), p*p*2] (token = py*(W/p)+px, feature =
+ * (ph, pw, c); docs/VIT_SPEC.md) -- the same values as VITMARL_IMG_BF16 in the order vitmarl_vit_fwd's patch-embedding GEMM
+ * reads them (pass save_for_bwd | VITMARL_VIT_INPUT_PATCHES there).  p % 4 == 0, H % p == 0, W % p == 0. */
+#define VITMARL_IMG_BF16_PATCHES 3
+#define VITMARL_IMG_BF16_PATCHES_OF(p) (((p) << 8) | VITMARL_IMG_BF16_PATCHES)
 
 /* Replaces job.get_vision_L2_state (JaxOrderBookArrays.py:1108-1140) and, when `norm` and
  * `mid_price` are given, ExecutionAgent.normalize_vision_obs (vision_env.py:2804-2854);
@@ -213,6 +218,10 @@ int vitmarl_vit_num_params(const VitmarlVitShape* s);
 long long vitmarl_vit_param_elems(const VitmarlVitShape* s, int index, int* is_bf16_matrix);
 /* Bytes of caller-owned activation workspace for fwd (save_for_bwd = 0) or fwd+bwd (1). */
 size_t vitmarl_vit_workspace_bytes(const VitmarlVitShape* s, int save_for_bwd);
+
+/* Flag for save_for_bwd (inference modes 0 / 2 only): x is already the patch matrix [B*T, P*P*C] bf16 (e.g. rendered by
+ * vitmarl_env_step with VITMARL_IMG_BF16_PATCHES_OF(P)), so no patchify pass runs. */
+#define VITMARL_VIT_INPUT_PATCHES 4
 
 /* y[B,D] (fp32) = ViT(x[B,H,W,C] bf16).  Replaces `module.apply({'params': p}, x)`.
  * save_for_bwd: 0 inference, 1 keep the activations vitmarl_vit_bwd needs, 2 inference that REUSES the folded

@@ -180,6 +180,30 @@ def test_fused_env_step_equals_composition(c_oracle, E, M, steps):
         asks, bids, last_a, last_b = w[0], w[1], w[3][:, -1, 0].copy(), w[4][:, -1, 0].copy()
 
 
+def test_raster_written_as_patch_matrix(c_oracle):
+    """`image_patch=p`: the fused step writes the same raster in the ViT's patch-matrix order (token = py*(W/p)+px,
+    feature = (ph, pw, c)) -- bit-identical to patchifying the [E,H,W,2] image -- and the encoder takes it as is."""
+    from vitmarl_b200 import vit
+    asks, bids, blocks = synthetic_case(70, 13, steps=1)
+    a, b = dev(asks), dev(bids)
+    for (H, W, p) in ((64, 64, 8), (128, 128, 16), (64, 32, 4)):
+        st0 = venv.reset(CFG, a.clone(), b.clone(), 13)
+        _, out_img = venv.step(CFG, st0, dev(blocks[0]), image_hw=(H, W), inplace=False)
+        st1 = venv.reset(CFG, a.clone(), b.clone(), 13)
+        _, out_pat = venv.step(CFG, st1, dev(blocks[0]), image_hw=(H, W), inplace=False, image_patch=p)
+        img = out_img.image
+        want = img.view(70, H // p, p, W // p, p, 2).permute(0, 1, 3, 2, 4, 5).reshape(70, (H // p) * (W // p), p * p * 2)
+        assert out_pat.image.shape == want.shape and torch.equal(out_pat.image, want), (H, W, p)
+        assert torch.equal(out_pat.vision_obs, out_img.vision_obs)
+        if (H, W, p) == (64, 64, 8):
+            cfg = vit.VIT_PARITY
+            enc = vit.ViTEncoder(cfg)
+            packed = vit.pack_params(cfg, vit.init_params(cfg, 0, "cuda"))
+            y_img = enc.apply_packed(packed, img).clone()
+            y_pat = enc.apply_packed(packed, out_pat.image, patches=True)
+            assert torch.equal(y_img, y_pat)
+
+
 def test_fused_ffill_with_emptied_books(c_oracle):
     """Sides that go empty mid-step exercise the forward fill and Q10 volumes."""
     E, N, M = 40, 6, 37

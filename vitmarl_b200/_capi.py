@@ -11,7 +11,8 @@ import os
 from . import _build
 
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENODEVICE = 0, -1, -2, -3, -4
-IMG_NONE, IMG_U8, IMG_BF16 = 0, 1, 2
+IMG_NONE, IMG_U8, IMG_BF16, IMG_BF16_PATCHES = 0, 1, 2, 3
+VIT_INPUT_PATCHES = 4
 
 _ERR_NAMES = {EINVAL: "VITMARL_EINVAL (bad shape / null / misaligned buffer)",
               EUNSUPPORTED: "VITMARL_EUNSUPPORTED (cancel_mode 2/3 or simulator_mode 1)",

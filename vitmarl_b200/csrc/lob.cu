@@ -584,7 +584,25 @@ __device__ __forceinline__ void render_env(const Side<RPL>& asks, const Side<RPL
     __syncwarp();
     for (int i = lane; i < 2 * H; i += 32) scratch[i] = bar_length(scratch[i], W);
     __syncwarp();
-    if (P.img_dtype == VITMARL_IMG_BF16) {
+    if ((P.img_dtype & 0xff) == VITMARL_IMG_BF16_PATCHES) {
+      // the raster written directly as the ViT's patch matrix [tokens = (H/p)(W/p), p*p*2] (token = py*(W/p)+px, feature =
+      // (ph, pw, c)): the same bytes as the NHWC image, so the encoder's patchify pass (a 2 x 67 MB copy) disappears.
+      // Chunks are walked in OUTPUT order: 32 lanes x 16 bytes stay one contiguous 512-byte store.
+      const int ps = P.img_dtype >> 8, cpr = ps / 4, cpp = ps * cpr, tpr = W / ps;      // chunks per patch row / per patch, patches per image row
+      uint4* img = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.image) + (size_t)e * H * W * 2);
+      const int total = H * W / 4;
+      for (int c = lane; c < total; c += 32) {
+        const int t = c / cpp, within = c - t * cpp;
+        const int ph = within / cpr, pw0 = (within - ph * cpr) * 4;
+        const int py = t / tpr, px = t - py * tpr;
+        const int r = py * ps + ph, x0 = px * ps + pw0;
+        const int la = scratch[r], lb = scratch[H + r];
+        unsigned w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = ((x0 + k) < la ? 0x3F80u : 0u) | ((x0 + k) < lb ? 0x3F800000u : 0u);
+        img[c] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    } else if (P.img_dtype == VITMARL_IMG_BF16) {
       // 16 bytes = 4 pixels x 2 channels x bf16
       uint4* img = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.image) + (size_t)e * H * W * 2);
       const int chunks_per_row = W / 4, total = H * chunks_per_row;
@@ -826,7 +844,12 @@ static int launch_lob(cudaStream_t stream, LobParams& P) {
     if ((P.raw && (reinterpret_cast<uintptr_t>(P.raw) & 15)) || (P.l2 && (reinterpret_cast<uintptr_t>(P.l2) & 15)) ||
         (P.norm && (reinterpret_cast<uintptr_t>(P.norm) & 7))) return VITMARL_EINVAL;
     if (P.image) {
-      if (P.img_dtype != VITMARL_IMG_U8 && P.img_dtype != VITMARL_IMG_BF16) return VITMARL_EINVAL;
+      const int kind = P.img_dtype & 0xff, ps = P.img_dtype >> 8;
+      if (kind == VITMARL_IMG_BF16_PATCHES) {
+        if (ps < 4 || ps % 4 || P.H % ps || P.W % ps) return VITMARL_EINVAL;
+      } else if (P.img_dtype != VITMARL_IMG_U8 && P.img_dtype != VITMARL_IMG_BF16) {
+        return VITMARL_EINVAL;
+      }
       if (P.H < 1 || P.W < 8 || (P.W % 8) || 2 * P.H > 12 * P.N) return VITMARL_EINVAL;
       if (reinterpret_cast<uintptr_t>(P.image) & 15) return VITMARL_EINVAL;
     }

@@ -153,12 +153,13 @@ static GemmDesc gd(int M, int N, int K, const bf16* A, int lda, bool amn, const 
   return g;
 }
 
-static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, const bf16* x, float* y, uint8_t* ws, bool save, bool reuse_folded = false) {
+static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, const bf16* x, float* y, uint8_t* ws, bool save, bool reuse_folded = false,
+                       bool x_is_patches = false) {
   const Ws w = layout(d, save);
   const int M = d.M, D = d.D;
   auto PB = [&](int i) { return static_cast<const bf16*>(prm[i]); };
   auto PF = [&](int i) { return static_cast<const float*>(prm[i]); };
-  bf16* patches = reinterpret_cast<bf16*>(ws + w.patches);
+  const bf16* patches = x_is_patches ? x : reinterpret_cast<const bf16*>(ws + w.patches);   // the caller may hand in the patch matrix itself
   auto X = [&](int l) { return reinterpret_cast<bf16*>(ws + w.x + (save ? (size_t)l * w.sz_md : 0)); };
   auto XM = [&](int l) { return reinterpret_cast<bf16*>(ws + w.xm + (save ? (size_t)l * w.sz_md : 0)); };
   auto LN1 = [&](int l) { return reinterpret_cast<bf16*>(ws + w.ln1 + (save ? (size_t)l * w.sz_md : 0)); };
@@ -203,7 +204,8 @@ static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, c
   bf16* pos_tile = reinterpret_cast<bf16*>(ws + w.pos_tile);
   if (pos_tiled && !reuse_folded) VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_pos_tile(st, PF(P_POS), pos_tile, d.T, D); }));
   // patch embedding: tokens = patches . Wpe^T + b + pos
-  VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_patchify(st, x, patches, d.B, d.H, d.W, d.C, d.P); }));
+  if (!x_is_patches)
+    VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_patchify(st, x, reinterpret_cast<bf16*>(ws + w.patches), d.B, d.H, d.W, d.C, d.P); }));
   {
     GemmDesc g = gd(M, D, d.Kp, patches, d.Kp, false, PB(P_PE_W), d.Kp, false, X(0), D, EPI_STORE_BF16);
     g.bias = PF(P_PE_B); g.pos = PF(P_POS); g.pos_period = d.T;
@@ -373,9 +375,13 @@ extern "C" int vitmarl_vit_fwd(void* stream, const VitmarlVitShape* s, const voi
   VM_TRY(get_dims(s, d));
   if (d.B == 0) return VITMARL_OK;
   if (!params || !x || !y || !workspace) return VITMARL_EINVAL;
+  const bool x_is_patches = (save_for_bwd & VITMARL_VIT_INPUT_PATCHES) != 0;
+  save_for_bwd &= ~VITMARL_VIT_INPUT_PATCHES;
   const bool save = save_for_bwd == 1;
+  if (x_is_patches && (save || (reinterpret_cast<uintptr_t>(x) & 15))) { set_last_error("vit_fwd: patch-matrix input is for inference and 16-byte aligned"); return VITMARL_EINVAL; }
   if (workspace_bytes < layout(d, save).total) { set_last_error("vit_fwd: workspace too small"); return VITMARL_EINVAL; }
-  return vit_forward(static_cast<cudaStream_t>(stream), d, params, static_cast<const bf16*>(x), y, static_cast<uint8_t*>(workspace), save, save_for_bwd == 2);
+  return vit_forward(static_cast<cudaStream_t>(stream), d, params, static_cast<const bf16*>(x), y, static_cast<uint8_t*>(workspace), save, save_for_bwd == 2,
+                     x_is_patches);
 }
 
 extern "C" int vitmarl_vit_bwd(void* stream, const VitmarlVitShape* s, const void* const* params, void* workspace,

@@ -47,8 +47,11 @@ def reset(cfg: World_EnvironmentConfig, asks: torch.Tensor, bids: torch.Tensor, 
 
 def step(cfg: World_EnvironmentConfig, state: BookState, msgs: torch.Tensor, *, n_levels: int = 10,
          want_obs: bool = True, want_raw: bool = False, image_hw=None, image_dtype=torch.bfloat16,
-         inplace: bool = True) -> tuple[BookState, StepOutput]:
-    """One fused env step for all E environments (msgs int32 [E,M,8])."""
+         inplace: bool = True, image_patch: Optional[int] = None) -> tuple[BookState, StepOutput]:
+    """One fused env step for all E environments (msgs int32 [E,M,8]).
+    ``image_patch=p`` (bf16 only) makes the kernel write the raster directly as the ViT's patch matrix
+    ``[E, (H/p)*(W/p), p*p*2]`` -- the same values as the ``[E,H,W,2]`` image, in the order the patch-embedding GEMM reads
+    them (``ViTEncoder.apply_packed(..., patches=True)``), so the encoder's patchify pass disappears."""
     asks, bids = _chk(state.ask_raw_orders, "asks", 6), _chk(state.bid_raw_orders, "bids", 6)
     msgs = _chk(msgs, "msgs", 8)
     E, N, _ = asks.shape
@@ -69,6 +72,11 @@ def step(cfg: World_EnvironmentConfig, state: BookState, msgs: torch.Tensor, *, 
         H, W = image_hw
         code = {torch.bfloat16: _capi.IMG_BF16, torch.uint8: _capi.IMG_U8}[image_dtype]
         img = torch.empty((E, H, W, 2), dtype=image_dtype, device=dev)
+        if image_patch is not None:
+            if image_dtype != torch.bfloat16 or image_patch % 4 or H % image_patch or W % image_patch:
+                raise _capi.VitmarlError(_capi.EINVAL, "image_patch needs a bf16 raster and a patch size that is a multiple of 4 dividing H and W")
+            code = (int(image_patch) << 8) | _capi.IMG_BF16_PATCHES
+            img = img.view(E, (H // image_patch) * (W // image_patch), image_patch * image_patch * 2)
     rc = _capi.lib().vitmarl_env_step(_stream(), E, N, T, M, _ptr(asks), _ptr(bids), _ptr(msgs), _ptr(last_a), _ptr(last_b),
                                       _ptr(a_out), _ptr(b_out), _ptr(t_out), _ptr(ba), _ptr(bb), _ptr(mid),
                                       n_levels, cfg.tick_size, _ptr(raw), None, _ptr(norm), _ptr(img), code, H, W,

@@ -22,12 +22,13 @@ __all__ = ["RolloutEncoder", "kernels_per_step"]
 
 def kernels_per_step(vit_cfg: vvit.ViTConfig) -> int:
     """Launches of this library's kernels in one rollout step.
-    ViT-Tiny (D=192, 3 heads): 1 env-step + patchify + patch-embed GEMM + L x (fused attention block + fused MLP block)
-    + final LN/pool (the 2 parameter-fold launches run only on the engine's first step).  Other shapes run the unfused sequence: (1 + 4 L) GEMMs + 2 L LayerNorm + L attention."""
+    ViT-Tiny (D=192, 3 heads): 1 env-step (which renders the patch matrix itself: no patchify) + patch-embed GEMM
+    + L x (fused attention block + fused MLP block) + final LN/pool (the 2 parameter-fold launches run only on the engine's
+    first step).  Other shapes run the unfused sequence: (1 + 4 L) GEMMs + 2 L LayerNorm + L attention."""
     L = vit_cfg.depth
     if vit_cfg.dim == 192 and vit_cfg.heads == 3 and vit_cfg.mlp_dim == 768 and vit_cfg.tokens == 64:
-        return 1 + 1 + 1 + 2 * L + 1
-    return 1 + 1 + (1 + 4 * L) + 2 * L + L + 1
+        return 1 + 1 + 2 * L + 1
+    return 1 + (1 + 4 * L) + 2 * L + L + 1
 
 
 class RolloutEncoder:
@@ -50,11 +51,18 @@ class RolloutEncoder:
 
     def step(self, msgs: torch.Tensor) -> torch.Tensor:
         c = self.vit_cfg
+        # the order-book kernel renders the raster directly as the encoder's patch matrix (no patchify pass in between)
         self.state, out = venv.step(self.cfg, self.state, msgs, n_levels=self.n_levels, want_obs=True,
-                                    image_hw=(c.img_h, c.img_w), image_dtype=torch.bfloat16, inplace=True)
+                                    image_hw=(c.img_h, c.img_w), image_dtype=torch.bfloat16, inplace=True, image_patch=c.patch)
         self.last = out
         # the parameters are fixed for the lifetime of this engine (a new one is built after an optimiser update)
-        return self.encoder.apply_packed(self.packed, out.image, params_unchanged=True)
+        return self.encoder.apply_packed(self.packed, out.image, params_unchanged=True, patches=True)
+
+    def last_image(self) -> torch.Tensor:
+        """The last step's raster as the reference-shaped [E,H,W,2] image (a view-permutation of the patch matrix)."""
+        c = self.vit_cfg
+        p, gh, gw = c.patch, c.img_h // c.patch, c.img_w // c.patch
+        return self.last.image.view(self.E, gh, gw, p, p, c.channels).permute(0, 1, 3, 2, 4, 5).reshape(self.E, c.img_h, c.img_w, c.channels)
 
     def step_host(self, msgs_pinned: torch.Tensor):
         """Host-buffer entry: H2D of the step's messages, the step, D2H of the encoding and the vision tensor."""

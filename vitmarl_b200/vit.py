@@ -160,14 +160,20 @@ class ViTEncoder:
         return self._ws
 
     def apply_packed(self, packed, x: torch.Tensor, *, train: bool = False, out: Optional[torch.Tensor] = None,
-                     params_unchanged: bool = False) -> torch.Tensor:
-        """``params_unchanged=True`` (inference only) tells the library that the CONTENTS of ``packed`` are the same as in the
+                     params_unchanged: bool = False, patches: bool = False) -> torch.Tensor:
+        """``patches=True`` (inference only): ``x`` is already the patch matrix ``[B, T, P*P*C]`` bf16 (the fused env step
+        renders it that way, ``env.step(..., image_patch=P)``) and the patchify pass is skipped.
+        ``params_unchanged=True`` (inference only) tells the library that the CONTENTS of ``packed`` are the same as in the
         previous call, so the folded parameters it left in the workspace are reused (the rollout loop between two optimiser
         updates).  It is honoured only when that previous call used the same workspace, batch size and table."""
         if not x.is_cuda:
             raise _capi.VitmarlError(_capi.ENODEVICE, "ViT input must be a CUDA tensor (there is no CPU fallback)")
         c = self.cfg
-        if x.dim() != 4 or tuple(x.shape[1:]) != (c.img_h, c.img_w, c.channels):
+        if patches:
+            want = (c.tokens, c.patch * c.patch * c.channels)
+            if train or x.dim() != 3 or tuple(x.shape[1:]) != want or x.dtype != torch.bfloat16:
+                raise _capi.VitmarlError(_capi.EINVAL, f"patches=True is for inference on a bf16 patch matrix [B,{want[0]},{want[1]}], got {tuple(x.shape)}")
+        elif x.dim() != 4 or tuple(x.shape[1:]) != (c.img_h, c.img_w, c.channels):
             raise _capi.VitmarlError(_capi.EINVAL, f"expected x [B,{c.img_h},{c.img_w},{c.channels}], got {tuple(x.shape)}")
         x = x.to(torch.bfloat16).contiguous()
         B = x.shape[0]
@@ -177,6 +183,8 @@ class ViTEncoder:
         ptrs = (ctypes.c_void_p * len(packed))(*[t.data_ptr() for t in packed])
         key = (ws.data_ptr(), B, id(packed))
         mode = 1 if train else (2 if (params_unchanged and self._fold_key == key) else 0)
+        if patches:
+            mode |= _capi.VIT_INPUT_PATCHES
         rc = _capi.lib().vitmarl_vit_fwd(torch.cuda.current_stream().cuda_stream, ctypes.byref(shape), ptrs, x.data_ptr(),
                                          y.data_ptr(), ws.data_ptr(), ws.numel(), mode)
         _capi.check(rc)
