@@ -212,33 +212,91 @@ int launch_layernorm_bwd(cudaStream_t s, const __nv_bfloat16* x, const float* ga
 }
 
 // ---------------------------------------------------------------- final LN + mean pool (one CTA of 8 warps per image)
+// EIGHT lanes per token row (each lane D/8 features as D/64 16-byte chunks), 32 rows in flight per CTA: a row of 192
+// features is too little work for a whole warp -- with one row per warp the kernel was bound by the two 5-step shuffle
+// reductions per row (45 us for 100 MB), not by memory.  Per-group partial sums are combined in a fixed order
+// (bitwise deterministic).
+__device__ __forceinline__ float group8_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+
 template <int NP>
-__global__ void __launch_bounds__(256) final_ln_pool_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, float* __restrict__ y,
-                                                             float* __restrict__ stats, int T, int D, float eps) {
-  extern __shared__ float red[];   // [warps][D]: per-warp partial sums, combined in a fixed order (bitwise deterministic)
-  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  float acc[2 * NP];
+__global__ void __launch_bounds__(256, NP <= 4 ? 2 : 1) final_ln_pool_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float* __restrict__ y,
+                                                                float* __restrict__ stats, int B, int T, int D, float eps) {
+  extern __shared__ float red[];   // [32 row groups][D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & 7, grp = warp * 4 + (lane >> 3);
+  // Persistent CTAs (thousands of 2-us CTAs were mostly launch and tail): the rows of the NEXT image are requested before
+  // the current one is reduced.  Up to 64 tokens (2 rows per 8-lane group) are held in registers at a time.
+  constexpr int RPG = NP <= 3 ? 2 : 1;
+  uint4 nxt[RPG][NP];
+  auto fetch = [&](int b, int t0) {
+    if (b < B) {
 #pragma unroll
-  for (int i = 0; i < 2 * NP; ++i) acc[i] = 0.f;
-  for (int t = warp; t < T; t += nw) {
-    const int row = b * T + t;
-    float v[2 * NP];
-    load_row<NP>(x + (size_t)row * D, lane, v);
-    float mean, rstd;
-    row_stats<NP>(v, D, eps, mean, rstd);
+      for (int r = 0; r < RPG; ++r) {
+        const int t = t0 + r * 32 + grp;
+        const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)(b * T + (t < T ? t : 0)) * D);
 #pragma unroll
-    for (int i = 0; i < 2 * NP; ++i) acc[i] += (v[i] - mean) * rstd;
-    if (stats && lane == 0) reinterpret_cast<float2*>(stats)[row] = make_float2(mean, rstd);
-  }
+        for (int i = 0; i < NP; ++i) nxt[r][i] = __ldg(src + sub + 8 * i);
+      }
+    }
+  };
+  fetch(blockIdx.x, 0);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    float acc[8 * NP];
 #pragma unroll
-  for (int i = 0; i < NP; ++i)
-    reinterpret_cast<float2*>(red + warp * D)[lane + 32 * i] = make_float2(acc[2 * i], acc[2 * i + 1]);
-  __syncthreads();
-  for (int i = threadIdx.x; i < D; i += blockDim.x) {
-    float s = 0.f;
-    for (int w = 0; w < nw; ++w) s += red[w * D + i];
-    y[(size_t)b * D + i] = s / T * __ldg(gamma + i) + __ldg(beta + i);
+    for (int i = 0; i < 8 * NP; ++i) acc[i] = 0.f;
+    for (int t0 = 0; t0 < T; t0 += 32 * RPG) {           // uniform trip count: the group shuffles run under a full mask
+      uint4 cur[RPG][NP];
+#pragma unroll
+      for (int r = 0; r < RPG; ++r)
+#pragma unroll
+        for (int i = 0; i < NP; ++i) cur[r][i] = nxt[r][i];
+      if (t0 + 32 * RPG < T) fetch(b, t0 + 32 * RPG); else fetch(b + gridDim.x, 0);
+#pragma unroll
+      for (int r = 0; r < RPG; ++r) {
+        const int t = t0 + r * 32 + grp;
+        const bool valid = t < T;
+        float v[8 * NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          const uint4 w = cur[r][i];
+          v[8 * i] = bf16_lo(w.x); v[8 * i + 1] = bf16_hi(w.x); v[8 * i + 2] = bf16_lo(w.y); v[8 * i + 3] = bf16_hi(w.y);
+          v[8 * i + 4] = bf16_lo(w.z); v[8 * i + 5] = bf16_hi(w.z); v[8 * i + 6] = bf16_lo(w.w); v[8 * i + 7] = bf16_hi(w.w);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8 * NP; ++i) s += v[i];
+        const float mean = group8_sum(s) / D;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8 * NP; ++i) { const float d = v[i] - mean; q += d * d; }
+        const float rstd = rsqrtf(group8_sum(q) / D + eps);
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 8 * NP; ++i) acc[i] += (v[i] - mean) * rstd;
+          if (stats && sub == 0) reinterpret_cast<float2*>(stats)[b * T + t] = make_float2(mean, rstd);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      float4* dst = reinterpret_cast<float4*>(red + (size_t)grp * D + (sub + 8 * i) * 8);
+      dst[0] = make_float4(acc[8 * i], acc[8 * i + 1], acc[8 * i + 2], acc[8 * i + 3]);
+      dst[1] = make_float4(acc[8 * i + 4], acc[8 * i + 5], acc[8 * i + 6], acc[8 * i + 7]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      float s = 0.f;
+#pragma unroll 8
+      for (int g = 0; g < 32; ++g) s += red[g * D + i];
+      y[(size_t)b * D + i] = s / T * __ldg(gamma + i) + __ldg(beta + i);
+    }
+    __syncthreads();                                     // red is rewritten for the next image
   }
 }
 
@@ -295,11 +353,20 @@ __global__ void __launch_bounds__(256) final_ln_pool_bwd_kernel(const __nv_bfloa
   }
 }
 
+template <int NP>
+static void launch_final_ln_pool_t(cudaStream_t s, const __nv_bfloat16* x, const float* gamma, const float* beta, float* y, float* stats,
+                                   int B, int T, int D, float eps, size_t smem) {
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(final_ln_pool_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return;
+  final_ln_pool_kernel<NP><<<min(B, 2 * num_sms()), 256, smem, s>>>(x, gamma, beta, y, stats, B, T, D, eps);
+}
+
 int launch_final_ln_pool(cudaStream_t s, const __nv_bfloat16* x, const float* gamma, const float* beta, float* y, float* stats,
                          int B, int T, int D, float eps) {
   if (B <= 0) return VITMARL_OK;
   if (D % 64) return VITMARL_EINVAL;
-  VM_DISPATCH_NP(D, (final_ln_pool_kernel<NP><<<B, 256, 8 * D * sizeof(float), s>>>(x, gamma, beta, y, stats, T, D, eps)));
+  const size_t smem = 32 * (size_t)D * sizeof(float);
+  if ((reinterpret_cast<uintptr_t>(x) & 15)) return VITMARL_EINVAL;
+  VM_DISPATCH_NP(D, (launch_final_ln_pool_t<NP>(s, x, gamma, beta, y, stats, B, T, D, eps, smem)));
   return check_cuda(cudaGetLastError());
 }
 int launch_final_ln_pool_bwd(cudaStream_t s, const __nv_bfloat16* x, const float* gamma, const float* stats, const float* dy,
