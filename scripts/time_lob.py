@@ -7,7 +7,7 @@ from vitmarl_b200.config import World_EnvironmentConfig
 CFG = World_EnvironmentConfig()
 HBM = 6548.2
 
-def run(E, M, N=100, fused=False, image=False, iters=20, quiet=False):
+def run(E, M, N=100, fused=False, image=False, iters=20, quiet=False, patch=None):
     l2 = synth.make_l2_books(E, 7)
     init = torch.from_numpy(synth.init_msgs_from_l2_batched(l2)).cuda()
     a, b, t = jaxob.scan_through_entire_array(CFG, None, init, (jaxob.init_orderside(N, E), jaxob.init_orderside(N, E), None))
@@ -21,7 +21,7 @@ def run(E, M, N=100, fused=False, image=False, iters=20, quiet=False):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         if fused:
-            venv.step(CFG, state, msgs, image_hw=(64, 64) if image else None, inplace=False)
+            venv.step(CFG, state, msgs, image_hw=(64, 64) if image else None, inplace=False, image_patch=patch)
         else:
             jaxob.scan_through_entire_array_save_bidask(CFG, None, msgs, (a, b, None), M)
         e1.record(); torch.cuda.synchronize()
@@ -30,7 +30,7 @@ def run(E, M, N=100, fused=False, image=False, iters=20, quiet=False):
     byts = E * (4 * N * 24 + 100 * 32 + M * 32 + 2 * M * 8)
     if quiet:
         return t, byts
-    print(f"E={E} M={M} N={N} fused={fused} image={image}: {t*1e6:.1f} us  {E*M/t/1e9:.3f} Gmsg/s  {E/t/1e6:.2f} Menv-steps/s  "
+    print(f"E={E} M={M} N={N} fused={fused} image={image} patch={patch}: {t*1e6:.1f} us  {E*M/t/1e9:.3f} Gmsg/s  {E/t/1e6:.2f} Menv-steps/s  "
           f"alg {byts/t/1e9:.0f} GB/s = {byts/t/1e9/HBM:.3f} of HBM peak")
 
 if __name__ == "__main__":
@@ -52,5 +52,5 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--quick" in sys.argv:
         run(4096, 13, iters=2); run(4096, 13, fused=True, image=True, iters=2); run(16384, 100, iters=2); sys.exit(0)
-    run(4096, 13); run(4096, 13, fused=True); run(4096, 13, fused=True, image=True)
+    run(4096, 13); run(4096, 13, fused=True); run(4096, 13, fused=True, image=True); run(4096, 13, fused=True, image=True, patch=8)
     run(4096, 113); run(16384, 13); run(65536, 13); run(65536, 100); run(16384, 100, N=50); run(16384, 100, N=10)

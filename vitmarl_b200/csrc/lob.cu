@@ -591,10 +591,20 @@ __device__ __forceinline__ void render_env(const Side<RPL>& asks, const Side<RPL
       const int ps = P.img_dtype >> 8, cpr = ps / 4, cpp = ps * cpr, tpr = W / ps;      // chunks per patch row / per patch, patches per image row
       uint4* img = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.image) + (size_t)e * H * W * 2);
       const int total = H * W / 4;
+      // patch sizes and grids are powers of two in practice: shifts instead of three integer divisions per chunk
+      const bool pow2 = !(cpr & (cpr - 1)) && !(ps & (ps - 1)) && !(tpr & (tpr - 1));
+      const int s_cpr = __ffs(cpr) - 1, s_cpp = __ffs(cpp) - 1, s_tpr = __ffs(tpr) - 1;
       for (int c = lane; c < total; c += 32) {
-        const int t = c / cpp, within = c - t * cpp;
-        const int ph = within / cpr, pw0 = (within - ph * cpr) * 4;
-        const int py = t / tpr, px = t - py * tpr;
+        int t, ph, pw0, py, px;
+        if (pow2) {
+          t = c >> s_cpp; const int within = c & (cpp - 1);
+          ph = within >> s_cpr; pw0 = (within & (cpr - 1)) * 4;
+          py = t >> s_tpr; px = t & (tpr - 1);
+        } else {
+          t = c / cpp; const int within = c - t * cpp;
+          ph = within / cpr; pw0 = (within - ph * cpr) * 4;
+          py = t / tpr; px = t - py * tpr;
+        }
         const int r = py * ps + ph, x0 = px * ps + pw0;
         const int la = scratch[r], lb = scratch[H + r];
         unsigned w[4];
