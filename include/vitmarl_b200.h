@@ -189,6 +189,9 @@ int vitmarl_gemm_bf16(void* stream, int M, int N, int K,
 /* Select the 2-CTA (tcgen05 cta_group::2, 256-row tiles per CTA pair) GEMM where it applies (1, default) or the
  * 1-CTA kernel only (0). */
 int vitmarl_gemm_set_2cta(int enable);
+/* Test hook for the weight-gradient launch of the backward pass: C[M,N] (fp32) += A^T . B, colsum[M] += column sums of A
+ * (A [K,M], B [K,N] bf16 row-major; colsum may be NULL). */
+int vitmarl_debug_gemm_dw(void* stream, int M, int N, int K, const void* A, const void* B, float* C, float* colsum);
 
 /* Shape of the encoder (docs/VIT_SPEC.md): pre-LN ViT, learned position embedding, no class
  * token, final LayerNorm then mean pool -> [B, dim].  Requires (H/P)*(W/P) == 64 tokens and

@@ -54,6 +54,20 @@ errs.append(run(1152, 384, 16384, epi=3, a_mn=True, b_mn=True)) # dW, last pair 
 errs.append(run(2048, 192, 200 * 64, epi=3, a_mn=True, b_mn=True))
 errs.append(run(384, 1536, 20000, epi=3, a_mn=True, b_mn=True))  # 256 x 384 work items, operands swapped + transposed output
 errs.append(run(1280, 768, 9984, epi=3, a_mn=True, b_mn=True))   # two 384-column work items per row block
+# bias gradient (column sums of A) fused into the weight-gradient kernel / separate pass for the other routes
+def run_colsum(M, N, K):
+    A = (torch.randn(K, M, device="cuda") * 0.5).bfloat16(); B = (torch.randn(K, N, device="cuda") * 0.5).bfloat16()
+    C = torch.zeros(M, N, device="cuda"); cs = torch.full((M,), 2.0, device="cuda")
+    rc = lib.vitmarl_debug_gemm_dw(S(), M, N, K, A.data_ptr(), B.data_ptr(), C.data_ptr(), cs.data_ptr())
+    torch.cuda.synchronize()
+    assert rc == 0, (rc, lib.vitmarl_last_error())
+    e1 = (C - A.float().t() @ B.float()).abs().max().item() / (A.float().t() @ B.float()).abs().max().item()
+    ref = 2.0 + A.float().sum(0)
+    e2 = (cs - ref).abs().max().item() / ref.abs().max().item()
+    print(f"dW+colsum M={M} N={N} K={K}: rel-max-err {e1:.2e} / colsum {e2:.2e}", flush=True)
+    return max(e1, e2)
+for shp in ((1536, 384, 32768), (1152, 384, 20000), (384, 384, 8192), (384, 1536, 8192), (576, 192, 4096), (768, 768, 6000)):
+    errs.append(run_colsum(*shp))
 assert max(errs) < 1e-2, max(errs)
 # throughput
 for (M, N, K) in ((262144, 576, 192), (262144, 768, 192), (262144, 192, 768)):

@@ -52,6 +52,7 @@ SIGNATURES = {
     "vitmarl_vit_set_fused": (_I, [_I]),
     "vitmarl_debug_fused_mlp_timeline": (_I, [_P]),
     "vitmarl_debug_set_flags": (_I, [_I]),
+    "vitmarl_debug_gemm_dw": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "vitmarl_vit_gemm_timing_enable": (_I, [_I]),
     "vitmarl_vit_gemm_timing_read": (_I, [_P, _P, _P]),
     "vitmarl_vit_timing_read_categories": (_I, [_P, _P]),

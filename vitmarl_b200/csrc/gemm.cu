@@ -262,8 +262,13 @@ int launch_gemm(cudaStream_t stream, const GemmDesc& g) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0 || !g.A || !g.B || !g.C) { set_last_error("gemm: bad arguments"); return VITMARL_EINVAL; }
   if (g.N % 64 || g.K % 8 || g.lda % 8 || g.ldb % 8 || (g.a_mn_major && g.M % 64)) { set_last_error("gemm: unsupported shape"); return VITMARL_EINVAL; }
   if (gemm_2cta_enabled() && g.a_mn_major && g.b_mn_major && g.epi == EPI_ATOMIC_F32) {
-    const int rc = launch_gemm2_dw(stream, g);
+    const int rc = launch_gemm2_dw(stream, g);           // (fuses g.colsum_a when it runs the product un-swapped)
     if (rc != 1) return rc;                              // 1: not a shape for the 256 x 384 weight-gradient kernel
+  }
+  if (g.colsum_a) {                                      // generic kernels: the bias gradient is a pass of its own
+    if (!g.a_mn_major) { set_last_error("gemm: colsum_a needs an MN-major A"); return VITMARL_EINVAL; }
+    const int rc = launch_colsum(stream, g.A, g.colsum_a, g.K, g.M);
+    if (rc) return rc;
   }
   if (gemm2_supported(g)) return launch_gemm2(stream, g);
   if (g.N % 192 == 0) return launch_gemm_bn<192>(stream, g);

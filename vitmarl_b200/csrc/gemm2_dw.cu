@@ -30,13 +30,15 @@ constexpr int kABytes = 2 * 8192, kBBytes = 3 * 8192, kStageBytes = kABytes + kB
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kTmemCols = 512;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+constexpr int kOnesBytes = 2048;   // [16 k x 64 n] bf16 ones: B operand of the column-sum MMA
+constexpr int kSmemBytes = kStages * kStageBytes + kOnesBytes + 1024 + 256;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
 }  // namespace g2dw
 
 struct DwParams {
   int M, N, K, kb_per_split, splits;
   float* C; int ldc; float scale; int transpose_out;
+  float* colsum;   // optional: colsum[m] += sum_k A[k][m] (the bias gradient of the layer whose dW this is)
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2dw::kThreads, 1)
@@ -44,7 +46,8 @@ gemm2_dw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   using namespace g2dw;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  const uint32_t ones_base = smem_base + kStages * kStageBytes;
+  const uint32_t bar_base = ones_base + kOnesBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   const uint32_t tfull_bar = bar_base + 8u * (2 * kStages), tempty_bar = bar_base + 8u * (2 * kStages + 1);
@@ -67,6 +70,11 @@ gemm2_dw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (p.colsum) {                                         // ones tile (generic-proxy writes -> visible to the tensor core's async proxy)
+    for (int i = threadIdx.x; i < kOnesBytes / 4; i += kThreads)
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(ones_base + 4u * i), "r"(0x3F803F80u) : "memory");
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -101,10 +109,14 @@ gemm2_dw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ================= MMA issuer (leader CTA only) =================
     if (rank == 0) {
       constexpr uint32_t id256 = umma_idesc_bf16(2 * BM, 256, true, true), id128 = umma_idesc_bf16(2 * BM, 128, true, true);
+      constexpr uint32_t id16 = umma_idesc_bf16(2 * BM, 16, true, true);     // A^T . ones: 16 identical columns of column sums
+      const uint64_t d_ones = umma_desc_from_lo(umma_desc_lo(ones_base, 8192));
+      const bool do_colsum = p.colsum != nullptr;
       int s = 0; uint32_t ph = 0;
       int it = 0;
       for (int w = cluster; w < num_work; w += num_clusters, ++it) {
         const int split = w % p.splits;
+        const bool cs = do_colsum && ((w / p.splits) % tiles_n) == 0;    // the first column tile of each row block carries the sums
         const int kb0 = split * p.kb_per_split, kb1 = min(KB, kb0 + p.kb_per_split);
         mbar_wait(tempty_bar, (it & 1) ^ 1);             // previous work item drained from tensor memory
         tc_fence_after();
@@ -120,6 +132,7 @@ gemm2_dw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               const uint64_t da = umma_desc_from_lo(la + k * 128);
               umma_bf16_2sm(tmem_base, da, umma_desc_from_lo(lb + k * 128), id256, accum);                         // blocks 0-1
               umma_bf16_2sm(tmem_base + 256, da, umma_desc_from_lo(lb + (2 * 8192 >> 4) + k * 128), id128, accum);  // block 2
+              if (cs) umma_bf16_2sm(tmem_base + NT, da, d_ones, id16, accum);
             }
             umma_commit_2sm(empty_bar(s));
           }
@@ -164,6 +177,12 @@ gemm2_dw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       }
+      if (p.colsum && tn == 0 && chalf == 0) {             // column NT of the accumulator: sum over this K range of A[k][row]
+        uint32_t r16[16];
+        tmem_ld_32x16(taddr + NT, r16);
+        tmem_ld_wait();
+        if (row_ok) atomicAdd(p.colsum + row, __uint_as_float(r16[0]));
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_bar & kPeerMask);
@@ -180,14 +199,14 @@ gemm2_dw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 // A = g.A viewed [K, M] (MN-major), B = g.B viewed [K, N]; C fp32 [M, N] (or [N, M] when transpose_out), ld = g.ldc
 static int launch_dw_pair(cudaStream_t stream, const __nv_bfloat16* A, int lda, int M, const __nv_bfloat16* B, int ldb, int N, int K,
-                          float* C, int ldc, float scale, bool transpose_out) {
+                          float* C, int ldc, float scale, bool transpose_out, float* colsum) {
   using namespace g2dw;
   CUtensorMap tmA, tmB;
   int rc;
   if ((rc = make_tmap_2d_bf16(&tmA, A, K, M, (uint64_t)lda * 2, BK, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmB, B, K, N, (uint64_t)ldb * 2, BK, 64))) return rc;
   DwParams p{};
-  p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.scale = scale; p.transpose_out = transpose_out ? 1 : 0;
+  p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.scale = scale; p.transpose_out = transpose_out ? 1 : 0; p.colsum = colsum;
   const int KB = (K + BK - 1) / BK;
   const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / NT);
   const int max_clusters = num_sms() / 2;
@@ -214,9 +233,11 @@ int launch_gemm2_dw(cudaStream_t stream, const GemmDesc& g) {
   const int direct = g.N % g2dw::NT == 0 ? fill(g.M) : 0;      // C   = A^T . B
   const int swapped = g.M % g2dw::NT == 0 ? fill(g.N) : 0;     // C^T = B^T . A: the other dimension becomes the row dimension of the tiles
   if (max(direct, swapped) < 768) return 1;
-  if (swapped >= direct)
-    return launch_dw_pair(stream, g.B, g.ldb, g.N, g.A, g.lda, g.M, g.K, C, g.ldc, g.out_scale, true);
-  return launch_dw_pair(stream, g.A, g.lda, g.M, g.B, g.ldb, g.N, g.K, C, g.ldc, g.out_scale, false);
+  if (swapped > direct || (swapped == direct && !g.colsum_a)) {    // (a fused bias gradient needs A on the row side)
+    if (g.colsum_a) { const int rc = launch_colsum(stream, g.A, g.colsum_a, g.K, g.M); if (rc) return rc; }
+    return launch_dw_pair(stream, g.B, g.ldb, g.N, g.A, g.lda, g.M, g.K, C, g.ldc, g.out_scale, true, nullptr);
+  }
+  return launch_dw_pair(stream, g.A, g.lda, g.M, g.B, g.ldb, g.N, g.K, C, g.ldc, g.out_scale, false, g.colsum_a);
 }
 
 }  // namespace vitmarl

@@ -302,8 +302,11 @@ static int vit_backward(cudaStream_t st, const Dims& d, const void* const* prm, 
     if (e != cudaSuccess) return check_cuda(e);
   }
   // dW[out,in] += dY^T . Xin   (both operands MN-major over the token dimension; split-K red.add)
-  auto dW = [&](float* dw, const bf16* dY, int n_out, const bf16* Xin, int n_in) {
+  // db[out] += column sums of dY: handed to the same launch (the CTA-pair weight-gradient kernel folds it into its main loop as
+  // one more MMA against a tile of ones, so dY is not read a second time; other shapes run the separate column-sum pass)
+  auto dW = [&](float* dw, float* db, const bf16* dY, int n_out, const bf16* Xin, int n_in) {
     GemmDesc g = gd(n_out, n_in, M, dY, n_out, true, Xin, n_in, true, dw, n_in, EPI_ATOMIC_F32);
+    g.colsum_a = db;
     return timed(st, CAT_GEMM_DW, 2.0 * g.M * g.N * g.K, [&] { return launch_gemm(st, g); });
   };
   // dXin[M,n_in] = dY[M,n_out] . W[n_out,n_in]   (W read as the MN-major B operand)
@@ -316,27 +319,22 @@ static int vit_backward(cudaStream_t st, const Dims& d, const void* const* prm, 
   VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_final_ln_pool_bwd(st, X(d.L), PF(p_lnf_g(d)), stf, dy, dA, G(p_lnf_g(d)), G(p_lnf_g(d) + 1), d.B, d.T, D); }));
   for (int l = d.L - 1; l >= 0; --l) {
     // ---- MLP branch: x_{l+1} = xm + fc2(gelu(fc1(ln2(xm))))
-    VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_colsum(st, dA, G(p_layer(l, L_FC2_B)), M, D); }));
-    VM_TRY(dW(G(p_layer(l, L_FC2_W)), dA, D, HACT(l), H));
+    VM_TRY(dW(G(p_layer(l, L_FC2_W)), G(p_layer(l, L_FC2_B)), dA, D, HACT(l), H));
     VM_TRY(dXg(dH, dA, D, PB(p_layer(l, L_FC2_W)), H, EPI_MUL_GELU_GRAD, HPRE(l)));
-    VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_colsum(st, dH, G(p_layer(l, L_FC1_B)), M, H); }));
-    VM_TRY(dW(G(p_layer(l, L_FC1_W)), dH, H, LN2(l), D));
+    VM_TRY(dW(G(p_layer(l, L_FC1_W)), G(p_layer(l, L_FC1_B)), dH, H, LN2(l), D));
     VM_TRY(dXg(dC, dH, H, PB(p_layer(l, L_FC1_W)), D, EPI_STORE_BF16, nullptr));
     VM_TRY(timed(st, CAT_LAYERNORM, 0, [&] { return launch_layernorm_bwd(st, XM(l), PF(p_layer(l, L_LN2_G)), ST2(l), dC, dA, dB, G(p_layer(l, L_LN2_G)), G(p_layer(l, L_LN2_B)), M, D); }));
     // ---- attention branch: xm = x_l + out(attn(qkv(ln1(x_l))))
-    VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_colsum(st, dB, G(p_layer(l, L_OUT_B)), M, D); }));
-    VM_TRY(dW(G(p_layer(l, L_OUT_W)), dB, D, ATT(l), D));
+    VM_TRY(dW(G(p_layer(l, L_OUT_W)), G(p_layer(l, L_OUT_B)), dB, D, ATT(l), D));
     VM_TRY(dXg(dC, dB, D, PB(p_layer(l, L_OUT_W)), D, EPI_STORE_BF16, nullptr));
     VM_TRY(timed(st, CAT_ATTENTION, 0, [&] { return launch_attention_bwd(st, QKV(l), dC, dQKV, d.B, d.heads); }));
-    VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_colsum(st, dQKV, G(p_layer(l, L_QKV_B)), M, 3 * D); }));
-    VM_TRY(dW(G(p_layer(l, L_QKV_W)), dQKV, 3 * D, LN1(l), D));
+    VM_TRY(dW(G(p_layer(l, L_QKV_W)), G(p_layer(l, L_QKV_B)), dQKV, 3 * D, LN1(l), D));
     VM_TRY(dXg(dC, dQKV, 3 * D, PB(p_layer(l, L_QKV_W)), D, EPI_STORE_BF16, nullptr));
     VM_TRY(timed(st, CAT_LAYERNORM, 0, [&] { return launch_layernorm_bwd(st, X(l), PF(p_layer(l, L_LN1_G)), ST1(l), dC, dB, dA, G(p_layer(l, L_LN1_G)), G(p_layer(l, L_LN1_B)), M, D); }));
   }
   // ---- patch embedding
   VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_colsum(st, dA, G(P_POS), d.B, d.T * D); }));     // dpos[t,:] = sum over images
-  VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_colsum(st, dA, G(P_PE_B), M, D); }));
-  VM_TRY(dW(G(P_PE_W), dA, D, patches, d.Kp));
+  VM_TRY(dW(G(P_PE_W), G(P_PE_B), dA, D, patches, d.Kp));
   if (dx) {
     VM_TRY(dXg(patches, dA, D, PB(P_PE_W), d.Kp, EPI_STORE_BF16, nullptr));   // reuse the patches buffer for d(patches)
     VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_unpatchify(st, patches, dx, d.B, d.H, d.W, d.C, d.P); }));
@@ -461,6 +459,17 @@ extern "C" int vitmarl_debug_set_flags(int flags) {
   fused_attn2_set_flags(flags & 0xff);
   g_pdl = (flags & 0x100) == 0;
   return VITMARL_OK;
+}
+
+// Test hook: C[M,N] (fp32, accumulated into) += A^T . B and colsum[M] += column sums of A, A [K,M] / B [K,N] bf16 row-major
+// (the dW + bias-gradient launch of the backward pass).
+extern "C" int vitmarl_debug_gemm_dw(void* stream, int M, int N, int K, const void* A, const void* B, float* C, float* colsum) {
+  GemmDesc g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = static_cast<const bf16*>(A); g.lda = M; g.a_mn_major = true;
+  g.B = static_cast<const bf16*>(B); g.ldb = N; g.b_mn_major = true;
+  g.C = C; g.ldc = N; g.epi = EPI_ATOMIC_F32; g.colsum_a = colsum;
+  return launch_gemm(static_cast<cudaStream_t>(stream), g);
 }
 
 // Use the 2-CTA (cta_group::2) GEMM where it applies (1, default) or only the 1-CTA kernel (0).

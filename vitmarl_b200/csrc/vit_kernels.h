@@ -29,6 +29,8 @@ struct GemmDesc {
   const __nv_bfloat16* pos_tile = nullptr;   // optional [128, N] bf16 copy of `pos` tiled to 128 rows (pos_period must divide 128):
                                              // lets the 2-CTA GEMM add it through its shared-memory-staged epilogue
   float out_scale = 1.0f;
+  float* colsum_a = nullptr;   // MN-major A only (dW = A^T . B): also accumulate the column sums of A (the bias gradient), fp32 [M];
+                               // fused into the weight-gradient kernel when it takes the product, a separate pass otherwise
 };
 
 int num_sms();
