@@ -1,15 +1,20 @@
 #!/usr/bin/env python
-"""Headline benchmark: env-steps/s INCLUDING the ViT observation encode (BASELINE.json metric).
+"""Headline benchmark: env-steps/s INCLUDING the ViT observation encode (BASELINE.json metric), plus -- in the same JSON line,
+under "extra" -- the other two BASELINE metrics (LOB msgs/s at configs[2]'s headline point, ViT-S/16 fwd+bwd ms at configs[3])
+and, for N > 1, the only collective of the path (gradient pmean) and the configs[4] rollout + update iteration.
 
     python bench.py --gpus N --steps K --warmup W              # our arm (one rank per GPU under torchrun for N>1)
-    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU restatement of the reference path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU restatement of the reference path (oracle port)
 
 Workload (BASELINE.json configs[1]): 2-agent MAPPO step shape -- market maker + execution agent,
 M = 1 data + 4 + 8 agent messages = 13 per env-step (jaxob_config.py:43,115,160), E = 4096 environments
 per GPU, N = T = 100 book / trade capacity, 64x64x2 LOB raster, ViT-Tiny/8 (D192, L12, h3) forward.
 One "step" = fused order-book kernel (scan + forward fill + mid + vision tensor + raster) + ViT encode
 for all E environments.  Synthetic LOBSTER-format streams (vitmarl_b200/synth.py), random-init weights.
-Multi-GPU: environments shard across ranks, no data-path collective -> weak scaling.
+Multi-GPU: environments shard across ranks, no data-path collective on the rollout path -> weak scaling.
+
+Timing discipline: `value` and `e2e` come from UN-INSTRUMENTED passes (no events between launches, programmatic dependent
+launch active); the per-kernel-class breakdown that feeds `roofline` comes from a separate pass that carries a timing handle.
 """
 from __future__ import annotations
 
@@ -30,6 +35,17 @@ M_MSGS = 13
 N_ORDERS = 100
 METRIC = "env_steps_per_sec_incl_vit_encode"
 UNIT = "env-steps/s"
+REF_SAMPLE_ENVS = 512          # the CPU arms time a bounded sample of the 4096-env workload per step
+
+
+def workload_config(world: int):
+    """`config` of BOTH arms (the reference arm runs the same workload definition on a bounded sample, see cpu_baseline.sample)."""
+    return {"workload": "configs[1]: 2-agent MAPPO step shape (MM+EXE), 4096 envs/GPU, M=13 msgs/step, N=T=100, "
+                        "64x64x2 LOB raster, ViT-Tiny/8 (D192 L12 h3) forward",
+            "envs_per_gpu": E_PER_GPU, "msgs_per_step": M_MSGS, "image": "64x64x2 bf16", "vit": "tiny/8 D192 L12",
+            "l2": "per-step working set ~215 MB (residual stream 100 MB + raster written as the patch matrix 67 MB + books/trades 35 MB + "
+                  "weights 11 MB) > 126 MB L2; no flush needed",
+            "parallelism": f"env-sharded x{world}, no data-path collective"}
 
 
 def _peaks():
@@ -39,6 +55,16 @@ def _peaks():
         return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
                 "source": "MEASURED_PEAKS.json (of measured)"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+def _ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json names the file
+    each figure was read from); None when no capture of this kernel is committed."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p)).get(kernel)
+    return (d["dram_bytes_per_launch"], d["source"]) if d else (None, None)
 
 
 class ClockSampler:
@@ -96,9 +122,10 @@ def _dist_env():
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
-def cpu_reference_steps(E: int, steps: int, seed: int = 1234, threads: int = 0):
+def cpu_reference_steps(E: int, steps: int, warmup: int = 1, seed: int = 1234, threads: int = 0):
     """The CPU restatement of the reference path (oracle/) on the host cores: C/OpenMP order-book step +
-    ffill/mid + vision tensor + raster, then the fp32 PyTorch ViT-Tiny forward.  Returns seconds per step."""
+    ffill/mid + vision tensor + raster, then the fp32 PyTorch ViT-Tiny forward.  `warmup` untimed steps first
+    (Speed_test.py:205-217), then exactly `steps` timed ones.  Returns (seconds per step, threads)."""
     import numpy as np
     import torch
     from oracle import c_oracle as C
@@ -111,13 +138,14 @@ def cpu_reference_steps(E: int, steps: int, seed: int = 1234, threads: int = 0):
     empty = np.full((E, N_ORDERS, 6), -1, dtype=np.int32)
     asks, bids, _, _, _ = C.lob_step(empty, empty.copy(), synth.init_msgs_from_l2_batched(l2), want_best=False, nthreads=threads)
     stream = synth.MessageStream(E, seed)
-    blocks = [stream.next(M_MSGS) for _ in range(steps + 1)]
+    blocks = [stream.next(M_MSGS) for _ in range(min(steps + warmup, 32))]      # cycled: the books keep evolving
     cfg = vit.VIT_TINY_8
     params = vit.init_params(cfg, 0, "cpu")
     ba, bb = C.best_bid_ask(asks, bids)
     last_a, last_b = ba[:, 0].copy(), bb[:, 0].copy()
-    times = []
-    for i, msgs in enumerate(blocks):
+    total = 0.0
+    for i in range(warmup + steps):
+        msgs = blocks[i % len(blocks)]
         t0 = time.perf_counter()
         asks, bids, trades, bas, bbs = C.lob_step(asks, bids, msgs, nthreads=threads)
         fa, fb, mid = C.ffill_mid(bas, bbs, last_a, last_b)
@@ -127,34 +155,205 @@ def cpu_reference_steps(E: int, steps: int, seed: int = 1234, threads: int = 0):
         float(y.sum())
         dt = time.perf_counter() - t0
         last_a, last_b = fa[:, -1, 0].copy(), fb[:, -1, 0].copy()
-        if i > 0:          # first call is the warm-up (Speed_test.py:205-217)
-            times.append(dt)
-    return sum(times) / len(times), threads
+        if i >= warmup:
+            total += dt
+    return total / steps, threads
 
 
 def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path.  The reference is pure JAX and JAX is not installable
+    here (no wheel, no network), so the oracle PORT stands in (kind "port").  EXACTLY args.steps timed steps after args.warmup
+    untimed ones; each step is a bounded sample (REF_SAMPLE_ENVS of the 4096 environments) of the workload named in `config`."""
     rank, world, _ = _dist_env()
     if rank != 0:
         return
-    E = 512                                  # bounded sample of the 4096-env workload per "step"
-    sec, threads = cpu_reference_steps(E, max(1, min(args.steps, 6)))
+    E = REF_SAMPLE_ENVS
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    sec, threads = cpu_reference_steps(E, steps, warmup)
     v = E / sec
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32+f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: MM+EXE (M=13 msgs/step), N=T=100, 64x64x2 raster, ViT-Tiny/8 fwd; bounded sample",
-                       "envs_per_step_sample": E, "envs_full": E_PER_GPU},
+            "config": workload_config(max(1, args.gpus)),
+            "sample_envs_per_step": E,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{E} envs/step x {max(1, min(args.steps, 6))} steps (C/OpenMP book+render, torch-CPU fp32 ViT); "
-                                       "JAX is not installable here, so the oracle port stands in for jax[cpu]"},
+                             "sample": f"{E} of the {E_PER_GPU} envs per step x {steps} timed steps after {warmup} warm-up steps "
+                                       "(C/OpenMP book+render oracle, torch-CPU fp32 ViT oracle); JAX is not installable here, so the "
+                                       "oracle port stands in for jax[cpu]; ms_per_step is per SAMPLE step"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ extras
+def _flush_l2(buf):
+    buf.add_(1)          # 256 MB read + write: evicts the 126 MB L2
+
+
+def extra_lob(peaks):
+    """BASELINE metric (ii) at configs[2]'s headline point: N = 100 levels per side, E = 65536 envs, M = 100 data messages per
+    launch (and the M = 13 step shape), L2 flushed before every timed launch, CUDA events around each launch."""
+    import numpy as np
+    import torch
+    from vitmarl_b200 import jaxob, synth
+    from vitmarl_b200.config import World_EnvironmentConfig
+    cfg = World_EnvironmentConfig()
+    E, N, T = 65536, 100, 100
+    l2 = synth.make_l2_books(E, 99)
+    init = torch.from_numpy(synth.init_msgs_from_l2_batched(l2)).cuda()
+    a, b, _ = jaxob.scan_through_entire_array(cfg, None, init, (jaxob.init_orderside(N, E), jaxob.init_orderside(N, E), None))
+    stream = synth.MessageStream(E, 99)
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.int32, device="cuda")
+    out = {}
+    for M in (100, 13):
+        blocks = [torch.from_numpy(stream.next(M)).cuda() for _ in range(4)]
+        aa, bb = a.clone(), b.clone()
+        times = []
+        for i in range(3 + 10):
+            _flush_l2(flush)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            (aa, bb, _), _ = jaxob.scan_through_entire_array_save_bidask(cfg, None, blocks[i % 4], (aa, bb, None), M)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                times.append(e0.elapsed_time(e1) * 1e-3)
+        t = statistics.median(times)
+        bytes_alg = E * (2 * (2 * N * 24) + T * 32 + M * 32 + 2 * M * 8)
+        out[f"M{M}"] = {"msgs_per_s": E * M / t, "us_per_launch": t * 1e6, "algorithmic_GBps": bytes_alg / t / 1e9,
+                        "frac_of_hbm": bytes_alg / t / 1e9 / peaks["hbm_gbs"], "bytes_per_env_step": bytes_alg // E}
+    out["config"] = "configs[2] point: N=100 levels/side, E=65536 envs, one launch = M messages per env, L2 flushed, median of 10"
+    del flush
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_vit_train(model: str, B: int, peaks, steps: int = 3, warmup: int = 3):
+    """BASELINE metric (iii): ViT encoder fwd+bwd ms (configs[3]: ViT-S/16 bf16 on 128x128x2, batch 8192)."""
+    import torch
+    from vitmarl_b200 import _capi, vit
+    cfg = vit.VIT_SMALL_16 if model == "small16" else vit.VIT_TINY_8
+    free, _ = torch.cuda.mem_get_info()
+    enc = vit.ViTEncoder(cfg)
+    need = _capi.lib().vitmarl_vit_workspace_bytes(__import__("ctypes").byref(enc._shape(B)), 1)
+    if need + (6 << 30) > free:
+        return {"skipped": f"workspace {need / 1e9:.0f} GB > free {free / 1e9:.0f} GB"}
+    packed = vit.pack_params(cfg, vit.init_params(cfg, 0, "cuda"))
+    g = torch.Generator(device="cpu").manual_seed(0)
+    lens = torch.randint(0, cfg.img_w + 1, (B, cfg.img_h, 1, cfg.channels), generator=g)
+    x = (torch.arange(cfg.img_w)[None, None, :, None] < lens).to(torch.bfloat16).cuda()
+    dy = torch.randn(B, cfg.dim, generator=g).cuda()
+    grads = [torch.empty(t.shape, dtype=torch.float32, device="cuda") for t in packed]
+
+    def step():
+        enc.apply_packed(packed, x, train=True)
+        enc.vjp_packed(packed, dy, grads=grads)
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    # per-class breakdown from a separate instrumented pass
+    tm = _capi.Timing()
+    enc.options.timing = tm.handle
+    step()
+    cat_ms, cat_n, _ = tm.read()
+    enc.options.timing = None
+    tm.close()
+    T, D, L, P, C = cfg.tokens, cfg.dim, cfg.depth, cfg.patch, cfg.channels
+    F = 2 * T * P * P * C * D + L * (24 * T * D * D + 4 * T * T * D)
+    tf = 3 * F * B / (ms * 1e-3) / 1e12
+    res = {"ms": ms, "batch": B, "model": model, "algorithmic_tflop": 3 * F * B / 1e12, "achieved_tflops": tf,
+           "frac_of_burst": tf / peaks["bf16_tflops"], "frac_of_sustained": tf / peaks["bf16_tflops_sustained"],
+           "workspace_GB": need / 1e9,
+           "ms_by_kernel_class": {nm: round(cat_ms[i], 3) for i, nm in enumerate(_capi.Timing.NAMES) if cat_n[i]}}
+    del enc, x, grads, packed
+    torch.cuda.empty_cache()
+    return res
+
+
+def extra_allreduce(dist, world: int):
+    """The one collective of the path in isolation: pmean of the ViT-Tiny gradient table (21.5 MB fp32) -- one ncclAllReduce(avg)
+    over the flat table and the per-block bucketed form the backward pass drives; bus bandwidth = 2 (N-1)/N * bytes / t against the
+    725 GB/s measured 8-rank reference (B200_PROFILING.md)."""
+    import torch
+    from vitmarl_b200 import parallel, vit
+    cfg = vit.VIT_TINY_8
+    enc = vit.ViTEncoder(cfg)
+    shapes = [t.shape for t in vit.pack_params(cfg, vit.init_params(cfg, 0, "cuda"))]
+    out = {}
+    for name, ranges in (("single", None), ("bucketed", enc.bucket_param_ranges())):
+        red = parallel.GradAllReducer(shapes, device="cuda", bucket_ranges=ranges, double_buffer=False)
+        for _ in range(5):
+            red.allreduce_mean(use_events=False)
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 20
+        e0.record()
+        for _ in range(n):
+            red.allreduce_mean(use_events=False)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n * 1e-3], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = float(t)
+        nbytes = red.flat.numel() * 4
+        out[name] = {"us": t * 1e6, "bytes": nbytes, "bus_GBps": 2 * (world - 1) / world * nbytes / t / 1e9,
+                     "frac_of_725": 2 * (world - 1) / world * nbytes / t / 1e9 / 725.0, "collectives": len(red.bucket_spans)}
+    return out
+
+
+def extra_train_step_dp(dist, world: int, B: int = 8192):
+    """Data-parallel ViT-Tiny/8 training step at the configs[4] minibatch shape: forward + backward over B images per GPU with the
+    bucketed gradient pmean hung behind the backward's events, against the same step without any collective -> the EXPOSED
+    collective time per minibatch (max over ranks)."""
+    import torch
+    from vitmarl_b200 import parallel, vit
+    cfg = vit.VIT_TINY_8
+    enc = vit.ViTEncoder(cfg)
+    packed = vit.pack_params(cfg, vit.init_params(cfg, 0, "cuda"))
+    red = parallel.GradAllReducer([t.shape for t in packed], device="cuda", bucket_ranges=enc.bucket_param_ranges())
+    g = torch.Generator(device="cpu").manual_seed(dist.get_rank())
+    x = (torch.rand(B, cfg.tokens, cfg.patch_dim, generator=g) < 0.3).to(torch.bfloat16).cuda()
+    dy = torch.randn(B, cfg.dim, generator=g).cuda()
+
+    def step(collective: bool):
+        enc.apply_packed(packed, x, train=True, patches=True)
+        enc.vjp_packed(packed, dy, grads=red.grads(), flat=red.flat, bucket_events=red.events if collective else None)
+        if collective:
+            red.allreduce_mean(async_op=True)
+            red.swap()
+            red.wait()
+
+    res = {}
+    for name, coll in (("no_collective", False), ("with_pmean", True)):
+        for _ in range(3):
+            step(coll)
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 5
+        e0.record()
+        for _ in range(n):
+            step(coll)
+        e1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[name + "_ms"] = float(t)
+    res["exposed_collective_us_per_minibatch_step"] = (res["with_pmean_ms"] - res["no_collective_ms"]) * 1e3
+    res["images_per_gpu"] = B
+    del enc, x, red
+    torch.cuda.empty_cache()
+    return res
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
-    import ctypes
     import numpy as np
     import torch
     rank, world, local = _dist_env()
@@ -166,8 +365,9 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from vitmarl_b200 import _capi, jaxob, rollout, synth, vit
+    from vitmarl_b200 import env as venv
     from vitmarl_b200.config import World_EnvironmentConfig
-    lib = _capi.lib()
+    _capi.lib()
     cfg = World_EnvironmentConfig()
     vcfg = vit.VIT_TINY_8
     E, M, K, W = E_PER_GPU, M_MSGS, args.steps, args.warmup
@@ -207,83 +407,133 @@ def run_ours(args):
             t = float(tt.item())
         return t
 
-    # ---- device-resident run (value) with per-launch GEMM event timing and clock sampling -----------------
+    # ---- (1) device-resident run: `value`.  No events between launches, clocks sampled during the region ----------
     sampler = ClockSampler(local)
-    lib.vitmarl_vit_gemm_timing_enable(1)
     if rank == 0:
         sampler.start()
     t_dev = timed(eng.step, False)
     clocks = sampler.stop() if rank == 0 else None
-    ms, n, fl = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
-    lib.vitmarl_vit_gemm_timing_read(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl))
-    cat_ms, cat_n = (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
-    lib.vitmarl_vit_timing_read_categories(cat_ms, cat_n)
-    lib.vitmarl_vit_gemm_timing_enable(0)
     feats_dev = eng.step(msgs_dev[-1]).clone()
-    # ---- end-to-end run through the host-buffer API (pinned H2D of the messages, D2H of the encoding) -------
+    # ---- (2) end-to-end run through the host-buffer API (pinned H2D of the messages, D2H of the encoding) -------
     t_e2e = timed(eng.step_host, True)
+    # ---- (3) separate INSTRUMENTED pass for the per-kernel-class breakdown (CUDA events around every ViT launch) ----
+    tm = _capi.Timing()
+    eng.encoder.options.timing = tm.handle
+    t_instr = timed(eng.step, False)
+    cat_ms, cat_n, gemm_flops = tm.read()
+    eng.encoder.options.timing = None
+    tm.close()
+    # the order-book kernel is launched by env.step (not in the ViT log): time it alone, same inputs, events around each launch
+    st = venv.reset(cfg, asks0.clone(), bids0.clone(), M)
+    bufs = venv.StepBuffers()
+    lob_t = []
+    for i in range(W + K):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st, _ = venv.step(cfg, st, msgs_dev[i], n_levels=10, want_obs=True, image_hw=(vcfg.img_h, vcfg.img_w), image_patch=vcfg.patch, buffers=bufs)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= W:
+            lob_t.append(e0.elapsed_time(e1))
+    lob_ms = statistics.median(lob_t)
     torch.cuda.synchronize()
 
+    peaks = _peaks()
+    extra = {}
+    if world > 1 and not args.no_extra:
+        extra["grad_allreduce"] = extra_allreduce(dist, world)
+        extra["train_step_dp_tiny8"] = extra_train_step_dp(dist, world)
+        if not args.no_loop:
+            from vitmarl_b200 import mappo_loop
+            del eng
+            torch.cuda.empty_cache()
+            loop = mappo_loop.MappoLoop(8192, 128, 4, 16, 8192, M, rank=rank, world=world)
+            extra["mappo_iteration_configs4"] = loop.run(dist)
+            del loop
+            torch.cuda.empty_cache()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-    peaks = _peaks()
-    steps_logged = W + K                      # the event log covers warm-up + timed steps of the device-resident run
-    names = ["gemm", "fused_mlp", "fused_attn_block", "attention", "layernorm", "other"]
-    breakdown = {nm: {"ms_per_step": cat_ms[i] / steps_logged, "launches_per_step": cat_n[i] / steps_logged}
-                 for i, nm in enumerate(names) if cat_n[i]}
-    # roofline of the DOMINANT kernel = the fused MLP block (largest share of the step): algorithmic FLOPs per launch
-    # 4 * tokens * D * mlp (DESIGN.md "Kernels") / its average launch duration (CUDA events around every launch)
+    steps_logged = W + K                      # the event log covers warm-up + timed steps of the instrumented pass
+    step_ms = t_dev / K * 1e3
     tokens = E * vcfg.tokens
-    mlp_flops = 4.0 * tokens * vcfg.dim * vcfg.mlp_dim
-    attn_flops = 8.0 * tokens * vcfg.dim * vcfg.dim + 4.0 * tokens * vcfg.tokens * vcfg.dim
-    mlp_us = cat_ms[1] / max(cat_n[1], 1) * 1e3
-    attn_us = cat_ms[2] / max(cat_n[2], 1) * 1e3
-    dom_tf = mlp_flops / max(mlp_us * 1e-6, 1e-12) / 1e12
-    # all tcgen05 launches of the step together (patch-embed GEMM + 24 fused block kernels)
-    gemm_ms_total, gemm_launches, gemm_flops = ms.value, n.value, fl.value
-    all_tf = gemm_flops / max(gemm_ms_total * 1e-3, 1e-12) / 1e12
+    classes = {
+        "fused_attn_block": {"kernel": "vitmarl::fused_attn2_kernel (LN1+QKV+softmax+PV+proj+residual, tcgen05 + TMEM operands)", "idx": 2,
+                             "key": "fused_attn2_kernel",
+                             "flops": 8.0 * tokens * vcfg.dim * vcfg.dim + 4.0 * tokens * vcfg.tokens * vcfg.dim},
+        "fused_mlp": {"kernel": "vitmarl::fused_mlp2_kernel (LN2+FC1+GELU+FC2+residual, CTA-pair tcgen05)", "idx": 1, "key": "fused_mlp2_kernel",
+                      "flops": 4.0 * tokens * vcfg.dim * vcfg.mlp_dim},
+        "gemm": {"kernel": "vitmarl::gemm2_kernel (patch embedding)", "idx": 0, "key": "gemm2_kernel", "flops": 2.0 * tokens * vcfg.patch_dim * vcfg.dim},
+    }
+    breakdown = {nm: {"ms_per_step": cat_ms[i] / steps_logged, "launches_per_step": cat_n[i] / steps_logged}
+                 for i, nm in enumerate(_capi.Timing.NAMES) if cat_n[i]}
+    breakdown["lob_env_step"] = {"ms_per_step": lob_ms, "launches_per_step": 1.0}
+    per_kernel = {}
+    for nm, c in classes.items():
+        n = cat_n[c["idx"]]
+        if not n:
+            continue
+        us = cat_ms[c["idx"]] / n * 1e3
+        tf = c["flops"] / (us * 1e-6) / 1e12
+        per_kernel[nm] = {"kernel": c["kernel"], "key": c["key"], "flops_per_launch": c["flops"], "avg_launch_us": us, "achieved": tf,
+                          "frac_of_burst": tf / peaks["bf16_tflops"], "frac_of_sustained": tf / peaks["bf16_tflops_sustained"],
+                          "ms_per_step": cat_ms[c["idx"]] / steps_logged,
+                          "share_of_step": (cat_ms[c["idx"]] / steps_logged) / (t_instr / K * 1e3)}
+    dom_name = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
+    dom = per_kernel[dom_name]
+    # denominator: the burst figure unless the timed region is long enough (>= 1 s) for the power cap to settle the clocks
+    region_s = t_dev
+    use_sustained = region_s >= 1.0
+    peak = peaks["bf16_tflops_sustained"] if use_sustained else peaks["bf16_tflops"]
+    traffic, traffic_src = _ncu_traffic(dom["key"])
+    tc_ms = sum(cat_ms[i] for i in (0, 1, 2)) / steps_logged
+    all_tf = (gemm_flops / steps_logged) / (tc_ms * 1e-3) / 1e12
+    step_flops = gemm_flops / steps_logged
     value = world * E * K / t_dev
     e2e = world * E * K / t_e2e
     # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        Es = 512
-        sec, threads = cpu_reference_steps(Es, 3)
-        cpu = {"value": Es / sec, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{Es} envs/step x 3 steps of the same workload (C/OpenMP book+render oracle, torch-CPU fp32 ViT oracle)"}
+        sec, threads = cpu_reference_steps(REF_SAMPLE_ENVS, 3, 1)
+        cpu = {"value": REF_SAMPLE_ENVS / sec, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{REF_SAMPLE_ENVS} of the {E} envs per step x 3 timed steps after 1 warm-up (C/OpenMP book+render oracle, torch-CPU fp32 ViT oracle)"}
+    if world == 1 and not args.no_extra:
+        del eng
+        torch.cuda.empty_cache()
+        extra["lob_msgs_per_s_configs2"] = extra_lob(peaks)
+        extra["vit_s16_fwd_bwd_configs3"] = extra_vit_train("small16", 8192, peaks)
+        extra["vit_tiny8_fwd_bwd_b8192"] = extra_vit_train("tiny8", 8192, peaks)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "configs[1]: 2-agent MAPPO step shape (MM+EXE), 4096 envs/GPU, M=13 msgs/step, N=T=100, "
-                               "64x64x2 LOB raster, ViT-Tiny/8 (D192 L12 h3) forward",
-                   "envs_per_gpu": E, "msgs_per_step": M, "image": "64x64x2 bf16", "vit": "tiny/8 D192 L12",
-                   "l2": "per-step working set ~215 MB (residual stream 100 MB + raster written as the patch matrix 67 MB + books/trades 35 MB + weights 11 MB) > 126 MB L2; no flush needed",
-                   "parallelism": f"env-sharded x{world}, no data-path collective"},
-        "roofline": {"bound": "tensor", "achieved": dom_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": dom_tf / peaks["bf16_tflops_sustained"],
-                     # dram__bytes_read.sum + dram__bytes_write.sum per launch of fused_mlp2_kernel at this shape, from the
-                     # ncu --set full capture profiles/r01_fused_blocks_ncu_full_v4.md (algorithmic: 100.7 MB in + 100.7 MB out;
-                     # part of the write-back is still in L2 when the kernel ends)
-                     "traffic": 145.0e6,
-                     "kernel": "vitmarl::fused_mlp2_kernel (LN2+FC1+GELU+FC2+residual, CTA-pair tcgen05), 12 launches per step",
-                     "flops_per_launch": mlp_flops, "avg_launch_us": mlp_us, "share_of_step": cat_ms[1] / steps_logged / (t_dev / K * 1e3),
-                     "second_kernel": {"kernel": "vitmarl::fused_attn2_kernel (LN1+QKV+softmax+PV+proj+residual)", "flops_per_launch": attn_flops,
-                                       "avg_launch_us": attn_us, "achieved": attn_flops / max(attn_us * 1e-6, 1e-12) / 1e12,
-                                       "frac": attn_flops / max(attn_us * 1e-6, 1e-12) / 1e12 / peaks["bf16_tflops_sustained"]},
-                     "all_tcgen05_launches": {"achieved": all_tf, "frac": all_tf / peaks["bf16_tflops_sustained"], "launches_timed": gemm_launches,
-                                              "flops_per_step": gemm_flops / max(steps_logged, 1),
-                                              "share_of_step": (gemm_ms_total / max(steps_logged, 1)) / (t_dev / K * 1e3)},
+        "config": workload_config(world),
+        "roofline": {"bound": "tensor", "achieved": dom["achieved"], "peak": peak, "unit": "TFLOP/s", "frac": dom["achieved"] / peak,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "kernel": dom["kernel"] + f", {int(round(cat_n[classes[dom_name]['idx']] / steps_logged))} launches per step: the LARGEST share of the step",
+                     "flops_per_launch": dom["flops_per_launch"], "avg_launch_us": dom["avg_launch_us"], "share_of_step": dom["share_of_step"],
+                     "frac_of_burst": dom["frac_of_burst"], "frac_of_sustained": dom["frac_of_sustained"],
+                     "peak_source": peaks["source"] + (", sustained figure (timed region >= 1 s)" if use_sustained else
+                                                       f", burst figure (timed region {region_s * 1e3:.0f} ms at un-capped clocks)"),
+                     "kernels": per_kernel,
+                     "whole_step": {"flops_per_step": step_flops, "achieved": step_flops / (step_ms * 1e-3) / 1e12,
+                                    "frac_of_burst": step_flops / (step_ms * 1e-3) / 1e12 / peaks["bf16_tflops"],
+                                    "frac_of_sustained": step_flops / (step_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]},
+                     "all_tcgen05_launches": {"achieved": all_tf, "frac_of_burst": all_tf / peaks["bf16_tflops"]},
+                     "lob_kernel": {"us_per_launch": lob_ms * 1e3, "algorithmic_bytes": E * (12800 + 48 * M + 240 + 64 * 64 * 2 * 2),
+                                    "achieved_GBps": E * (12800 + 48 * M + 240 + 64 * 64 * 2 * 2) / (lob_ms * 1e-3) / 1e9,
+                                    "frac_of_hbm": E * (12800 + 48 * M + 240 + 64 * 64 * 2 * 2) / (lob_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
                      "per_step_ms_by_kernel_class": breakdown,
-                     "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)"},
+                     "instrumented_pass_ms_per_step": t_instr / K * 1e3,
+                     "note": "breakdown from a separate instrumented pass (events around every launch); value / e2e are un-instrumented"},
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": eng.h2d_bytes_per_step * world, "d2h_bytes_per_step": eng.d2h_bytes_per_step * world,
-                "ms_per_step": t_e2e / K * 1e3},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": E * M * 8 * 4 * world,
+                "d2h_bytes_per_step": (E * vcfg.dim * 4 + E * 10 * 6 * 4) * world, "ms_per_step": t_e2e / K * 1e3},
         "gpu_launches": rollout.kernels_per_step(vcfg) * K,
         "clocks": clocks,
         "checksum": float(feats_dev.double().abs().sum().item()),
+        "extra": extra,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -297,6 +547,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra block (LOB sweep point, ViT fwd+bwd, collectives)")
+    ap.add_argument("--no-loop", action="store_true", help="N>1: skip the configs[4] rollout+update iteration (~30 s)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

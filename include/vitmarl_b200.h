@@ -21,6 +21,8 @@
  * Conventions: every pointer is caller-owned DEVICE memory unless the function name ends
  * in _host; no allocation, no synchronisation, work is only enqueued on `stream`
  * (a cudaStream_t passed as void*).  Returns 0 or a negative VITMARL_E* code; never aborts.
+ * Threading: no process-global mutable state -- tuning / debug / measurement switches are per-call
+ * (VitmarlVitOptions, `flags` arguments, caller-owned timing handles); the last-error text is thread-local.
  * All book / message / trade arrays are int32, row-major, layouts of
  * gymnax_exchange/jaxob/jaxob_constants.py:36-52,76-83.
  */
@@ -40,7 +42,7 @@ extern "C" {
 #define VITMARL_ECUDA (-3)        /* launch failure (cudaGetLastError)                      */
 #define VITMARL_ENODEVICE (-4)    /* no sm_100 device                                       */
 
-#define VITMARL_ABI_VERSION 1
+#define VITMARL_ABI_VERSION 2
 
 int vitmarl_abi_version(void);
 /* Human-readable text for the last CUDA error seen by this thread (static storage). */
@@ -116,6 +118,29 @@ int vitmarl_env_step(void* stream, int E, int N, int T, int M,
                      void* image, int img_dtype, int H, int W,
                      int cancel_mode, int32_t init_id);
 
+/* vitmarl_env_step with named arguments plus what the callers either side of it need:
+ *   last_price_stride   element stride of last_ask_price / last_bid_price: 1 = dense [E]; 2*M = the caller points at
+ *                       best_asks[0, M-1, 0] / best_bids[0, M-1, 0] of the PREVIOUS step (state.world_state.best_asks[-1, 0],
+ *                       marl_env.py:392-393).  Those buffers may be the SAME ones passed as best_asks / best_bids outputs: each
+ *                       environment's last price is read before its rows are rewritten.
+ *   n_stat_agents (0..4), stat_agent_ids, trade_stats [E, n_stat_agents, 8]
+ *                       the integer trade reductions of the reward functions for these trader ids, computed from the step's
+ *                       trade log while it is still on chip; row layout and arithmetic of vitmarl_agent_trade_stats
+ *                       (get_agent_trades JaxOrderBookArrays.py:824-831; vision_env.py:2076-2078,2156-2163,2191; mm_env.py:1906-1936).
+ *   trades_out          may be NULL when n_stat_agents > 0: the [T,8] log is then never written to HBM (-3.2 KB per env-step). */
+typedef struct VitmarlEnvStepArgs {
+  int E, N, T, M;
+  const int32_t* asks_in; const int32_t* bids_in; const int32_t* msgs;
+  const int32_t* last_ask_price; const int32_t* last_bid_price; int last_price_stride;
+  int32_t* asks_out; int32_t* bids_out; int32_t* trades_out;
+  int32_t* best_asks; int32_t* best_bids; float* mid_price;
+  int n_levels; int tick_size; int32_t* raw; int32_t* l2; float* norm;
+  void* image; int img_dtype; int H; int W;
+  int cancel_mode; int32_t init_id;
+  int n_stat_agents; int32_t stat_agent_ids[4]; int32_t* trade_stats;
+} VitmarlEnvStepArgs;
+int vitmarl_env_step2(void* stream, const VitmarlEnvStepArgs* args);
+
 /* ---- callers either side of the order-book step --------------------- */
 
 /* Replaces job.getCancelMsgs under vmap (JaxOrderBookArrays.py:756-782): for each env the first `size` rows
@@ -130,11 +155,13 @@ int vitmarl_get_cancel_msgs(void* stream, int E, int N, int size, const int32_t*
  * best_asks / best_bids [E,M,2] are tiled from the window's initial best ask / bid [n_windows,2] (marl_env.py:186-189) and
  * mid_price = float32((best_bid + best_ask) / 2) (:190).  Environments that are not done are untouched (the reference builds a
  * full reset state for every env and selects).  window_index is the caller's jax.random.randint draw (base_env.py:219-222);
- * init_trades [n_windows,T,8] may be NULL (= all -1).  All buffers int32 device memory, 16-byte aligned trades. */
+ * init_trades [n_windows,T,8] may be NULL (= all -1).  All buffers int32 device memory, 16-byte aligned trades.
+ * A done environment whose window_index is outside [0, n_windows) is left untouched and flagged: if `bad_window` (int32 [1],
+ * device, nullable) is given it receives 1 (JAX would clamp the gather; silently reading out of bounds is not an option here). */
 int vitmarl_auto_reset(void* stream, int E, int N, int T, int M, int n_windows, const int32_t* done, const int32_t* window_index,
                        const int32_t* init_asks, const int32_t* init_bids, const int32_t* init_trades,
                        const int32_t* init_best_asks, const int32_t* init_best_bids, int32_t* asks, int32_t* bids,
-                       int32_t* trades, int32_t* best_asks, int32_t* best_bids, float* mid_price);
+                       int32_t* trades, int32_t* best_asks, int32_t* best_bids, float* mid_price, int32_t* bad_window);
 
 /* Replaces job.get_agent_trades under vmap (JaxOrderBookArrays.py:824-831): rows of trades [E,T,8] that are executed
  * (price >= 0) and involve agent_id as passive or aggressive trader are kept, all others zeroed. */
@@ -180,18 +207,17 @@ int vitmarl_build_step_msgs(void* stream, int E, int n_total, int n_data, int Mc
  *   C[M,N] = epi( A[M,K] . B[N,K]^T ),  A/B bf16, fp32 accumulate.
  * Operand X is K-major when element (r,k) is X[r*ldx + k] (activations [tokens,features],
  * flax Dense kernels stored [out,in]) and MN-major when it is X[k*ldx + r].
- * Limits: N % 64 == 0, K % 8 == 0, lda/ldb % 8 == 0, 16-byte aligned bases. */
+ * Limits: N % 64 == 0, K % 8 == 0, lda/ldb % 8 == 0, 16-byte aligned bases.
+ * flags: VITMARL_GEMM_NO_2CTA = use the 1-CTA kernels only (default: the CTA-pair tcgen05 cta_group::2 kernels where they apply). */
+#define VITMARL_GEMM_NO_2CTA 1
 int vitmarl_gemm_bf16(void* stream, int M, int N, int K,
                       const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major,
                       void* C, int ldc, int epi, const float* bias, const void* residual, int ldr,
-                      const float* pos, int pos_period, float out_scale);
+                      const float* pos, int pos_period, float out_scale, int flags);
 
-/* Select the 2-CTA (tcgen05 cta_group::2, 256-row tiles per CTA pair) GEMM where it applies (1, default) or the
- * 1-CTA kernel only (0). */
-int vitmarl_gemm_set_2cta(int enable);
 /* Test hook for the weight-gradient launch of the backward pass: C[M,N] (fp32) += A^T . B, colsum[M] += column sums of A
- * (A [K,M], B [K,N] bf16 row-major; colsum may be NULL). */
-int vitmarl_debug_gemm_dw(void* stream, int M, int N, int K, const void* A, const void* B, float* C, float* colsum);
+ * (A [K,M], B [K,N] bf16 row-major; colsum may be NULL); flags as vitmarl_gemm_bf16. */
+int vitmarl_debug_gemm_dw(void* stream, int M, int N, int K, const void* A, const void* B, float* C, float* colsum, int flags);
 
 /* Shape of the encoder (docs/VIT_SPEC.md): pre-LN ViT, learned position embedding, no class
  * token, final LayerNorm then mean pool -> [B, dim].  Requires (H/P)*(W/P) == 64 tokens and
@@ -222,8 +248,9 @@ long long vitmarl_vit_param_elems(const VitmarlVitShape* s, int index, int* is_b
 /* Bytes of caller-owned activation workspace for fwd (save_for_bwd = 0) or fwd+bwd (1). */
 size_t vitmarl_vit_workspace_bytes(const VitmarlVitShape* s, int save_for_bwd);
 
-/* Flag for save_for_bwd (inference modes 0 / 2 only): x is already the patch matrix [B*T, P*P*C] bf16 (e.g. rendered by
- * vitmarl_env_step with VITMARL_IMG_BF16_PATCHES_OF(P)), so no patchify pass runs. */
+/* Flag for save_for_bwd: x is already the patch matrix [B*T, P*P*C] bf16 (e.g. rendered by vitmarl_env_step with
+ * VITMARL_IMG_BF16_PATCHES_OF(P)), so no patchify pass runs.  With save_for_bwd = 1 the matrix is copied into the workspace
+ * (the backward pass reads it for the patch-embedding weight gradient); vitmarl_vit_bwd's dx stays d(image) [B,H,W,C]. */
 #define VITMARL_VIT_INPUT_PATCHES 4
 
 /* y[B,D] (fp32) = ViT(x[B,H,W,C] bf16).  Replaces `module.apply({'params': p}, x)`.
@@ -239,24 +266,46 @@ int vitmarl_vit_bwd(void* stream, const VitmarlVitShape* s, const void* const* p
                     void* workspace, size_t workspace_bytes, const float* dy,
                     void* const* dparams, void* dx);
 
-/* Inference forward: 1 (default) the fused per-block kernels (CTA-pair MLP block, warp-specialised attention block on
- * folded parameters), 0 the unfused kernel sequence, 2 the first-generation 1-CTA fused kernels. */
-int vitmarl_vit_set_fused(int mode);
+/* Per-call options of vitmarl_vit_fwd_ex / vitmarl_vit_bwd_ex.  The library keeps NO process-global mutable state: every
+ * switch travels with the call, so XLA may invoke the handlers concurrently from several threads / devices.  Zero-initialise,
+ * then set fields; integer switches use -1 (or 0 pointers) for "default".  NULL options = all defaults. */
+typedef struct VitmarlVitOptions {
+  int fused;                  /* -1 default (1): fused per-block tcgen05 kernels where the shape allows; 0: the unfused kernel sequence */
+  int gemm_2cta;              /* -1 default (1): CTA-pair GEMMs; 0: 1-CTA kernels only                                      */
+  int pdl;                    /* -1 default (1): programmatic dependent launch of the fused block kernels                   */
+  int attn_flags;             /* -1 default: tuning switches of the fused attention block (FusedAttn2Params::flags)         */
+  void* timing;               /* handle from vitmarl_timing_create: every launch of this call is bracketed by CUDA events   */
+  long long* debug_timeline;  /* device buffer (>= 512 int64) receiving clock64() phase stamps of the fused block kernels    */
+  /* backward only */
+  void* grads_flat;           /* if the gradient table is carved out of ONE buffer: its base ...                            */
+  size_t grads_flat_bytes;    /* ... and size, zeroed with a single memset instead of one per tensor                        */
+  int accumulate;             /* 1: do NOT zero the gradient table first -- this call's gradients are added to its contents
+                                 (micro-batches of one minibatch accumulate in place; every dW / bias / LayerNorm gradient is
+                                 produced by fp32 reductions anyway).  0 / -1: zero first (default)                         */
+  void* const* bucket_events; /* cudaEvent_t[vitmarl_vit_num_buckets()] or NULL.  Event b is recorded on `stream` as soon as
+                                 gradient bucket b is final: 0 = encoder_norm, 1 + (depth-1-l) = block l (its 12 tensors),
+                                 depth+1 = patch_embed + pos_embed.  The caller starts each bucket's all-reduce on a side stream
+                                 behind its event, overlapping the rest of the backward pass (the pmean of
+                                 jaxrl/MARL/ippo_rnn_JAXMARL_pmap.py:564-565).                                              */
+} VitmarlVitOptions;
 
-/* Debug hook: device buffer (>= 512 int64) that receives clock64() phase stamps of the fused block kernels
- * (CTA 0, second tile; [0,256) MLP block, [256,512) attention block); NULL switches it off. */
-int vitmarl_debug_fused_mlp_timeline(long long* device_buf);
-/* Debug hook: tuning switches of the fused attention block (0 = defaults; see FusedAttn2Params::flags). */
-int vitmarl_debug_set_flags(int flags);
+int vitmarl_vit_fwd_ex(void* stream, const VitmarlVitShape* s, const void* const* params,
+                       const void* x, float* y, void* workspace, size_t workspace_bytes, int save_for_bwd,
+                       const VitmarlVitOptions* options);
+int vitmarl_vit_bwd_ex(void* stream, const VitmarlVitShape* s, const void* const* params,
+                       void* workspace, size_t workspace_bytes, const float* dy,
+                       void* const* dparams, void* dx, const VitmarlVitOptions* options);
+/* Number of gradient buckets (depth + 2) of vitmarl_vit_bwd_ex's bucket_events. */
+int vitmarl_vit_num_buckets(const VitmarlVitShape* s);
 
-/* Measurement hook: CUDA-event timing (on the launch stream) of every tensor-core GEMM launch
- * (plain GEMMs and fused block kernels) issued by vitmarl_vit_fwd / vitmarl_vit_bwd.  enable(1) resets the log;
- * read() synchronises on the last logged launch and returns total ms, launch count and algorithmic FLOPs. */
-int vitmarl_vit_gemm_timing_enable(int enable);
-int vitmarl_vit_gemm_timing_read(double* total_ms, long long* launches, double* flops);
-/* Per-category totals over the same log; arrays of 8: 0 gemm, 1 fused MLP block, 2 fused attention block,
- * 3 attention, 4 layernorm, 5 other (patchify, pool, bias column sums), 6 dW GEMMs, 7 dX GEMMs. */
-int vitmarl_vit_timing_read_categories(double* ms8, long long* n8);
+/* Measurement: a caller-owned log of CUDA-event timings (on the launch stream) of every kernel launch issued by the calls that
+ * carry the handle in VitmarlVitOptions::timing.  read() synchronises on the last logged launch and returns per-category
+ * totals -- arrays of 8: 0 gemm, 1 fused MLP block, 2 fused attention block, 3 attention, 4 layernorm, 5 other (patchify,
+ * pool, parameter folding), 6 dW GEMMs, 7 dX GEMMs -- and the algorithmic FLOPs of the tensor-core launches. */
+void* vitmarl_timing_create(void);
+void vitmarl_timing_destroy(void* timing);
+int vitmarl_timing_reset(void* timing);
+int vitmarl_timing_read(void* timing, double* ms8, long long* n8, double* flops);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ def main():
     stream = synth.MessageStream(E, 1234)
     msgs = [torch.from_numpy(stream.next(M)).cuda() for _ in range(8)]
     for flags in (4, 4 | 0x100, 4, 4 | 0x100):
-        lib.vitmarl_debug_set_flags(flags)
+        eng.encoder.options.pdl = 0 if (flags & 0x100) else 1      # per-call option
         eng.reset(a.clone(), b.clone())
         for i in range(5): eng.step(msgs[i % 8])
         torch.cuda.synchronize()

@@ -30,12 +30,14 @@ g = torch.Generator(device="cpu").manual_seed(rank)
 lens = torch.randint(0, cfg.img_w + 1, (B, cfg.img_h, 1, cfg.channels), generator=g)
 x = (torch.arange(cfg.img_w)[None, None, :, None] < lens).to(torch.bfloat16).cuda()
 dy = torch.randn(B, cfg.dim, generator=g).cuda()
-red = parallel.GradAllReducer([t.shape for t in packed], device="cuda")
+red = parallel.GradAllReducer([t.shape for t in packed], device="cuda", bucket_ranges=enc.bucket_param_ranges())
 
 def step():
     enc.apply_packed(packed, x, train=True)
-    enc.vjp_packed(packed, dy, grads=red.grads())
-    red.allreduce_mean()
+    enc.vjp_packed(packed, dy, grads=red.grads(), flat=red.flat, bucket_events=red.events)
+    red.allreduce_mean(async_op=True)      # per-block buckets behind the backward's events (overlaps the remaining blocks)
+    red.swap()                             # the next step's backward writes the other flat buffer
+    red.wait()
 
 def sync():
     if world > 1: dist.barrier()
@@ -43,16 +45,17 @@ def sync():
 
 for _ in range(a.warmup): step()
 sync()
-lib.vitmarl_vit_gemm_timing_enable(1)
+tm = _capi.Timing(); enc.options.timing = tm.handle
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(a.steps): step()
 e1.record(); sync()
 ms = e0.elapsed_time(e1) / a.steps
-gm, gn, gf = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
-lib.vitmarl_vit_gemm_timing_read(ctypes.byref(gm), ctypes.byref(gn), ctypes.byref(gf))
-cat_ms, cat_n = (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
-lib.vitmarl_vit_timing_read_categories(cat_ms, cat_n)
+cat_ms, cat_n, flops = tm.read()
+class _V:      # (kept field names of the old report)
+    pass
+gm, gf = _V(), _V()
+gm.value = sum(cat_ms[i] for i in (0, 1, 2, 6, 7)); gf.value = flops
 names = ["gemm_fwd", "fused_mlp", "fused_attn", "attention", "layernorm", "other", "gemm_dW", "gemm_dX"]
 breakdown = {nm: round(cat_ms[i] / a.steps, 3) for i, nm in enumerate(names) if cat_n[i]}
 if world > 1:

@@ -5,16 +5,16 @@ import ctypes
 import torch
 from vitmarl_b200 import vit, _capi
 lib = _capi.lib()
-if len(sys.argv) > 1: lib.vitmarl_debug_set_flags(int(sys.argv[1]))
 cfg = vit.ViTConfig(64, 64, 2, 8, 192, 1, 3, 768)
 enc = vit.ViTEncoder(cfg)
 packed = vit.pack_params(cfg, vit.init_params(cfg, 0, "cuda"))
 x = (torch.rand(4096, 64, 64, 2, device="cuda") < 0.3).to(torch.bfloat16)
 buf = torch.zeros(512, dtype=torch.int64, device="cuda")
 for _ in range(2): enc.apply_packed(packed, x)
-lib.vitmarl_debug_fused_mlp_timeline(buf.data_ptr())
+enc.options.debug_timeline = buf.data_ptr()
+if len(sys.argv) > 1: enc.options.attn_flags = int(sys.argv[1], 0) & 0xff
 enc.apply_packed(packed, x); torch.cuda.synchronize()
-lib.vitmarl_debug_fused_mlp_timeline(None)
+enc.options.debug_timeline = None
 t = buf.cpu().tolist()[256:]
 t0 = min(v for v in t if v)
 r = lambda i: t[i] - t0 if t[i] else None
@@ -24,11 +24,9 @@ for h in range(3):
 print(" epi(h1): ld+pack done", r(70), "waits done", r(71), "sts issued", r(72), "fence done", r(73))
 print(" LN(next): start", r(51), "xfull", r(52), "stats+bar", r(53), "xnfree", r(54))
 print(" LN(next) done", r(50), "| proj start", r(130), "issued", r(131), "| CV: projfull", r(60), "tile end", r(61))
-lib.vitmarl_vit_gemm_timing_enable(1)
+tm = _capi.Timing(); enc.options.timing = tm.handle
 for _ in range(5): enc.apply_packed(packed, x)
 torch.cuda.synchronize()
-ms, n = (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
-lib.vitmarl_vit_timing_read_categories(ms, n)
-lib.vitmarl_vit_gemm_timing_enable(0)
+ms, n, _ = tm.read(); enc.options.timing = None
 names = ["gemm", "fused_mlp", "fused_attn", "attention", "layernorm", "other", "dw", "dx"]
 print({nm: round(ms[i] / max(n[i], 1) * 1e3, 1) for i, nm in enumerate(names) if n[i]}, "us per launch")

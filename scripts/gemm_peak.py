@@ -6,7 +6,7 @@ lib = _capi.lib(); S = torch.cuda.current_stream().cuda_stream
 for (M, N, K) in ((8192, 3840, 4096), (8192, 4096, 4096), (8192, 4160, 4096)):
     A = torch.randn(M, K, device="cuda").bfloat16(); B = torch.randn(N, K, device="cuda").bfloat16()
     C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    f = lambda: lib.vitmarl_gemm_bf16(S, M, N, K, A.data_ptr(), K, 0, B.data_ptr(), K, 0, C.data_ptr(), N, 0, None, None, N, None, 0, 1.0)
+    f = lambda: lib.vitmarl_gemm_bf16(S, M, N, K, A.data_ptr(), K, 0, B.data_ptr(), K, 0, C.data_ptr(), N, 0, None, None, N, None, 0, 1.0, 0)
     for i in range(3): f()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

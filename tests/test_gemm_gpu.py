@@ -13,7 +13,7 @@ def _S():
     return torch.cuda.current_stream().cuda_stream
 
 
-def _gemm(M, N, K, *, epi=0, bias=False, res=False, a_mn=False, b_mn=False, seed=0):
+def _gemm(M, N, K, *, epi=0, bias=False, res=False, a_mn=False, b_mn=False, seed=0, flags=0):
     lib = _capi.lib()
     g = torch.Generator(device="cuda").manual_seed(seed)
     A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
@@ -36,7 +36,7 @@ def _gemm(M, N, K, *, epi=0, bias=False, res=False, a_mn=False, b_mn=False, seed
         C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     rc = lib.vitmarl_gemm_bf16(_S(), M, N, K, Am.data_ptr(), Am.stride(0), int(a_mn), Bm.data_ptr(), Bm.stride(0), int(b_mn),
                                C.data_ptr(), N, epi, bias_t.data_ptr() if bias else None, res_t.data_ptr() if res else None, N,
-                               None, 0, 0.5 if epi == 3 else 1.0)
+                               None, 0, 0.5 if epi == 3 else 1.0, flags)
     torch.cuda.synchronize()
     _capi.check(rc)
     return (C.float() - ref).abs().max().item() / ref.abs().max().item()
@@ -44,16 +44,12 @@ def _gemm(M, N, K, *, epi=0, bias=False, res=False, a_mn=False, b_mn=False, seed
 
 @pytest.mark.parametrize("two_cta", [1, 0])
 def test_forward_and_dx_shapes(two_cta):
-    lib = _capi.lib()
-    lib.vitmarl_gemm_set_2cta(two_cta)
-    try:
-        assert _gemm(1000, 576, 192, bias=True) < 1e-2                       # ragged M
-        assert _gemm(2048, 768, 192, epi=1, bias=True) < 1e-2                # bias + GELU
-        assert _gemm(2048, 192, 768, bias=True, res=True) < 1e-2             # residual epilogue
-        assert _gemm(2048, 384, 1536, b_mn=True, res=True) < 1e-2            # dX: MN-major B, 1.5-block halves on the pair kernel
-        assert _gemm(1300, 384, 3072, b_mn=True, bias=True) < 1e-2           # large K: per-thread epilogue, ragged M
-    finally:
-        lib.vitmarl_gemm_set_2cta(1)
+    f = 0 if two_cta else _capi.GEMM_NO_2CTA       # per-call flag (the library has no global switch)
+    assert _gemm(1000, 576, 192, bias=True, flags=f) < 1e-2                       # ragged M
+    assert _gemm(2048, 768, 192, epi=1, bias=True, flags=f) < 1e-2                # bias + GELU
+    assert _gemm(2048, 192, 768, bias=True, res=True, flags=f) < 1e-2             # residual epilogue
+    assert _gemm(2048, 384, 1536, b_mn=True, res=True, flags=f) < 1e-2            # dX: MN-major B, 1.5-block halves on the pair kernel
+    assert _gemm(1300, 384, 3072, b_mn=True, bias=True, flags=f) < 1e-2           # large K: per-thread epilogue, ragged M
 
 
 @pytest.mark.parametrize("M,N,K", [(192, 192, 4096), (768, 192, 8192), (1536, 384, 16384), (1152, 384, 10000),
@@ -72,7 +68,7 @@ def test_weight_gradient_with_fused_bias_gradient(M, N, K):
     B = (torch.randn(K, N, device="cuda", generator=g) * 0.5).bfloat16()
     C = torch.zeros(M, N, device="cuda")
     cs = torch.full((M,), 2.0, device="cuda")
-    _capi.check(lib.vitmarl_debug_gemm_dw(_S(), M, N, K, A.data_ptr(), B.data_ptr(), C.data_ptr(), cs.data_ptr()))
+    _capi.check(lib.vitmarl_debug_gemm_dw(_S(), M, N, K, A.data_ptr(), B.data_ptr(), C.data_ptr(), cs.data_ptr(), 0))
     torch.cuda.synchronize()
     ref = A.float().t() @ B.float()
     assert (C - ref).abs().max().item() / ref.abs().max().item() < 1e-4

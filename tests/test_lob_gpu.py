@@ -9,7 +9,7 @@ from tests.util import fuzz_case, lobster_to_msg, synthetic_case
 pytestmark = pytest.mark.gpu
 
 from vitmarl_b200 import env as venv            # noqa: E402
-from vitmarl_b200 import jaxob, vision           # noqa: E402
+from vitmarl_b200 import _capi, jaxob, vision    # noqa: E402
 from vitmarl_b200.config import World_EnvironmentConfig  # noqa: E402
 
 CFG = World_EnvironmentConfig()
@@ -160,7 +160,8 @@ def _oracle_env_step(C, asks, bids, msgs, last_a, last_b, n_levels, H, W):
     return a, b, t, fa, fb, mid, raw, norm, img
 
 
-@pytest.mark.parametrize("E,M,steps", [(16, 9, 6), (257, 13, 4), (64, 113, 2)])
+# (4096, 13, 8) is BASELINE configs[1] at its full size: 8 chained steps, every output leaf compared byte for byte with the C oracle
+@pytest.mark.parametrize("E,M,steps", [(16, 9, 6), (257, 13, 4), (64, 113, 2), (4096, 13, 8)])
 def test_fused_env_step_equals_composition(c_oracle, E, M, steps):
     asks, bids, blocks = synthetic_case(E, M, steps=steps)
     state = venv.reset(CFG, dev(asks), dev(bids), M)
@@ -251,3 +252,44 @@ def test_full_size_properties():
     # volume conservation: resting volume change = added limit qty - cancelled - 2 * traded
     traded = t2[..., 1].abs().where(t2[..., 0] != -1, torch.zeros_like(t2[..., 1])).sum(1).long()
     assert bool((traded > 0).any())
+
+
+def test_fused_trade_stats_and_on_chip_trade_log(c_oracle):
+    """the reward functions' trade reductions are computed inside the step kernel from the trade log while it
+    is on chip; with keep_trades=False the [T,8] log is never written.  Everything else must stay byte-identical, over chained
+    steps that rewrite the best-price tracks in place (the previous step's last prices are read by stride from them)."""
+    from oracle import lob_oracle as O
+    E, M, steps = 193, 13, 5
+    asks, bids, blocks = synthetic_case(E, M, steps=steps, seed=77)
+    # synthetic streams carry trader_id = order_id; make some resting / aggressing orders belong to the two agents
+    ids = [-100, -37]
+    rng = np.random.default_rng(3)
+    for blk in blocks:
+        who = rng.random((E, M))
+        blk[..., 5] = np.where(who < 0.25, ids[0], np.where(who < 0.5, ids[1], blk[..., 5]))
+    bufs = venv.StepBuffers()
+    st_a = venv.reset(CFG, dev(asks), dev(bids), M)
+    st_b = venv.reset(CFG, dev(asks), dev(bids), M)
+    sentinel = st_b.trades.clone()
+    ba0, bb0 = c_oracle.best_bid_ask(asks, bids)
+    last_a, last_b = ba0[:, 0].copy(), bb0[:, 0].copy()
+    any_trade = False
+    for msgs in blocks:
+        w = _oracle_env_step(c_oracle, asks, bids, msgs, last_a, last_b, 10, 0, 0)
+        st_a, out_a = venv.step(CFG, st_a, dev(msgs), want_raw=True, stat_agent_ids=ids, buffers=bufs)
+        st_b, out_b = venv.step(CFG, st_b, dev(msgs), want_raw=True, stat_agent_ids=ids, keep_trades=False)
+        torch.cuda.synchronize()
+        for st, out in ((st_a, out_a), (st_b, out_b)):
+            got = (st.ask_raw_orders, st.bid_raw_orders, st.best_asks, st.best_bids, st.mid_price, out.vision_raw, out.vision_obs)
+            want = (w[0], w[1], w[3], w[4], w[5], w[6], w[7])
+            for name, x, y in zip("asks bids best_asks best_bids mid raw norm".split(), want, got):
+                assert host(y).tobytes() == np.ascontiguousarray(x).tobytes(), name
+        assert host(st_a.trades).tobytes() == w[2].tobytes()
+        assert torch.equal(st_b.trades, sentinel)                       # never written
+        want_stats = np.stack([np.stack([O.agent_trade_stats(w[2][e], a, CFG.tick_size) for a in ids]) for e in range(E)])
+        assert np.array_equal(host(out_a.trade_stats), want_stats) and np.array_equal(host(out_b.trade_stats), want_stats)
+        any_trade = any_trade or bool((want_stats[..., 1] > 0).any())
+        asks, bids, last_a, last_b = w[0], w[1], w[3][:, -1, 0].copy(), w[4][:, -1, 0].copy()
+    assert any_trade
+    with pytest.raises(_capi.VitmarlError):
+        venv.step(CFG, st_b, dev(blocks[0]), keep_trades=False)          # the log may stay on chip only when its reductions are asked for

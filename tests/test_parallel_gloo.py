@@ -25,11 +25,18 @@ def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     shapes = [torch.Size((3, 5)), torch.Size((7,)), torch.Size((2, 2, 2))]
-    red = parallel.GradAllReducer(shapes, device="cpu")
-    for i, g in enumerate(red.grads()):
-        g.copy_(torch.full(g.shape, float((rank + 1) * (i + 1))))
-    red.allreduce_mean()
-    ok = all(torch.allclose(g, torch.full(g.shape, (1 + 2) / 2 * (i + 1))) for i, g in enumerate(red.grads()))
+    # two buckets in backward-completion order (last tensor first), double-buffered flat gradient
+    red = parallel.GradAllReducer(shapes, device="cpu", bucket_ranges=[(2, 3), (0, 2)])
+    ok = True
+    for rnd in range(3):
+        for i, g in enumerate(red.grads()):
+            g.copy_(torch.full(g.shape, float((rank + 1) * (i + 1) + rnd)))
+        red.allreduce_mean(async_op=True)
+        reduced = red.wait()
+        ok = ok and all(torch.allclose(g, torch.full(g.shape, (1 + 2) / 2 * (i + 1) + rnd)) for i, g in enumerate(reduced))
+        prev = red.flat
+        red.swap()                                   # the next "backward" writes the other buffer
+        ok = ok and red.flat.data_ptr() != prev.data_ptr()
     # sharded rollout bookkeeping: every rank owns a disjoint env range, union is everything
     lo, hi = parallel.shard_envs(13, world, rank)
     owned = torch.zeros(13)

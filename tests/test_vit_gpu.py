@@ -43,7 +43,9 @@ def _rel(a, b):
                                    # > 148 attention tiles / > 74 MLP pair tiles: every CTA of the persistent fused kernels loops
                                    # over 2-3 tiles (cross-tile prefetch, barrier phase wrap-around), last pair tile half empty
                                    (vit.ViTConfig(64, 64, 2, 8, 192, 2, 3, 768), 701),
-                                   (vit.ViTConfig(128, 128, 2, 16, 384, 2, 6, 1536), 5)])
+                                   (vit.ViTConfig(128, 128, 2, 16, 384, 2, 6, 1536), 5),
+                                   # BASELINE configs[3] architecture at its full depth, >= 148 row tiles of 128 tokens
+                                   (vit.VIT_SMALL_16, 296)])
 def test_forward_matches_fp32_oracle(cfg, B):
     params = _perturbed_params(cfg, 0)
     x = _images(B, cfg)
@@ -56,21 +58,22 @@ def test_forward_matches_fp32_oracle(cfg, B):
     assert _rel(y, ref) <= ACT_TOL, _rel(y, ref)
     # the inference path runs the fused block kernels, the training path the unfused sequence: same maths
     assert _rel(y, y_train) <= 1e-2, _rel(y, y_train)
-    lib = _capi.lib()
-    lib.vitmarl_vit_set_fused(0)
+    enc.options.fused = 0                    # per-call option (no process-global switch): the unfused kernel sequence
     y_unfused = enc.apply({"params": params}, x)
-    lib.vitmarl_vit_set_fused(2)             # legacy 1-CTA fused block kernels
-    y_legacy = enc.apply({"params": params}, x)
-    lib.vitmarl_vit_set_fused(1)
-    assert _rel(y_legacy, ref) <= ACT_TOL, _rel(y_legacy, ref)
-    assert torch.equal(y_unfused, y_train)    # saving activations must not change the result
+    enc.options.fused = -1
+    assert _rel(y_unfused, ref) <= ACT_TOL, _rel(y_unfused, ref)
     assert torch.equal(y, enc.apply({"params": params}, x))   # forward is bitwise deterministic
 
 
 @pytest.mark.parametrize("cfg,B", [(vit.ViTConfig(64, 64, 2, 8, 192, 0, 3, 768), 6),
                                    (vit.ViTConfig(64, 64, 2, 8, 192, 1, 3, 768), 8),
                                    (vit.VIT_PARITY, 16),
-                                   (vit.ViTConfig(128, 128, 2, 16, 384, 2, 6, 1536), 4)])
+                                   (vit.ViTConfig(128, 128, 2, 16, 384, 2, 6, 1536), 4),
+                                   # full depth at a batch of >= 296 images (18 944 tokens = 148 row tiles): every persistent CTA
+                                   # works, the weight-gradient kernel takes its split-K / operand-swap paths inside the encoder
+                                   (vit.VIT_TINY_8, 296),
+                                   (vit.VIT_TINY_8, 333),       # ragged: last pair tile half empty
+                                   (vit.VIT_SMALL_16, 296)])
 def test_backward_matches_autograd(cfg, B):
     params = _perturbed_params(cfg, 3)
     x = _images(B, cfg, 1)
@@ -98,6 +101,33 @@ def test_backward_matches_autograd(cfg, B):
     assert not bad, bad
     g, r = dx.float().reshape(-1), ref_dx.reshape(-1)
     assert torch.dot(g, r) / (g.norm() * r.norm()) >= GRAD_COS
+
+
+@pytest.mark.parametrize("cfg,B", [(vit.VIT_PARITY, 64), (vit.VIT_TINY_8, 296)])
+def test_scalar_loss_matches_fp32_oracle(cfg, B):
+    """'PPO loss abs-diff <= 1e-3'.  The reference's loss consumes the encoder through a linear read-out
+    (ippo_rnn_JAXMARL.py:423-475: value head + 0.5 * mean((value - target)^2), VF_COEF-style scalar); the same scalar is
+    evaluated on our encoding and on the fp32 oracle's, and its gradient w.r.t. the encoding is what vjp receives."""
+    params = _perturbed_params(cfg, 11)
+    x = _images(B, cfg, 4)
+    g = torch.Generator().manual_seed(5)
+    w = (torch.randn(cfg.dim, generator=g) / cfg.dim ** 0.5).cuda()
+    target = torch.randn(B, generator=g).cuda()
+    enc = vit.ViTEncoder(cfg)
+    y = enc.apply({"params": params}, x, train=True)
+    ref = VO.vit_forward(cfg, params, x)
+    loss = 0.5 * ((y @ w - target) ** 2).mean()
+    loss_ref = 0.5 * ((ref @ w - target) ** 2).mean()
+    assert abs(float(loss) - float(loss_ref)) <= 1e-3, (float(loss), float(loss_ref))
+    # d loss / d encoding -> vjp -> parameter gradients of the scalar loss
+    dy = ((y @ w - target) / B)[:, None] * w[None, :]
+    grads = enc.vjp({"params": params}, dy)
+    _, gref, _ = VO.vit_value_and_grad(cfg, params, x, ((ref @ w - target) / B)[:, None] * w[None, :])
+    for (name, a), (_, b) in zip(VO.tree_leaves(grads), VO.tree_leaves(gref)):
+        if name.endswith("key/bias"):
+            continue
+        a, b = a.float().reshape(-1), b.float().reshape(-1)
+        assert torch.dot(a, b) / (a.norm() * b.norm() + 1e-30) >= GRAD_COS, name
 
 
 def test_gemm_operand_layouts_and_epilogues():
@@ -133,7 +163,7 @@ def test_gemm_operand_layouts_and_epilogues():
             C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
         rc = lib.vitmarl_gemm_bf16(S, M, N, K, Am.data_ptr(), Am.stride(0), a_mn, Bm.data_ptr(), Bm.stride(0), b_mn,
                                    C.data_ptr(), N, epi, bias_t.data_ptr() if bias else None, res_t.data_ptr() if res else None, N,
-                                   pos_t.data_ptr() if pos else None, pos, 0.5 if epi == 3 else 1.0)
+                                   pos_t.data_ptr() if pos else None, pos, 0.5 if epi == 3 else 1.0, 0)
         torch.cuda.synchronize()
         assert rc == 0
         assert _rel(C, ref) < 1e-2, (M, N, K, epi, a_mn, b_mn, _rel(C, ref))
@@ -146,21 +176,45 @@ def test_rejects_unsupported_shapes():
 
 
 def test_folded_parameter_reuse_in_the_rollout_loop():
-    """save_for_bwd = 2: the fold launches are skipped and the folded parameters of the previous call are reused."""
+    """save_for_bwd = 2: the fold launches are skipped and the folded parameters of the previous call are reused -- keyed on
+    the CALLER's generation counter (params_version), never on Python object identity."""
     cfg = vit.VIT_PARITY
     params = _perturbed_params(cfg, 5)
     x = _images(40, cfg, 2)
     enc = vit.ViTEncoder(cfg)
     packed = vit.pack_params(cfg, params)
-    y0 = enc.apply_packed(packed, x).clone()
-    y1 = enc.apply_packed(packed, x, params_unchanged=True).clone()
+    y0 = enc.apply_packed(packed, x, params_version=0).clone()
+    y1 = enc.apply_packed(packed, x, params_version=0).clone()          # reuses the folded parameters
     assert torch.equal(y0, y1)
-    # an optimiser step changes the table's contents: the caller must NOT claim "unchanged", and the result must move
+    # an optimiser step changes the table's contents IN PLACE (same Python objects): a bumped version folds again ...
     packed[3 + 8].mul_(1.5)                              # block 0 fc1.kernel
-    y2 = enc.apply_packed(packed, x).clone()
+    y2 = enc.apply_packed(packed, x, params_version=1).clone()
     assert not torch.equal(y0, y2)
-    y3 = enc.apply_packed(packed, x, params_unchanged=True)
-    assert torch.equal(y2, y3)
+    assert torch.equal(y2, enc.apply_packed(packed, x, params_version=1))
+    # ... and so does a call without a version (the default never trusts the workspace)
+    assert torch.equal(y2, enc.apply_packed(packed, x))
     # a different batch size lays the workspace out differently: the claim is ignored and the parameters are folded again
-    y4 = enc.apply_packed(packed, x[:8], params_unchanged=True)
+    y4 = enc.apply_packed(packed, x[:8], params_version=1)
     assert torch.equal(y4, y2[:8])
+
+
+def test_apply_sees_in_place_parameter_updates():
+    """an optimiser updates the fp32 master tensors in place (same dict object); apply() / vjp() must not serve
+    stale packed weights."""
+    cfg = vit.VIT_PARITY
+    params = _perturbed_params(cfg, 7)
+    x = _images(8, cfg, 3)
+    enc = vit.ViTEncoder(cfg)
+    v = {"params": params}
+    y0 = enc.apply(v, x).clone()
+    params["encoderblock_0"]["MlpBlock_0"]["Dense_0"]["kernel"].mul_(1.5)        # in place: `params` is the same object
+    y1 = enc.apply(v, x).clone()
+    assert not torch.equal(y0, y1)
+    assert _rel(y1, VO.vit_forward(cfg, params, x)) <= ACT_TOL
+    # training pass + vjp run on the updated table as well
+    enc.apply(v, x, train=True)
+    dy = torch.randn(8, cfg.dim, device="cuda")
+    g = enc.vjp(v, dy)
+    _, ref, _ = VO.vit_value_and_grad(cfg, params, x, dy)
+    a, b = g["encoderblock_0"]["MlpBlock_0"]["Dense_0"]["kernel"].reshape(-1), ref["encoderblock_0"]["MlpBlock_0"]["Dense_0"]["kernel"].reshape(-1)
+    assert torch.dot(a, b) / (a.norm() * b.norm()) >= GRAD_COS

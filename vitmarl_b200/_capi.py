@@ -32,6 +32,66 @@ class VitShape(ctypes.Structure):
                 ("ln_eps", ctypes.c_float)]
 
 
+class VitOptions(ctypes.Structure):
+    """VitmarlVitOptions (include/vitmarl_b200.h); ``VitOptions.defaults()`` = every switch at its default."""
+    _fields_ = [("fused", ctypes.c_int), ("gemm_2cta", ctypes.c_int), ("pdl", ctypes.c_int), ("attn_flags", ctypes.c_int),
+                ("timing", ctypes.c_void_p), ("debug_timeline", ctypes.c_void_p),
+                ("grads_flat", ctypes.c_void_p), ("grads_flat_bytes", ctypes.c_size_t), ("accumulate", ctypes.c_int),
+                ("bucket_events", ctypes.c_void_p)]
+
+    @classmethod
+    def defaults(cls, **kw):
+        o = cls(-1, -1, -1, -1, None, None, None, 0, -1, None)
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+
+
+class Timing:
+    """Caller-owned CUDA-event log (vitmarl_timing_*): pass ``handle`` in ``VitOptions.timing``."""
+    NAMES = ["gemm", "fused_mlp", "fused_attn_block", "attention", "layernorm", "other", "gemm_dW", "gemm_dX"]
+
+    def __init__(self):
+        self.handle = lib().vitmarl_timing_create()
+        if not self.handle:
+            raise VitmarlError(ECUDA, "vitmarl_timing_create failed")
+
+    def reset(self):
+        check(lib().vitmarl_timing_reset(self.handle))
+
+    def read(self):
+        ms, n, fl = (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)(), ctypes.c_double()
+        check(lib().vitmarl_timing_read(self.handle, ms, n, ctypes.byref(fl)))
+        return list(ms), list(n), fl.value
+
+    def close(self):
+        if self.handle:
+            lib().vitmarl_timing_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+GEMM_NO_2CTA = 1
+
+
+class EnvStepArgs(ctypes.Structure):
+    """VitmarlEnvStepArgs (include/vitmarl_b200.h)."""
+    _fields_ = [("E", ctypes.c_int), ("N", ctypes.c_int), ("T", ctypes.c_int), ("M", ctypes.c_int),
+                ("asks_in", ctypes.c_void_p), ("bids_in", ctypes.c_void_p), ("msgs", ctypes.c_void_p),
+                ("last_ask_price", ctypes.c_void_p), ("last_bid_price", ctypes.c_void_p), ("last_price_stride", ctypes.c_int),
+                ("asks_out", ctypes.c_void_p), ("bids_out", ctypes.c_void_p), ("trades_out", ctypes.c_void_p),
+                ("best_asks", ctypes.c_void_p), ("best_bids", ctypes.c_void_p), ("mid_price", ctypes.c_void_p),
+                ("n_levels", ctypes.c_int), ("tick_size", ctypes.c_int), ("raw", ctypes.c_void_p), ("l2", ctypes.c_void_p),
+                ("norm", ctypes.c_void_p), ("image", ctypes.c_void_p), ("img_dtype", ctypes.c_int), ("H", ctypes.c_int),
+                ("W", ctypes.c_int), ("cancel_mode", ctypes.c_int), ("init_id", ctypes.c_int32),
+                ("n_stat_agents", ctypes.c_int), ("stat_agent_ids", ctypes.c_int32 * 4), ("trade_stats", ctypes.c_void_p)]
+
+
 _lib = None
 _P, _I, _SZ = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
 
@@ -42,25 +102,26 @@ SIGNATURES = {
     "vitmarl_lob_step": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, ctypes.c_int32]),
     "vitmarl_lob_best_bid_ask": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "vitmarl_lob_render": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I]),
-    "vitmarl_gemm_bf16": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, ctypes.c_float]),
-    "vitmarl_gemm_set_2cta": (_I, [_I]),
+    "vitmarl_gemm_bf16": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _P, _I, _P, _I, ctypes.c_float, _I]),
     "vitmarl_vit_num_params": (_I, [_P]),
     "vitmarl_vit_param_elems": (ctypes.c_longlong, [_P, _I, _P]),
     "vitmarl_vit_workspace_bytes": (_SZ, [_P, _I]),
     "vitmarl_vit_fwd": (_I, [_P, _P, _P, _P, _P, _P, _SZ, _I]),
     "vitmarl_vit_bwd": (_I, [_P, _P, _P, _P, _SZ, _P, _P, _P]),
-    "vitmarl_vit_set_fused": (_I, [_I]),
-    "vitmarl_debug_fused_mlp_timeline": (_I, [_P]),
-    "vitmarl_debug_set_flags": (_I, [_I]),
-    "vitmarl_debug_gemm_dw": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
-    "vitmarl_vit_gemm_timing_enable": (_I, [_I]),
-    "vitmarl_vit_gemm_timing_read": (_I, [_P, _P, _P]),
-    "vitmarl_vit_timing_read_categories": (_I, [_P, _P]),
+    "vitmarl_vit_fwd_ex": (_I, [_P, _P, _P, _P, _P, _P, _SZ, _I, _P]),
+    "vitmarl_vit_bwd_ex": (_I, [_P, _P, _P, _P, _SZ, _P, _P, _P, _P]),
+    "vitmarl_vit_num_buckets": (_I, [_P]),
+    "vitmarl_timing_create": (_P, []),
+    "vitmarl_timing_destroy": (None, [_P]),
+    "vitmarl_timing_reset": (_I, [_P]),
+    "vitmarl_timing_read": (_I, [_P, _P, _P, _P]),
+    "vitmarl_debug_gemm_dw": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _I]),
     "vitmarl_get_cancel_msgs": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "vitmarl_get_agent_trades": (_I, [_P, _I, _I, _P, _I, _P]),
     "vitmarl_agent_trade_stats": (_I, [_P, _I, _I, _P, _I, _I, _P]),
     "vitmarl_filter_messages": (_I, [_P, _I, _I, _P, _P, _P, _P]),
-    "vitmarl_auto_reset": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "vitmarl_auto_reset": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "vitmarl_env_step2": (_I, [_P, _P]),
     "vitmarl_build_step_msgs": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vitmarl_env_step": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                               _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, ctypes.c_int32]),

@@ -28,14 +28,14 @@ extern "C" const char* vitmarl_last_error(void) { return vitmarl::g_err; }
 
 extern "C" int vitmarl_gemm_bf16(void* stream, int M, int N, int K, const void* A, int lda, int a_mn_major, const void* B,
                                  int ldb, int b_mn_major, void* C, int ldc, int epi, const float* bias, const void* residual,
-                                 int ldr, const float* pos, int pos_period, float out_scale) {
+                                 int ldr, const float* pos, int pos_period, float out_scale, int flags) {
   vitmarl::GemmDesc g;
   g.M = M; g.N = N; g.K = K;
   g.A = static_cast<const __nv_bfloat16*>(A); g.lda = lda; g.a_mn_major = a_mn_major != 0;
   g.B = static_cast<const __nv_bfloat16*>(B); g.ldb = ldb; g.b_mn_major = b_mn_major != 0;
   g.C = C; g.ldc = ldc; g.epi = epi; g.bias = bias;
   g.residual = static_cast<const __nv_bfloat16*>(residual); g.ldr = ldr; g.pos = pos; g.pos_period = pos_period;
-  g.out_scale = out_scale;
+  g.out_scale = out_scale; g.allow_2cta = !(flags & VITMARL_GEMM_NO_2CTA);
   if (epi < 0 || epi > 4) return VITMARL_EINVAL;
   return vitmarl::launch_gemm(static_cast<cudaStream_t>(stream), g);
 }

@@ -96,7 +96,8 @@ __global__ void step_msgs_kernel(const StepMsgParams p) {
 // message slots, mid = float32((best_bid + best_ask) / 2), trades of the loaded state).  One warp per environment; environments
 // that are not done are untouched (the reference materialises a full reset state for every env and selects).
 struct ResetParams {
-  int E, N, T, M;
+  int E, N, T, M, n_windows;
+  int32_t* bad_window;
   const int32_t* done; const int32_t* window;
   const int32_t* init_asks; const int32_t* init_bids; const int32_t* init_trades; const int32_t* init_best_asks; const int32_t* init_best_bids;
   int32_t* asks; int32_t* bids; int32_t* trades; int32_t* best_asks; int32_t* best_bids; float* mid;
@@ -105,7 +106,12 @@ struct ResetParams {
 __global__ void __launch_bounds__(128) auto_reset_kernel(const ResetParams p) {
   const int e = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (e >= p.E || p.done[e] == 0) return;
-  const size_t w = (size_t)p.window[e];
+  const int wi = p.window[e];
+  if (wi < 0 || wi >= p.n_windows) {                                // never index the init tables out of bounds
+    if (lane == 0 && p.bad_window) *p.bad_window = 1;
+    return;
+  }
+  const size_t w = (size_t)wi;
   const int side_v = p.N * 6 / 2;                                   // int2 elements per book side (N * 6 is even)
   const int2* sa = reinterpret_cast<const int2*>(p.init_asks + w * p.N * 6);
   const int2* sb = reinterpret_cast<const int2*>(p.init_bids + w * p.N * 6);
@@ -272,7 +278,7 @@ extern "C" int vitmarl_build_step_msgs(void* stream, int E, int n_total, int n_d
 extern "C" int vitmarl_auto_reset(void* stream, int E, int N, int T, int M, int n_windows, const int32_t* done, const int32_t* window_index,
                                   const int32_t* init_asks, const int32_t* init_bids, const int32_t* init_trades,
                                   const int32_t* init_best_asks, const int32_t* init_best_bids, int32_t* asks, int32_t* bids,
-                                  int32_t* trades, int32_t* best_asks, int32_t* best_bids, float* mid_price) {
+                                  int32_t* trades, int32_t* best_asks, int32_t* best_bids, float* mid_price, int32_t* bad_window) {
   if (E == 0) return VITMARL_OK;
   if (E < 0 || N < 1 || T < 0 || M < 0 || n_windows < 1 || !done || !window_index || !init_asks || !init_bids || !init_best_asks ||
       !init_best_bids || !asks || !bids || !trades || !best_asks || !best_bids)
@@ -283,7 +289,7 @@ extern "C" int vitmarl_auto_reset(void* stream, int E, int N, int T, int M, int 
        reinterpret_cast<uintptr_t>(init_bids) | reinterpret_cast<uintptr_t>(best_asks) | reinterpret_cast<uintptr_t>(best_bids) |
        reinterpret_cast<uintptr_t>(init_best_asks) | reinterpret_cast<uintptr_t>(init_best_bids)) & 7)
     return VITMARL_EINVAL;
-  ResetParams p{E, N, T, M, done, window_index, init_asks, init_bids, init_trades, init_best_asks, init_best_bids,
+  ResetParams p{E, N, T, M, n_windows, bad_window, done, window_index, init_asks, init_bids, init_trades, init_best_asks, init_best_bids,
                 asks, bids, trades, best_asks, best_bids, mid_price};
   auto_reset_kernel<<<(E + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return check_cuda(cudaGetLastError());

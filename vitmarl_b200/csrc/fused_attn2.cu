@@ -542,17 +542,12 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   }
 }
 
-static long long* g_fattn2_dbg = nullptr;
-static int g_fattn2_flags = 4;
-void fused_attn2_set_flags(int f) { g_fattn2_flags = f; }
-void fused_attn2_set_debug(long long* buf) { g_fattn2_dbg = buf; }
-
 bool fused_attn2_supported(int D, int heads, int tokens) { return D == fattn2::D && heads == fattn2::NH && tokens == 64; }
 
 // wqkvf: [3D, D] bf16 folded (Q rows scaled by log2(e)/8, all rows times LN gamma); bqp: [D] bf16 folded Q bias;
 // wo: [D, D] bf16; bof: [D] fp32 = bo + Wo . (bv + Wv . beta)   (vit_fold.cu)
 int launch_fused_attn2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16* out, const __nv_bfloat16* wqkvf, const __nv_bfloat16* bqp,
-                       const __nv_bfloat16* wo, const float* bof, int M, int D, int heads, float eps) {
+                       const __nv_bfloat16* wo, const float* bof, int M, int D, int heads, float eps, const FusedOpts& o) {
   using namespace fattn2;
   if (D != fattn2::D || heads != NH) { set_last_error("fused_attn2: only D=192, 3 heads"); return VITMARL_EINVAL; }
   if (M <= 0) return VITMARL_OK;
@@ -563,7 +558,7 @@ int launch_fused_attn2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat1
   if ((rc = make_tmap_2d_bf16(&tmOut, out, M, D, (uint64_t)D * 2, TM, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmWqkv, wqkvf, 3 * D, D, (uint64_t)D * 2, 64, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmWo, wo, D, D, (uint64_t)D * 2, D, 64))) return rc;
-  FusedAttn2Params p{M, x, reinterpret_cast<const uint32_t*>(bqp), bof, eps, g_fattn2_dbg, out == x ? 1 : 0, g_fattn2_flags};
+  FusedAttn2Params p{M, x, reinterpret_cast<const uint32_t*>(bqp), bof, eps, o.dbg ? o.dbg + 256 : nullptr, out == x ? 1 : 0, o.attn_flags};
   cudaError_t e = cudaFuncSetAttribute(fused_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return check_cuda(e);
   const int tiles = (M + TM - 1) / TM;
@@ -572,7 +567,7 @@ int launch_fused_attn2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat1
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = o.pdl ? 1 : 0;
   return check_cuda(cudaLaunchKernelEx(&cfg, fused_attn2_kernel, tmX, tmWqkv, tmWo, tmOut, p));
 }
 

@@ -414,14 +414,11 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
 }
 
-static long long* g_fmlp2_dbg = nullptr;
-void fused_mlp2_set_debug(long long* buf) { g_fmlp2_dbg = buf; }
-
 bool fused_mlp2_supported(int D, int hidden) { return D == fmlp2::D && hidden == fmlp2::HID; }
 
 // w1f: [HID, D] bf16 = W1 . diag(gamma);  b1p: [HID] bf16 = b1 + W1 . beta;  w2h: [D, HID] bf16 = W2 / 2  (vit_fold.cu)
 int launch_fused_mlp2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16* out, const __nv_bfloat16* w1f, const __nv_bfloat16* b1p,
-                      const __nv_bfloat16* w2h, const float* b2, int M, int D, int hidden, float eps) {
+                      const __nv_bfloat16* w2h, const float* b2, int M, int D, int hidden, float eps, const FusedOpts& o) {
   using namespace fmlp2;
   if (D != fmlp2::D || hidden != HID) { set_last_error("fused_mlp2: only D=192, hidden=768"); return VITMARL_EINVAL; }
   if (M <= 0) return VITMARL_OK;
@@ -431,7 +428,7 @@ int launch_fused_mlp2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16
   if ((rc = make_tmap_2d_bf16(&tmOut, out, M, D, (uint64_t)D * 2, TM, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmW1, w1f, HID, D, (uint64_t)D * 2, HC / 2, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmW2, w2h, fmlp2::D, HID, (uint64_t)HID * 2, fmlp2::D / 2, 64))) return rc;
-  FusedMlp2Params p{M, x, reinterpret_cast<const uint32_t*>(b1p), b2, eps, g_fmlp2_dbg, out == x ? 1 : 0};
+  FusedMlp2Params p{M, x, reinterpret_cast<const uint32_t*>(b1p), b2, eps, o.dbg, out == x ? 1 : 0};
   cudaError_t e = cudaFuncSetAttribute(fused_mlp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return check_cuda(e);
   const int pair_tiles = (M + 2 * TM - 1) / (2 * TM);
@@ -441,7 +438,7 @@ int launch_fused_mlp2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = o.pdl ? 1 : 0;
   return check_cuda(cudaLaunchKernelEx(&cfg, fused_mlp2_kernel, tmX, tmW1, tmW2, tmOut, p));
 }
 

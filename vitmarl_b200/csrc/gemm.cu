@@ -261,7 +261,7 @@ static int launch_gemm_bn(cudaStream_t stream, const GemmDesc& g) {
 int launch_gemm(cudaStream_t stream, const GemmDesc& g) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0 || !g.A || !g.B || !g.C) { set_last_error("gemm: bad arguments"); return VITMARL_EINVAL; }
   if (g.N % 64 || g.K % 8 || g.lda % 8 || g.ldb % 8 || (g.a_mn_major && g.M % 64)) { set_last_error("gemm: unsupported shape"); return VITMARL_EINVAL; }
-  if (gemm_2cta_enabled() && g.a_mn_major && g.b_mn_major && g.epi == EPI_ATOMIC_F32) {
+  if (g.allow_2cta && g.a_mn_major && g.b_mn_major && g.epi == EPI_ATOMIC_F32) {
     const int rc = launch_gemm2_dw(stream, g);           // (fuses g.colsum_a when it runs the product un-swapped)
     if (rc != 1) return rc;                              // 1: not a shape for the 256 x 384 weight-gradient kernel
   }

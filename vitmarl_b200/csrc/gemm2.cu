@@ -207,12 +207,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
-static bool g_use_2cta = true;
-void gemm_set_2cta(bool on) { g_use_2cta = on; }
-bool gemm_2cta_enabled() { return g_use_2cta; }
-
 bool gemm2_supported(const GemmDesc& g) {
-  if (!g_use_2cta || g.M < 512 || g.N % 192) return false;
+  if (!g.allow_2cta || g.M < 512 || g.N % 192) return false;
   if (!g.a_mn_major && !g.b_mn_major) return g.epi != EPI_ATOMIC_F32;
   if (!g.a_mn_major && g.b_mn_major) return g.epi != EPI_ATOMIC_F32;             // dX = dY . W (W read as an MN-major B)
   // dW = dY^T . X: both MN-major, split-K with fp32 red.add; output rows = features, worth it when 256-row pair tiles fill up

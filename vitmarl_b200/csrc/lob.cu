@@ -49,7 +49,11 @@ struct LobParams {
   int do_step;            // 0: render-only kernel (books are read, not written)
   int do_ffill;           // ffill best prices + mid price
   const int32_t* last_ask_price; const int32_t* last_bid_price;
+  int last_stride;        // element stride of the two arrays above (1 = dense [E]; 2*M = column [:, -1, 0] of a best-price track)
   float* mid_out;
+  // fused reward reductions over the step's trade log: stats [E, n_stat, 8] for up to 4 trader ids; with them
+  // the caller may pass trades_out = NULL and the [T,8] log never leaves the chip
+  int n_stat; int32_t stat_ids[4]; int32_t* stats; int stat_tick;
   // render
   int do_render; int n_levels; int tick;
   const float* mid_in;    // render-only: mid price input (nullable -> no norm)
@@ -644,6 +648,34 @@ __device__ __forceinline__ void render_env(const Side<RPL>& asks, const Side<RPL
   }
 }
 
+// ---------------------------------------------------------------- fused reward reductions
+// The integer trade reductions of both reward functions over ONE environment's trade log in shared memory -- the same
+// arithmetic as trade_stats_kernel (env_glue.cu; vision_env.py:2076-2078, 2156-2163, 2191, mm_env.py:1906-1936), int32
+// wrap-around like XLA.  out[8] = [sum qty, sum |qty|, c_rl, buyQuant, sellQuant, TradedVolume, inventory_delta, other |qty|].
+__device__ __forceinline__ void trade_stats_from_slab(const int32_t* sm_tr, int T, int agent_id, int tick, int32_t* out, int lane) {
+  unsigned s_q = 0, s_abs = 0, s_rev = 0, s_buy = 0, s_sell = 0, s_other = 0;
+  for (int r = lane; r < T; r += 32) {
+    const int4 a = *reinterpret_cast<const int4*>(sm_tr + r * 8), b = *reinterpret_cast<const int4*>(sm_tr + r * 8 + 4);
+    const bool executed = a.x >= 0;                                  // JOBA:827
+    const int price = executed ? a.x : 0, qty = executed ? a.y : 0, ptid = executed ? b.z : 0, atid = executed ? b.w : 0;
+    const bool mine = agent_id == ptid || agent_id == atid;         // evaluated on the zeroed row, as the reference does
+    const unsigned aq = qty < 0 ? 0u - (unsigned)qty : (unsigned)qty;
+    if (mine) {
+      s_q += (unsigned)qty; s_abs += aq; s_rev += (unsigned)(price / tick) * aq;
+      if ((qty >= 0 && agent_id == ptid) || (qty < 0 && agent_id == atid)) s_buy += aq;
+      if ((qty < 0 && agent_id == ptid) || (qty >= 0 && agent_id == atid)) s_sell += aq;
+    } else {
+      s_other += aq;
+    }
+  }
+  s_q = __reduce_add_sync(FULL, s_q); s_abs = __reduce_add_sync(FULL, s_abs); s_rev = __reduce_add_sync(FULL, s_rev);
+  s_buy = __reduce_add_sync(FULL, s_buy); s_sell = __reduce_add_sync(FULL, s_sell); s_other = __reduce_add_sync(FULL, s_other);
+  if (lane == 0) {
+    reinterpret_cast<int4*>(out)[0] = make_int4((int)s_q, (int)s_abs, (int)s_rev, (int)s_buy);
+    reinterpret_cast<int4*>(out)[1] = make_int4((int)s_sell, (int)(s_buy + s_sell), (int)(s_buy - s_sell), (int)s_other);
+  }
+}
+
 // ---------------------------------------------------------------- the kernel
 template <int RPL, int MINB>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) lob_kernel(const LobParams P) {
@@ -730,8 +762,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) lob_kernel(const LobP
         if (P.do_ffill) {
           // marl_env.py:685-711 on both tracks
           if (gi == 0) {
-            if (oa_p == -1) { oa_p = P.last_ask_price[e]; oa_v = 0; }
-            if (ob_p == -1) { ob_p = P.last_bid_price[e]; ob_v = 0; }
+            if (oa_p == -1) { oa_p = P.last_ask_price[(size_t)e * P.last_stride]; oa_v = 0; }
+            if (ob_p == -1) { ob_p = P.last_bid_price[(size_t)e * P.last_stride]; ob_v = 0; }
           }
           if (oa_p == -1) oa_v = 0;
           if (ob_p == -1) ob_v = 0;
@@ -793,6 +825,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) lob_kernel(const LobP
       have_mid = true;
       if (lane == 0 && P.mid_out) P.mid_out[e] = mid;
     }
+    // ---- reward-function reductions over the step's trade log while it is still on chip ----
+    if (P.n_stat > 0) {
+      __syncwarp();
+      for (int a = 0; a < P.n_stat; ++a) trade_stats_from_slab(sm_tr, T, P.stat_ids[a], P.stat_tick, P.stats + ((size_t)e * P.n_stat + a) * 8, lane);
+    }
     // ---- store: the shared-memory slabs are already up to date -> TMA bulk stores ---------
     if (P.bulk_ok) {
       fence_proxy_async_smem();
@@ -800,14 +837,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) lob_kernel(const LobP
       if (lane == 0) {
         bulk_s2g(P.asks_out + (size_t)e * side_words, smem_u32(sm_asks), side_words * 4);
         bulk_s2g(P.bids_out + (size_t)e * side_words, smem_u32(sm_bids), side_words * 4);
-        bulk_s2g(P.trades_out + (size_t)e * trade_words, smem_u32(sm_tr), trade_words * 4);
+        if (P.trades_out) bulk_s2g(P.trades_out + (size_t)e * trade_words, smem_u32(sm_tr), trade_words * 4);
         bulk_commit();
       }
     } else {
       __syncwarp();
       warp_copy_s2g(P.asks_out + (size_t)e * side_words, sm_asks, side_words, lane);
       warp_copy_s2g(P.bids_out + (size_t)e * side_words, sm_bids, side_words, lane);
-      warp_copy_s2g(P.trades_out + (size_t)e * trade_words, sm_tr, trade_words, lane);
+      if (P.trades_out) warp_copy_s2g(P.trades_out + (size_t)e * trade_words, sm_tr, trade_words, lane);
     }
   } else if (P.mid_in) {
     mid = P.mid_in[e];
@@ -841,7 +878,10 @@ static int launch_lob(cudaStream_t stream, LobParams& P) {
   if (P.E == 0) return VITMARL_OK;
   if (P.E < 0 || P.N < 1 || P.N > 256 || !P.asks_in || !P.bids_in) return VITMARL_EINVAL;
   if (P.do_step) {
-    if (P.T < 1 || P.T > 1024 || P.M < 0 || P.n_keep < 0 || !P.asks_out || !P.bids_out || !P.trades_out) return VITMARL_EINVAL;
+    if (P.T < 1 || P.T > 1024 || P.M < 0 || P.n_keep < 0 || !P.asks_out || !P.bids_out) return VITMARL_EINVAL;
+    if (!P.trades_out && P.n_stat <= 0) return VITMARL_EINVAL;                // the trade log may stay on chip only when its reductions are asked for
+    if (P.n_stat < 0 || P.n_stat > 4 || (P.n_stat > 0 && (!P.stats || (reinterpret_cast<uintptr_t>(P.stats) & 15) || P.stat_tick < 1))) return VITMARL_EINVAL;
+    if (P.last_stride < 1) P.last_stride = 1;
     if (P.M > 0 && !P.msgs) return VITMARL_EINVAL;
     if (P.n_keep > P.M) P.n_keep = P.M;
     if (P.do_ffill && (P.M < 1 || !P.last_ask_price || !P.last_bid_price || P.n_keep != P.M)) return VITMARL_EINVAL;
@@ -866,7 +906,7 @@ static int launch_lob(cudaStream_t stream, LobParams& P) {
   }
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   P.bulk_ok = ((P.N * 24) % 16 == 0) && al16(P.asks_in) && al16(P.bids_in) &&
-              (!P.do_step || (al16(P.asks_out) && al16(P.bids_out) && al16(P.trades_out) && (!P.trades_in || al16(P.trades_in))));
+              (!P.do_step || (al16(P.asks_out) && al16(P.bids_out) && (!P.trades_out || al16(P.trades_out)) && (!P.trades_in || al16(P.trades_in))));
   const int rpl = (P.N + 31) / 32;
   const size_t smem = (size_t)kWarpsPerCta * (2 * P.N * 6 + (P.do_step ? P.T * 8 : 0)) * sizeof(int32_t);
   const dim3 grid((P.E + kWarpsPerCta - 1) / kWarpsPerCta), block(kWarpsPerCta * 32);
@@ -929,6 +969,25 @@ extern "C" int vitmarl_lob_render(void* stream, int E, int N, int n_levels, int 
   P.do_render = 1; P.n_levels = n_levels; P.tick = tick_size; P.mid_in = mid_price;
   P.raw = raw; P.l2 = l2; P.norm = norm;
   P.image = (img_dtype == VITMARL_IMG_NONE) ? nullptr : image; P.img_dtype = img_dtype; P.H = H; P.W = W;
+  return vitmarl::launch_lob(static_cast<cudaStream_t>(stream), P);
+}
+
+extern "C" int vitmarl_env_step2(void* stream, const VitmarlEnvStepArgs* a) {
+  if (!a) return VITMARL_EINVAL;
+  if (a->cancel_mode != 0 && a->cancel_mode != 1) return VITMARL_EUNSUPPORTED;
+  LobParams P{};
+  P.E = a->E; P.N = a->N; P.T = a->T; P.M = a->M; P.n_keep = a->M; P.init_id = a->init_id;
+  P.asks_in = a->asks_in; P.bids_in = a->bids_in; P.msgs = a->msgs;
+  P.asks_out = a->asks_out; P.bids_out = a->bids_out; P.trades_out = a->trades_out;
+  P.best_asks = a->best_asks; P.best_bids = a->best_bids;
+  P.do_step = 1; P.do_ffill = 1; P.last_ask_price = a->last_ask_price; P.last_bid_price = a->last_bid_price;
+  P.last_stride = a->last_price_stride; P.mid_out = a->mid_price;
+  const bool img = a->image && a->img_dtype != VITMARL_IMG_NONE;
+  P.do_render = (a->raw || a->l2 || a->norm || img) ? 1 : 0;
+  P.n_levels = a->n_levels; P.tick = a->tick_size; P.raw = a->raw; P.l2 = a->l2; P.norm = a->norm;
+  P.image = img ? a->image : nullptr; P.img_dtype = a->img_dtype; P.H = a->H; P.W = a->W;
+  P.n_stat = a->n_stat_agents; P.stats = a->trade_stats; P.stat_tick = a->tick_size;
+  for (int i = 0; i < 4; ++i) P.stat_ids[i] = a->stat_agent_ids[i];
   return vitmarl::launch_lob(static_cast<cudaStream_t>(stream), P);
 }
 

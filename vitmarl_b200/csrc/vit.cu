@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <new>
+
 #include "common.cuh"
 #include "vit_kernels.h"
 #include "../../include/vitmarl_b200.h"
@@ -107,37 +109,51 @@ static Ws layout(const Dims& d, bool save) {
   return w;
 }
 
-// ---- optional per-launch timing (CUDA events on the launch stream; used by bench.py) ---------------
+// ---- optional per-launch timing (CUDA events on the launch stream), owned by a caller-created handle ---------------
 enum { CAT_GEMM = 0, CAT_FUSED_MLP = 1, CAT_FUSED_ATTN = 2, CAT_ATTENTION = 3, CAT_LAYERNORM = 4, CAT_OTHER = 5, CAT_GEMM_DW = 6, CAT_GEMM_DX = 7, CAT_COUNT = 8 };
 struct OpTiming {
-  bool enabled = false;
   static constexpr int kMax = 16384;
   cudaEvent_t ev[2 * kMax];
   unsigned char cat[kMax];
-  bool created = false;
+  int created = 0;        // events created so far (lazily, two per logged launch)
   int n = 0;
-  double flops = 0.0;     // algorithmic FLOPs of the tensor-core launches (categories 0-2)
+  double flops = 0.0;     // algorithmic FLOPs of the tensor-core launches
 };
-static OpTiming g_timing;
-static int g_fused_mode = 1;      // inference path: 0 unfused kernel sequence, 1 fused block kernels (CTA-pair MLP), 2 legacy 1-CTA fused kernels
+
+// Everything a call may switch, resolved from VitmarlVitOptions (NULL = defaults).  No process-global mutable state: two
+// threads / devices calling into the library concurrently never see each other's settings.
+struct RunOpts {
+  int fused = 1;                    // 0 unfused kernel sequence, 1 fused block kernels where the shape allows
+  bool two_cta = true;
+  FusedOpts fo;
+  OpTiming* timing = nullptr;
+  void* grads_flat = nullptr; size_t grads_flat_bytes = 0;
+  bool accumulate = false;
+  void* const* bucket_events = nullptr;
+};
 
 template <typename F>
-static int timed(cudaStream_t st, int cat, double flops, F&& launch) {
-  OpTiming& t = g_timing;
-  const bool on = t.enabled && t.n < OpTiming::kMax;
-  if (on) cudaEventRecord(t.ev[2 * t.n], st);
+static int timed(cudaStream_t st, const RunOpts& o, int cat, double flops, F&& launch) {
+  OpTiming* t = o.timing;
+  bool on = t && t->n < OpTiming::kMax;
+  if (on && t->created < 2 * (t->n + 1)) {
+    for (int i = t->created; i < 2 * (t->n + 1); ++i)
+      if (cudaEventCreate(&t->ev[i]) != cudaSuccess) { on = false; break; } else t->created = i + 1;
+  }
+  if (on) cudaEventRecord(t->ev[2 * t->n], st);
   int rc = launch();
   if (on) {
-    cudaEventRecord(t.ev[2 * t.n + 1], st);
-    t.cat[t.n] = (unsigned char)cat;
-    t.flops += flops;
-    ++t.n;
+    cudaEventRecord(t->ev[2 * t->n + 1], st);
+    t->cat[t->n] = (unsigned char)cat;
+    t->flops += flops;
+    ++t->n;
   }
   return rc;
 }
 
-static int timed_gemm(cudaStream_t st, const GemmDesc& g) {
-  return timed(st, CAT_GEMM, 2.0 * g.M * g.N * g.K, [&] { return launch_gemm(st, g); });
+static int timed_gemm(cudaStream_t st, const RunOpts& o, GemmDesc& g) {
+  g.allow_2cta = o.two_cta;
+  return timed(st, o, CAT_GEMM, 2.0 * g.M * g.N * g.K, [&] { return launch_gemm(st, g); });
 }
 
 #define VM_TRY(x)            \
@@ -153,13 +169,17 @@ static GemmDesc gd(int M, int N, int K, const bf16* A, int lda, bool amn, const 
   return g;
 }
 
-static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, const bf16* x, float* y, uint8_t* ws, bool save, bool reuse_folded = false,
-                       bool x_is_patches = false) {
+static int vit_forward(cudaStream_t st, const RunOpts& o, const Dims& d, const void* const* prm, const bf16* x, float* y, uint8_t* ws, bool save,
+                       bool reuse_folded = false, bool x_is_patches = false) {
   const Ws w = layout(d, save);
   const int M = d.M, D = d.D;
   auto PB = [&](int i) { return static_cast<const bf16*>(prm[i]); };
   auto PF = [&](int i) { return static_cast<const float*>(prm[i]); };
-  const bf16* patches = x_is_patches ? x : reinterpret_cast<const bf16*>(ws + w.patches);   // the caller may hand in the patch matrix itself
+  const bf16* patches = (x_is_patches && !save) ? x : reinterpret_cast<const bf16*>(ws + w.patches);   // the caller may hand in the patch matrix itself
+  if (x_is_patches && save) {   // training: the backward pass needs the patch matrix (patch-embedding dW) -> keep a copy in the workspace
+    cudaError_t e = cudaMemcpyAsync(ws + w.patches, x, (size_t)M * d.Kp * sizeof(bf16), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return check_cuda(e);
+  }
   auto X = [&](int l) { return reinterpret_cast<bf16*>(ws + w.x + (save ? (size_t)l * w.sz_md : 0)); };
   auto XM = [&](int l) { return reinterpret_cast<bf16*>(ws + w.xm + (save ? (size_t)l * w.sz_md : 0)); };
   auto LN1 = [&](int l) { return reinterpret_cast<bf16*>(ws + w.ln1 + (save ? (size_t)l * w.sz_md : 0)); };
@@ -173,8 +193,8 @@ static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, c
 
   // inference: fold LayerNorm scale/shift, the GELU 1/2, the softmax scale and the K / V biases into the projections
   // (vit_fold.cu), all layers in two launches (the second one needs the folded V bias of the first)
-  const bool fuse_mlp2 = !save && g_fused_mode == 1 && fused_mlp2_supported(D, d.mlp) && d.L * 5 <= 64;
-  const bool fuse_attn2 = !save && g_fused_mode == 1 && fused_attn2_supported(D, d.heads, d.T) && d.L * 5 <= 64;
+  const bool fuse_mlp2 = !save && o.fused == 1 && fused_mlp2_supported(D, d.mlp) && d.L * 5 <= 64;
+  const bool fuse_attn2 = !save && o.fused == 1 && fused_attn2_supported(D, d.heads, d.T) && d.L * 5 <= 64;
   auto FW = [&](int l, size_t o) { return reinterpret_cast<bf16*>(ws + w.fold + (size_t)l * w.sz_fold + o); };
   auto FF = [&](int l, size_t o) { return reinterpret_cast<float*>(ws + w.fold + (size_t)l * w.sz_fold + o); };
   if ((fuse_mlp2 || fuse_attn2) && !reuse_folded) {
@@ -197,81 +217,66 @@ static int vit_forward(cudaStream_t st, const Dims& d, const void* const* prm, c
         jobs2.job[jobs2.n++] = FoldJob{PB(p_layer(l, L_OUT_W)), PF(p_layer(l, L_OUT_B)), nullptr, FF(l, w.f_bv), nullptr, FF(l, w.f_bo), D, D, 0, 1.0f};
       }
     }
-    VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_fold_params(st, jobs); }));
-    if (jobs2.n) VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_fold_params(st, jobs2); }));
+    VM_TRY(timed(st, o, CAT_OTHER, 0, [&] { return launch_fold_params(st, jobs); }));
+    if (jobs2.n) VM_TRY(timed(st, o, CAT_OTHER, 0, [&] { return launch_fold_params(st, jobs2); }));
   }
   const bool pos_tiled = 128 % d.T == 0;
   bf16* pos_tile = reinterpret_cast<bf16*>(ws + w.pos_tile);
-  if (pos_tiled && !reuse_folded) VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_pos_tile(st, PF(P_POS), pos_tile, d.T, D); }));
+  if (pos_tiled && !reuse_folded) VM_TRY(timed(st, o, CAT_OTHER, 0, [&] { return launch_pos_tile(st, PF(P_POS), pos_tile, d.T, D); }));
   // patch embedding: tokens = patches . Wpe^T + b + pos
   if (!x_is_patches)
-    VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_patchify(st, x, reinterpret_cast<bf16*>(ws + w.patches), d.B, d.H, d.W, d.C, d.P); }));
+    VM_TRY(timed(st, o, CAT_OTHER, 0, [&] { return launch_patchify(st, x, reinterpret_cast<bf16*>(ws + w.patches), d.B, d.H, d.W, d.C, d.P); }));
   {
     GemmDesc g = gd(M, D, d.Kp, patches, d.Kp, false, PB(P_PE_W), d.Kp, false, X(0), D, EPI_STORE_BF16);
     g.bias = PF(P_PE_B); g.pos = PF(P_POS); g.pos_period = d.T;
     if (pos_tiled) g.pos_tile = pos_tile;
-    VM_TRY(timed_gemm(st, g));
+    VM_TRY(timed_gemm(st, o, g));
   }
   for (int l = 0; l < d.L; ++l) {
-    const bool fuse_attn = !save && g_fused_mode && fused_attn_supported(D, d.heads, d.T);
     if (fuse_attn2) {
       // inference: LN1 + QKV + softmax(QK^T)V + out-projection + residual in one kernel on the folded parameters
-      VM_TRY(timed(st, CAT_FUSED_ATTN, 8.0 * M * D * D + 4.0 * M * d.T * D, [&] {
-        return launch_fused_attn2(st, X(l), XM(l), FW(l, w.f_wqkv), FW(l, w.f_bq), PB(p_layer(l, L_OUT_W)), FF(l, w.f_bo), M, D, d.heads, d.eps);
-      }));
-    } else if (fuse_attn) {
-      // legacy 1-CTA fused attention block
-      VM_TRY(timed(st, CAT_FUSED_ATTN, 8.0 * M * D * D + 4.0 * M * d.T * D, [&] {
-        return launch_fused_attn(st, X(l), XM(l), PF(p_layer(l, L_LN1_G)), PF(p_layer(l, L_LN1_B)), PB(p_layer(l, L_QKV_W)),
-                                 PF(p_layer(l, L_QKV_B)), PB(p_layer(l, L_OUT_W)), PF(p_layer(l, L_OUT_B)), M, D, d.heads, d.eps);
+      VM_TRY(timed(st, o, CAT_FUSED_ATTN, 8.0 * M * D * D + 4.0 * M * d.T * D, [&] {
+        return launch_fused_attn2(st, X(l), XM(l), FW(l, w.f_wqkv), FW(l, w.f_bq), PB(p_layer(l, L_OUT_W)), FF(l, w.f_bo), M, D, d.heads, d.eps, o.fo);
       }));
     } else {
-    VM_TRY(timed(st, CAT_LAYERNORM, 0, [&] { return launch_layernorm(st, X(l), PF(p_layer(l, L_LN1_G)), PF(p_layer(l, L_LN1_B)), LN1(l), ST1(l), M, D, d.eps); }));
+    VM_TRY(timed(st, o, CAT_LAYERNORM, 0, [&] { return launch_layernorm(st, X(l), PF(p_layer(l, L_LN1_G)), PF(p_layer(l, L_LN1_B)), LN1(l), ST1(l), M, D, d.eps); }));
     {
       GemmDesc g = gd(M, 3 * D, D, LN1(l), D, false, PB(p_layer(l, L_QKV_W)), D, false, QKV(l), 3 * D, EPI_STORE_BF16);
       g.bias = PF(p_layer(l, L_QKV_B));
-      VM_TRY(timed_gemm(st, g));
+      VM_TRY(timed_gemm(st, o, g));
     }
-    VM_TRY(timed(st, CAT_ATTENTION, 0, [&] { return launch_attention(st, QKV(l), ATT(l), d.B, d.heads); }));
+    VM_TRY(timed(st, o, CAT_ATTENTION, 0, [&] { return launch_attention(st, QKV(l), ATT(l), d.B, d.heads); }));
     {
       GemmDesc g = gd(M, D, D, ATT(l), D, false, PB(p_layer(l, L_OUT_W)), D, false, XM(l), D, EPI_STORE_BF16);
       g.bias = PF(p_layer(l, L_OUT_B)); g.residual = X(l); g.ldr = D;
-      VM_TRY(timed_gemm(st, g));
+      VM_TRY(timed_gemm(st, o, g));
     }
     }
     if (fuse_mlp2) {
       // inference: LN2 + FC1 + GELU + FC2 + residual in one CTA-pair kernel on the folded parameters
-      VM_TRY(timed(st, CAT_FUSED_MLP, 4.0 * M * D * d.mlp, [&] {
-        return launch_fused_mlp2(st, XM(l), X(l + 1), FW(l, w.f_w1), FW(l, w.f_b1), FW(l, w.f_w2), PF(p_layer(l, L_FC2_B)), M, D, d.mlp, d.eps);
+      VM_TRY(timed(st, o, CAT_FUSED_MLP, 4.0 * M * D * d.mlp, [&] {
+        return launch_fused_mlp2(st, XM(l), X(l + 1), FW(l, w.f_w1), FW(l, w.f_b1), FW(l, w.f_w2), PF(p_layer(l, L_FC2_B)), M, D, d.mlp, d.eps, o.fo);
       }));
       continue;
     }
-    if (!save && g_fused_mode && fused_mlp_supported(D, d.mlp)) {
-      // legacy 1-CTA fused MLP block
-      VM_TRY(timed(st, CAT_FUSED_MLP, 4.0 * M * D * d.mlp, [&] {
-        return launch_fused_mlp(st, XM(l), X(l + 1), PF(p_layer(l, L_LN2_G)), PF(p_layer(l, L_LN2_B)), PB(p_layer(l, L_FC1_W)),
-                                PF(p_layer(l, L_FC1_B)), PB(p_layer(l, L_FC2_W)), PF(p_layer(l, L_FC2_B)), M, D, d.mlp, d.eps);
-      }));
-      continue;
-    }
-    VM_TRY(timed(st, CAT_LAYERNORM, 0, [&] { return launch_layernorm(st, XM(l), PF(p_layer(l, L_LN2_G)), PF(p_layer(l, L_LN2_B)), LN2(l), ST2(l), M, D, d.eps); }));
+    VM_TRY(timed(st, o, CAT_LAYERNORM, 0, [&] { return launch_layernorm(st, XM(l), PF(p_layer(l, L_LN2_G)), PF(p_layer(l, L_LN2_B)), LN2(l), ST2(l), M, D, d.eps); }));
     {
       GemmDesc g = gd(M, d.mlp, D, LN2(l), D, false, PB(p_layer(l, L_FC1_W)), D, false, HACT(l), d.mlp, EPI_BIAS_GELU);
       g.bias = PF(p_layer(l, L_FC1_B)); g.C2 = HPRE(l);
-      VM_TRY(timed_gemm(st, g));
+      VM_TRY(timed_gemm(st, o, g));
     }
     {
       GemmDesc g = gd(M, D, d.mlp, HACT(l), d.mlp, false, PB(p_layer(l, L_FC2_W)), d.mlp, false, X(l + 1), D, EPI_STORE_BF16);
       g.bias = PF(p_layer(l, L_FC2_B)); g.residual = XM(l); g.ldr = D;
-      VM_TRY(timed_gemm(st, g));
+      VM_TRY(timed_gemm(st, o, g));
     }
   }
   float* stf = save ? reinterpret_cast<float*>(ws + w.stf) : nullptr;
-  VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_final_ln_pool(st, X(d.L), PF(p_lnf_g(d)), PF(p_lnf_g(d) + 1), y, stf, d.B, d.T, D, d.eps); }));
+  VM_TRY(timed(st, o, CAT_OTHER, 0, [&] { return launch_final_ln_pool(st, X(d.L), PF(p_lnf_g(d)), PF(p_lnf_g(d) + 1), y, stf, d.B, d.T, D, d.eps); }));
   return VITMARL_OK;
 }
 
-static int vit_backward(cudaStream_t st, const Dims& d, const void* const* prm, uint8_t* ws, const float* dy, void* const* dprm, bf16* dx) {
+static int vit_backward(cudaStream_t st, const RunOpts& o, const Dims& d, const void* const* prm, uint8_t* ws, const float* dy, void* const* dprm, bf16* dx) {
   const Ws w = layout(d, true);
   const int M = d.M, D = d.D, H = d.mlp;
   auto PB = [&](int i) { return static_cast<const bf16*>(prm[i]); };
@@ -295,49 +300,67 @@ static int vit_backward(cudaStream_t st, const Dims& d, const void* const* prm, 
   bf16* dH = reinterpret_cast<bf16*>(ws + w.dH);
   bf16* dQKV = reinterpret_cast<bf16*>(ws + w.dQKV);
 
-  for (int i = 0; i < num_params(d); ++i) {
-    bool mat;
-    size_t n = param_elems(d, i, &mat);
-    cudaError_t e = cudaMemsetAsync(dprm[i], 0, n * sizeof(float), st);
+  if (o.accumulate) {
+    // micro-batch accumulation: the table keeps its contents, every gradient below is ADDED by fp32 reductions
+  } else if (o.grads_flat) {
+    // the caller carved the whole gradient table out of ONE buffer (GradAllReducer): a single memset instead of one per tensor
+    cudaError_t e = cudaMemsetAsync(o.grads_flat, 0, o.grads_flat_bytes, st);
     if (e != cudaSuccess) return check_cuda(e);
+  } else {
+    for (int i = 0; i < num_params(d); ++i) {
+      bool mat;
+      size_t n = param_elems(d, i, &mat);
+      cudaError_t e = cudaMemsetAsync(dprm[i], 0, n * sizeof(float), st);
+      if (e != cudaSuccess) return check_cuda(e);
+    }
   }
+  // gradient buckets in the order the backward pass completes them: 0 = final LayerNorm, 1 + (L-1-l) = block l, L+1 = patch
+  // embedding + position embedding.  An event per bucket lets the caller start that bucket's all-reduce on a side stream while
+  // the next block's backward runs (jax.lax.pmean of the pmap trainer, ippo_rnn_JAXMARL_pmap.py:564-565).
+  auto bucket_done = [&](int b) -> int {
+    if (!o.bucket_events || !o.bucket_events[b]) return VITMARL_OK;
+    return check_cuda(cudaEventRecord(static_cast<cudaEvent_t>(o.bucket_events[b]), st));
+  };
   // dW[out,in] += dY^T . Xin   (both operands MN-major over the token dimension; split-K red.add)
   // db[out] += column sums of dY: handed to the same launch (the CTA-pair weight-gradient kernel folds it into its main loop as
   // one more MMA against a tile of ones, so dY is not read a second time; other shapes run the separate column-sum pass)
   auto dW = [&](float* dw, float* db, const bf16* dY, int n_out, const bf16* Xin, int n_in) {
     GemmDesc g = gd(n_out, n_in, M, dY, n_out, true, Xin, n_in, true, dw, n_in, EPI_ATOMIC_F32);
-    g.colsum_a = db;
-    return timed(st, CAT_GEMM_DW, 2.0 * g.M * g.N * g.K, [&] { return launch_gemm(st, g); });
+    g.colsum_a = db; g.allow_2cta = o.two_cta;
+    return timed(st, o, CAT_GEMM_DW, 2.0 * g.M * g.N * g.K, [&] { return launch_gemm(st, g); });
   };
   // dXin[M,n_in] = dY[M,n_out] . W[n_out,n_in]   (W read as the MN-major B operand)
   auto dXg = [&](bf16* dXin, const bf16* dY, int n_out, const bf16* W, int n_in, int epi, const bf16* aux) {
     GemmDesc g = gd(M, n_in, n_out, dY, n_out, false, W, n_in, true, dXin, n_in, epi);
-    g.residual = aux; g.ldr = n_in;
-    return timed(st, CAT_GEMM_DX, 2.0 * g.M * g.N * g.K, [&] { return launch_gemm(st, g); });
+    g.residual = aux; g.ldr = n_in; g.allow_2cta = o.two_cta;
+    return timed(st, o, CAT_GEMM_DX, 2.0 * g.M * g.N * g.K, [&] { return launch_gemm(st, g); });
   };
 
-  VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_final_ln_pool_bwd(st, X(d.L), PF(p_lnf_g(d)), stf, dy, dA, G(p_lnf_g(d)), G(p_lnf_g(d) + 1), d.B, d.T, D); }));
+  VM_TRY(timed(st, o, CAT_OTHER, 0, [&] { return launch_final_ln_pool_bwd(st, X(d.L), PF(p_lnf_g(d)), stf, dy, dA, G(p_lnf_g(d)), G(p_lnf_g(d) + 1), d.B, d.T, D); }));
+  VM_TRY(bucket_done(0));
   for (int l = d.L - 1; l >= 0; --l) {
     // ---- MLP branch: x_{l+1} = xm + fc2(gelu(fc1(ln2(xm))))
     VM_TRY(dW(G(p_layer(l, L_FC2_W)), G(p_layer(l, L_FC2_B)), dA, D, HACT(l), H));
     VM_TRY(dXg(dH, dA, D, PB(p_layer(l, L_FC2_W)), H, EPI_MUL_GELU_GRAD, HPRE(l)));
     VM_TRY(dW(G(p_layer(l, L_FC1_W)), G(p_layer(l, L_FC1_B)), dH, H, LN2(l), D));
     VM_TRY(dXg(dC, dH, H, PB(p_layer(l, L_FC1_W)), D, EPI_STORE_BF16, nullptr));
-    VM_TRY(timed(st, CAT_LAYERNORM, 0, [&] { return launch_layernorm_bwd(st, XM(l), PF(p_layer(l, L_LN2_G)), ST2(l), dC, dA, dB, G(p_layer(l, L_LN2_G)), G(p_layer(l, L_LN2_B)), M, D); }));
+    VM_TRY(timed(st, o, CAT_LAYERNORM, 0, [&] { return launch_layernorm_bwd(st, XM(l), PF(p_layer(l, L_LN2_G)), ST2(l), dC, dA, dB, G(p_layer(l, L_LN2_G)), G(p_layer(l, L_LN2_B)), M, D); }));
     // ---- attention branch: xm = x_l + out(attn(qkv(ln1(x_l))))
     VM_TRY(dW(G(p_layer(l, L_OUT_W)), G(p_layer(l, L_OUT_B)), dB, D, ATT(l), D));
     VM_TRY(dXg(dC, dB, D, PB(p_layer(l, L_OUT_W)), D, EPI_STORE_BF16, nullptr));
-    VM_TRY(timed(st, CAT_ATTENTION, 0, [&] { return launch_attention_bwd(st, QKV(l), dC, dQKV, d.B, d.heads); }));
+    VM_TRY(timed(st, o, CAT_ATTENTION, 0, [&] { return launch_attention_bwd(st, QKV(l), dC, dQKV, d.B, d.heads); }));
     VM_TRY(dW(G(p_layer(l, L_QKV_W)), G(p_layer(l, L_QKV_B)), dQKV, 3 * D, LN1(l), D));
     VM_TRY(dXg(dC, dQKV, 3 * D, PB(p_layer(l, L_QKV_W)), D, EPI_STORE_BF16, nullptr));
-    VM_TRY(timed(st, CAT_LAYERNORM, 0, [&] { return launch_layernorm_bwd(st, X(l), PF(p_layer(l, L_LN1_G)), ST1(l), dC, dB, dA, G(p_layer(l, L_LN1_G)), G(p_layer(l, L_LN1_B)), M, D); }));
+    VM_TRY(timed(st, o, CAT_LAYERNORM, 0, [&] { return launch_layernorm_bwd(st, X(l), PF(p_layer(l, L_LN1_G)), ST1(l), dC, dB, dA, G(p_layer(l, L_LN1_G)), G(p_layer(l, L_LN1_B)), M, D); }));
+    VM_TRY(bucket_done(1 + (d.L - 1 - l)));
   }
   // ---- patch embedding
-  VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_colsum(st, dA, G(P_POS), d.B, d.T * D); }));     // dpos[t,:] = sum over images
+  VM_TRY(timed(st, o, CAT_OTHER, 0, [&] { return launch_colsum(st, dA, G(P_POS), d.B, d.T * D); }));     // dpos[t,:] = sum over images
   VM_TRY(dW(G(P_PE_W), G(P_PE_B), dA, D, patches, d.Kp));
+  VM_TRY(bucket_done(d.L + 1));
   if (dx) {
     VM_TRY(dXg(patches, dA, D, PB(P_PE_W), d.Kp, EPI_STORE_BF16, nullptr));   // reuse the patches buffer for d(patches)
-    VM_TRY(timed(st, CAT_OTHER, 0, [&] { return launch_unpatchify(st, patches, dx, d.B, d.H, d.W, d.C, d.P); }));
+    VM_TRY(timed(st, o, CAT_OTHER, 0, [&] { return launch_unpatchify(st, patches, dx, d.B, d.H, d.W, d.C, d.P); }));
   }
   return VITMARL_OK;
 }
@@ -367,8 +390,23 @@ extern "C" size_t vitmarl_vit_workspace_bytes(const VitmarlVitShape* s, int save
   return layout(d, save_for_bwd == 1).total;
 }
 
-extern "C" int vitmarl_vit_fwd(void* stream, const VitmarlVitShape* s, const void* const* params, const void* x, float* y,
-                               void* workspace, size_t workspace_bytes, int save_for_bwd) {
+static RunOpts resolve(const VitmarlVitOptions* v) {
+  RunOpts o;
+  if (!v) return o;
+  if (v->fused >= 0) o.fused = v->fused ? 1 : 0;
+  if (v->gemm_2cta >= 0) o.two_cta = v->gemm_2cta != 0;
+  if (v->pdl >= 0) o.fo.pdl = v->pdl != 0;
+  if (v->attn_flags >= 0) o.fo.attn_flags = v->attn_flags & 0xff;
+  o.fo.dbg = v->debug_timeline;
+  o.timing = static_cast<OpTiming*>(v->timing);
+  o.grads_flat = v->grads_flat; o.grads_flat_bytes = v->grads_flat_bytes;
+  o.accumulate = v->accumulate > 0;
+  o.bucket_events = v->bucket_events;
+  return o;
+}
+
+extern "C" int vitmarl_vit_fwd_ex(void* stream, const VitmarlVitShape* s, const void* const* params, const void* x, float* y,
+                                  void* workspace, size_t workspace_bytes, int save_for_bwd, const VitmarlVitOptions* opt) {
   Dims d;
   VM_TRY(get_dims(s, d));
   if (d.B == 0) return VITMARL_OK;
@@ -376,104 +414,82 @@ extern "C" int vitmarl_vit_fwd(void* stream, const VitmarlVitShape* s, const voi
   const bool x_is_patches = (save_for_bwd & VITMARL_VIT_INPUT_PATCHES) != 0;
   save_for_bwd &= ~VITMARL_VIT_INPUT_PATCHES;
   const bool save = save_for_bwd == 1;
-  if (x_is_patches && (save || (reinterpret_cast<uintptr_t>(x) & 15))) { set_last_error("vit_fwd: patch-matrix input is for inference and 16-byte aligned"); return VITMARL_EINVAL; }
+  if (x_is_patches && (reinterpret_cast<uintptr_t>(x) & 15)) { set_last_error("vit_fwd: patch-matrix input must be 16-byte aligned"); return VITMARL_EINVAL; }
   if (workspace_bytes < layout(d, save).total) { set_last_error("vit_fwd: workspace too small"); return VITMARL_EINVAL; }
-  return vit_forward(static_cast<cudaStream_t>(stream), d, params, static_cast<const bf16*>(x), y, static_cast<uint8_t*>(workspace), save, save_for_bwd == 2,
-                     x_is_patches);
+  return vit_forward(static_cast<cudaStream_t>(stream), resolve(opt), d, params, static_cast<const bf16*>(x), y, static_cast<uint8_t*>(workspace), save,
+                     save_for_bwd == 2, x_is_patches);
 }
 
-extern "C" int vitmarl_vit_bwd(void* stream, const VitmarlVitShape* s, const void* const* params, void* workspace,
-                               size_t workspace_bytes, const float* dy, void* const* dparams, void* dx) {
+extern "C" int vitmarl_vit_fwd(void* stream, const VitmarlVitShape* s, const void* const* params, const void* x, float* y,
+                               void* workspace, size_t workspace_bytes, int save_for_bwd) {
+  return vitmarl_vit_fwd_ex(stream, s, params, x, y, workspace, workspace_bytes, save_for_bwd, nullptr);
+}
+
+extern "C" int vitmarl_vit_bwd_ex(void* stream, const VitmarlVitShape* s, const void* const* params, void* workspace,
+                                  size_t workspace_bytes, const float* dy, void* const* dparams, void* dx, const VitmarlVitOptions* opt) {
   Dims d;
   VM_TRY(get_dims(s, d));
   if (d.B == 0) return VITMARL_OK;
   if (!params || !workspace || !dy || !dparams) return VITMARL_EINVAL;
   if (workspace_bytes < layout(d, true).total) { set_last_error("vit_bwd: workspace too small"); return VITMARL_EINVAL; }
-  return vit_backward(static_cast<cudaStream_t>(stream), d, params, static_cast<uint8_t*>(workspace), dy, dparams, static_cast<bf16*>(dx));
+  return vit_backward(static_cast<cudaStream_t>(stream), resolve(opt), d, params, static_cast<uint8_t*>(workspace), dy, dparams, static_cast<bf16*>(dx));
 }
 
-// Enable / disable CUDA-event timing of the launches issued by vit_fwd / vit_bwd (resets the log).
-extern "C" int vitmarl_vit_gemm_timing_enable(int enable) {
-  OpTiming& t = g_timing;
-  if (enable && !t.created) {
-    for (int i = 0; i < 2 * OpTiming::kMax; ++i)
-      if (cudaEventCreate(&t.ev[i]) != cudaSuccess) return check_cuda(cudaGetLastError());
-    t.created = true;
-  }
-  t.enabled = enable != 0;
-  t.n = 0;
-  t.flops = 0.0;
+extern "C" int vitmarl_vit_bwd(void* stream, const VitmarlVitShape* s, const void* const* params, void* workspace,
+                               size_t workspace_bytes, const float* dy, void* const* dparams, void* dx) {
+  return vitmarl_vit_bwd_ex(stream, s, params, workspace, workspace_bytes, dy, dparams, dx, nullptr);
+}
+
+extern "C" int vitmarl_vit_num_buckets(const VitmarlVitShape* s) {
+  Dims d;
+  if (get_dims(s, d)) return VITMARL_EINVAL;
+  return d.L + 2;
+}
+
+// ---- timing handle: CUDA-event log of the launches issued by calls that carry it in their options --------------------------
+extern "C" void* vitmarl_timing_create(void) { return new (std::nothrow) OpTiming(); }
+
+extern "C" void vitmarl_timing_destroy(void* h) {
+  OpTiming* t = static_cast<OpTiming*>(h);
+  if (!t) return;
+  for (int i = 0; i < t->created; ++i) cudaEventDestroy(t->ev[i]);
+  delete t;
+}
+
+extern "C" int vitmarl_timing_reset(void* h) {
+  OpTiming* t = static_cast<OpTiming*>(h);
+  if (!t) return VITMARL_EINVAL;
+  t->n = 0; t->flops = 0.0;
   return VITMARL_OK;
 }
 
 // Per-category totals: ms8 / n8 are arrays of 8 (0 gemm, 1 fused mlp, 2 fused attention block, 3 attention,
-// 4 layernorm, 5 other, 6 dW gemm, 7 dX gemm).  Synchronises on the last logged launch.
-extern "C" int vitmarl_vit_timing_read_categories(double* ms8, long long* n8) {
-  OpTiming& t = g_timing;
+// 4 layernorm, 5 other, 6 dW gemm, 7 dX gemm); flops = algorithmic FLOPs of the tensor-core launches (categories 0-2, 6, 7).
+// Synchronises on the last logged launch.
+extern "C" int vitmarl_timing_read(void* h, double* ms8, long long* n8, double* flops) {
+  OpTiming* t = static_cast<OpTiming*>(h);
+  if (!t) return VITMARL_EINVAL;
   for (int i = 0; i < CAT_COUNT; ++i) { if (ms8) ms8[i] = 0.0; if (n8) n8[i] = 0; }
-  if (t.n > 0) {
-    cudaError_t e = cudaEventSynchronize(t.ev[2 * t.n - 1]);
+  if (t->n > 0) {
+    cudaError_t e = cudaEventSynchronize(t->ev[2 * t->n - 1]);
     if (e != cudaSuccess) return check_cuda(e);
-    for (int i = 0; i < t.n; ++i) {
+    for (int i = 0; i < t->n; ++i) {
       float x = 0.f;
-      if (cudaEventElapsedTime(&x, t.ev[2 * i], t.ev[2 * i + 1]) == cudaSuccess && ms8) ms8[t.cat[i]] += x;
-      if (n8) n8[t.cat[i]] += 1;
+      if (cudaEventElapsedTime(&x, t->ev[2 * i], t->ev[2 * i + 1]) == cudaSuccess && ms8) ms8[t->cat[i]] += x;
+      if (n8) n8[t->cat[i]] += 1;
     }
   }
-  return VITMARL_OK;
-}
-
-// Tensor-core launches only (GEMM + fused block kernels): total ms, launches, algorithmic FLOPs.
-extern "C" int vitmarl_vit_gemm_timing_read(double* total_ms, long long* launches, double* flops) {
-  double ms8[CAT_COUNT];
-  long long n8[CAT_COUNT];
-  int rc = vitmarl_vit_timing_read_categories(ms8, n8);
-  if (rc) return rc;
-  if (total_ms) *total_ms = ms8[CAT_GEMM] + ms8[CAT_FUSED_MLP] + ms8[CAT_FUSED_ATTN] + ms8[CAT_GEMM_DW] + ms8[CAT_GEMM_DX];
-  if (launches) *launches = n8[CAT_GEMM] + n8[CAT_FUSED_MLP] + n8[CAT_FUSED_ATTN] + n8[CAT_GEMM_DW] + n8[CAT_GEMM_DX];
-  if (flops) *flops = g_timing.flops;
-  return VITMARL_OK;
-}
-
-// Inference forward: 1 (default) fused block kernels, 0 the unfused v0 kernel sequence, 2 the legacy 1-CTA fused kernels.
-extern "C" int vitmarl_vit_set_fused(int mode) {
-  g_fused_mode = mode < 0 ? 0 : (mode > 2 ? 1 : mode);
-  return VITMARL_OK;
-}
-
-// Debug: device buffer (>= 512 int64) receiving clock64() phase stamps of the fused block kernels (CTA 0, 2nd tile):
-// [0,256) fused MLP, [256,512) fused attention block.
-extern "C" int vitmarl_debug_fused_mlp_timeline(long long* device_buf) {
-  fused_mlp_set_debug(device_buf);
-  fused_mlp2_set_debug(device_buf);
-  fused_attn_set_debug(device_buf ? device_buf + 256 : nullptr);
-  fused_attn2_set_debug(device_buf ? device_buf + 256 : nullptr);
-  return VITMARL_OK;
-}
-
-// Tuning switches of the fused kernels (debug / experiments).  Bits 0-7: fused_attn2 flags (default 4);
-// bit 8: launch the fused block kernels WITHOUT programmatic dependent launch.
-static bool g_pdl = true;
-namespace vitmarl { bool pdl_enabled() { return g_pdl; } }
-extern "C" int vitmarl_debug_set_flags(int flags) {
-  fused_attn2_set_flags(flags & 0xff);
-  g_pdl = (flags & 0x100) == 0;
+  if (flops) *flops = t->flops;
   return VITMARL_OK;
 }
 
 // Test hook: C[M,N] (fp32, accumulated into) += A^T . B and colsum[M] += column sums of A, A [K,M] / B [K,N] bf16 row-major
 // (the dW + bias-gradient launch of the backward pass).
-extern "C" int vitmarl_debug_gemm_dw(void* stream, int M, int N, int K, const void* A, const void* B, float* C, float* colsum) {
+extern "C" int vitmarl_debug_gemm_dw(void* stream, int M, int N, int K, const void* A, const void* B, float* C, float* colsum, int flags) {
   GemmDesc g;
   g.M = M; g.N = N; g.K = K;
   g.A = static_cast<const bf16*>(A); g.lda = M; g.a_mn_major = true;
   g.B = static_cast<const bf16*>(B); g.ldb = N; g.b_mn_major = true;
-  g.C = C; g.ldc = N; g.epi = EPI_ATOMIC_F32; g.colsum_a = colsum;
+  g.C = C; g.ldc = N; g.epi = EPI_ATOMIC_F32; g.colsum_a = colsum; g.allow_2cta = !(flags & VITMARL_GEMM_NO_2CTA);
   return launch_gemm(static_cast<cudaStream_t>(stream), g);
-}
-
-// Use the 2-CTA (cta_group::2) GEMM where it applies (1, default) or only the 1-CTA kernel (0).
-extern "C" int vitmarl_gemm_set_2cta(int enable) {
-  gemm_set_2cta(enable != 0);
-  return VITMARL_OK;
 }

@@ -29,6 +29,7 @@ struct GemmDesc {
   const __nv_bfloat16* pos_tile = nullptr;   // optional [128, N] bf16 copy of `pos` tiled to 128 rows (pos_period must divide 128):
                                              // lets the 2-CTA GEMM add it through its shared-memory-staged epilogue
   float out_scale = 1.0f;
+  bool allow_2cta = true;     // per-call switch (VitmarlVitOptions::gemm_2cta / vitmarl_gemm_bf16 flags): false = 1-CTA kernels only
   float* colsum_a = nullptr;   // MN-major A only (dW = A^T . B): also accumulate the column sums of A (the bias gradient), fp32 [M];
                                // fused into the weight-gradient kernel when it takes the product, a separate pass otherwise
 };
@@ -38,8 +39,6 @@ int launch_gemm(cudaStream_t stream, const GemmDesc& g);
 // 2-CTA (cta_group::2, M = 256 per CTA pair) variant for K-major operands; used by launch_gemm when supported
 bool gemm2_supported(const GemmDesc& g);
 int launch_gemm2(cudaStream_t stream, const GemmDesc& g);
-void gemm_set_2cta(bool on);
-bool gemm_2cta_enabled();
 // dW-shaped products (MN x MN, split-K, fp32 red.add) on CTA pairs with 256 x 384 work items; returns 1 when the shape is not handled
 int launch_gemm2_dw(cudaStream_t stream, const GemmDesc& g);
 
@@ -66,33 +65,24 @@ int launch_final_ln_pool(cudaStream_t s, const __nv_bfloat16* x, const float* ga
 int launch_final_ln_pool_bwd(cudaStream_t s, const __nv_bfloat16* x, const float* gamma, const float* stats, const float* dy,
                              __nv_bfloat16* dx, float* dgamma, float* dbeta, int B, int T, int D);
 
-// Fused MLP block (inference, D = 192): out = x + fc2(gelu(fc1(LN(x))));  `out` may alias `x`
-int launch_fused_mlp(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16* out, const float* gamma, const float* beta,
-                     const __nv_bfloat16* w1, const float* b1, const __nv_bfloat16* w2, const float* b2, int M, int D, int hidden, float eps);
-bool fused_mlp_supported(int D, int hidden);
-void fused_mlp_set_debug(long long* buf);   // device buffer of >= 256 int64 for clock64 phase stamps (null = off)
-
-// Fused attention block (inference, D = 192, 3 heads, 64 tokens): out = x + Wo.attn(LN(x)) + bo; `out` may alias `x`
-int launch_fused_attn(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16* out, const float* gamma, const float* beta,
-                      const __nv_bfloat16* wqkv, const float* bqkv, const __nv_bfloat16* wo, const float* bo, int M, int D, int heads, float eps);
-bool fused_attn_supported(int D, int heads, int tokens);
-void fused_attn_set_debug(long long* buf);
+// Per-launch switches of the fused block kernels (no process-global state: the C ABI passes them per call)
+struct FusedOpts {
+  bool pdl = true;            // programmatic dependent launch
+  int attn_flags = 4;         // FusedAttn2Params::flags
+  long long* dbg = nullptr;   // device buffer (>= 512 int64) for clock64 phase stamps: [0,256) MLP block, [256,512) attention block
+};
 
 // CTA-pair (cta_group::2) fused MLP block on FOLDED parameters (vit_fold.cu): w1f = W1.diag(gamma), b1p = bf16(b1 + W1.beta),
 // w2h = W2/2.  out = x + fc2(gelu(fc1(LN(x))));  `out` may alias `x`
 int launch_fused_mlp2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16* out, const __nv_bfloat16* w1f, const __nv_bfloat16* b1p,
-                      const __nv_bfloat16* w2h, const float* b2, int M, int D, int hidden, float eps);
+                      const __nv_bfloat16* w2h, const float* b2, int M, int D, int hidden, float eps, const FusedOpts& o);
 bool fused_mlp2_supported(int D, int hidden);
-void fused_mlp2_set_debug(long long* buf);
 
 // Second-generation fused attention block on FOLDED parameters (vit_fold.cu): wqkvf = Wqkv.diag(gamma) with the Q rows scaled
 // by log2(e)/8, bqp = bf16 folded Q bias, bof = bo + Wo.(bv + Wv.beta).  `out` may alias `x`
 int launch_fused_attn2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16* out, const __nv_bfloat16* wqkvf, const __nv_bfloat16* bqp,
-                       const __nv_bfloat16* wo, const float* bof, int M, int D, int heads, float eps);
+                       const __nv_bfloat16* wo, const float* bof, int M, int D, int heads, float eps, const FusedOpts& o);
 bool fused_attn2_supported(int D, int heads, int tokens);
-void fused_attn2_set_debug(long long* buf);
-void fused_attn2_set_flags(int flags);
-bool pdl_enabled();                  // programmatic dependent launch of the fused block kernels (default on)
 
 // parameter folding: Wf = scale * W . diag(gamma) (bf16 [N,K]), bias_out = bias + W . beta (fp32 or bf16 [N]); null = identity
 struct FoldJob {

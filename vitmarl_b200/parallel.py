@@ -5,9 +5,9 @@ The reference is data-parallel only: environments are sharded over devices
 collective is ``jax.lax.pmean`` of the loss and the gradient pytree once per minibatch
 (``:564-565``).  Here: ``shard_envs`` gives the contiguous env range of a rank (no data-path
 collective on the rollout-and-encode path), ``GradAllReducer`` is the pmean of the packed fp32
-gradient table: the gradients are produced directly into ONE flat buffer (views per tensor), so the
-psum is a single ncclAllReduce launch per minibatch on a side stream, overlappable with the next
-backward's first kernels."""
+gradient table: the gradients are produced directly into ONE flat buffer (views per tensor) cut into per-block
+buckets; each bucket's ncclAllReduce(avg) is enqueued on a side stream behind the CUDA event the backward pass
+records when that block's gradients are final, so the reduction of block l overlaps the backward of blocks l-1..0."""
 from __future__ import annotations
 
 from typing import List, Sequence, Tuple
@@ -41,36 +41,109 @@ def flat_views(shapes: Sequence[torch.Size], dtype=torch.float32, device="cuda")
 
 
 class GradAllReducer:
-    """pmean of a gradient table (``jax.lax.pmean(grads, 'device_batch')``, pmap trainer :565)."""
+    """pmean of a gradient table (``jax.lax.pmean(grads, 'device_batch')``, pmap trainer :565), bucketed and overlapped.
 
-    def __init__(self, shapes: Sequence[torch.Size], device="cuda", group=None):
+    * The gradients are produced directly into ONE flat fp32 buffer (per-tensor views, 16-byte aligned segments): no
+      gather / scatter copies, one memset per backward pass.
+    * ``bucket_ranges`` (index ranges into the table, in the order the backward pass completes them --
+      ``ViTEncoder.bucket_param_ranges()``) cut the flat buffer into per-block buckets.  ``ViTEncoder.vjp_packed(...,
+      bucket_events=red.events)`` records an event per bucket on the compute stream; :meth:`allreduce_mean` enqueues one
+      ``ncclAllReduce`` per bucket on a side stream behind its event, so block l's reduction runs over NVLink while
+      blocks l-1 .. 0 are still in their backward pass.
+    * The mean is folded into the collective (``ReduceOp.AVG`` on NCCL): no separate scaling pass.
+    * DOUBLE BUFFERED: :meth:`swap` flips to the second flat buffer, so the next minibatch's backward may start writing
+      while the previous buffer is still being reduced / consumed by the optimiser (without it the next backward's memset
+      would race with the in-flight all-reduce).  ``wait()`` makes the compute stream wait for the reduction of the buffer
+      it was started on and returns that buffer's views."""
+
+    def __init__(self, shapes: Sequence[torch.Size], device="cuda", group=None, bucket_ranges=None, double_buffer: bool = True):
         self.group = group
-        self.flat, self.views = flat_views(shapes, torch.float32, device)
+        dev = torch.device(device)
+        self.cuda = dev.type == "cuda"
+        nbuf = 2 if double_buffer else 1
+        self._flat, self._views = [], []
+        for _ in range(nbuf):
+            f, v = flat_views(shapes, torch.float32, device)
+            self._flat.append(f); self._views.append(v)
+        self._cur = 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.stream = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
-        self._work = None
+        self.stream = torch.cuda.Stream(device=device) if self.cuda else None
+        # element offsets of every tensor in the flat buffer
+        offs, total = [], 0
+        for s in shapes:
+            offs.append(total)
+            total += (int(torch.Size(s).numel()) + 3) // 4 * 4
+        offs.append(total)
+        self._offs = offs
+        if bucket_ranges is None:
+            bucket_ranges = [(0, len(shapes))]
+        self.bucket_ranges = [(int(a), int(b)) for a, b in bucket_ranges]
+        self.bucket_spans = [(offs[a], offs[b]) for a, b in self.bucket_ranges]      # element spans in the flat buffer
+        self.events = None
+        if self.cuda:
+            self.events = [torch.cuda.Event() for _ in self.bucket_ranges]
+            for e in self.events:
+                e.record()                       # materialises the cudaEvent_t (torch creates it lazily)
+        self._work = []
+        self._pending = None
+        # NCCL reduces with ncclAvg; gloo (CPU tests) has no AVG -> sum, then scale
+        self._avg = self.cuda and dist.is_initialized() and dist.get_backend(group) == "nccl"
+
+    # ---- buffers -------------------------------------------------------------------------------------------------
+    @property
+    def flat(self) -> torch.Tensor:
+        return self._flat[self._cur]
+
+    @property
+    def views(self) -> List[torch.Tensor]:
+        return self._views[self._cur]
 
     def grads(self) -> List[torch.Tensor]:
-        """Views to hand to ``ViTEncoder.vjp_packed(..., grads=...)`` so the backward writes in place."""
-        return self.views
+        """Views to hand to ``ViTEncoder.vjp_packed(..., grads=red.grads(), flat=red.flat, bucket_events=red.events)``."""
+        return self._views[self._cur]
 
-    def allreduce_mean(self, async_op: bool = False):
+    def swap(self):
+        """Flip to the other flat buffer (double buffering): the next backward writes there."""
+        self._cur = (self._cur + 1) % len(self._flat)
+
+    # ---- the collective ------------------------------------------------------------------------------------------
+    def allreduce_mean(self, async_op: bool = False, use_events: bool = True):
+        """Enqueue the per-bucket all-reduces of the CURRENT buffer.  With ``use_events`` (and a preceding
+        ``vjp_packed(..., bucket_events=self.events)``) bucket b starts as soon as its event has fired; otherwise the side
+        stream waits for everything enqueued so far on the compute stream."""
         if self.world == 1:
             return None
+        flat = self._flat[self._cur]
+        self._pending = self._cur
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
         if self.stream is not None:
-            self.stream.wait_stream(torch.cuda.current_stream())
+            if not use_events:
+                self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
-                self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                for b, (lo, hi) in enumerate(self.bucket_spans):
+                    if hi <= lo:
+                        continue
+                    if use_events:
+                        self.stream.wait_event(self.events[b])
+                    self._work.append(dist.all_reduce(flat[lo:hi], op=op, group=self.group, async_op=True))
         else:
-            self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            for lo, hi in self.bucket_spans:
+                if hi > lo:
+                    self._work.append(dist.all_reduce(flat[lo:hi], op=op, group=self.group, async_op=True))
         if not async_op:
-            self.wait()
+            return self.wait()
         return self._work
 
-    def wait(self):
-        if self._work is not None:
-            self._work.wait()
-            self._work = None
+    def wait(self) -> List[torch.Tensor]:
+        """Order the compute stream after the in-flight reduction; returns the reduced buffer's views."""
+        idx = self._cur if self._pending is None else self._pending
+        if self._work:
+            for w in self._work:
+                w.wait()
+            self._work = []
             if self.stream is not None:
                 torch.cuda.current_stream().wait_stream(self.stream)
-            self.flat.mul_(1.0 / self.world)
+            if not self._avg:
+                self._flat[idx].mul_(1.0 / self.world)
+        self._pending = None
+        return self._views[idx]

@@ -38,9 +38,12 @@ class RolloutEncoder:
         self.device = torch.device(device)
         self.encoder = vvit.ViTEncoder(vit_cfg)
         self.packed = vvit.pack_params(vit_cfg, params)
+        self.params_version = 0          # generation counter of `packed`'s contents (bumped by update_params)
+        self._bufs = venv.StepBuffers()   # step outputs allocated once, rewritten in place every step
         self.state = None
         self.last = None
         # staging for the host-buffer path
+        self._feat = None
         self._msgs_dev = torch.empty((E, M, 8), dtype=torch.int32, device=self.device)
         self._feat_host = torch.empty((E, vit_cfg.dim), dtype=torch.float32).pin_memory() if torch.cuda.is_available() else None
         self._obs_host = torch.empty((E, n_levels, 3, 2), dtype=torch.float32).pin_memory() if torch.cuda.is_available() else None
@@ -49,14 +52,28 @@ class RolloutEncoder:
         self.state = venv.reset(self.cfg, asks, bids, self.M)
         return self.state
 
-    def step(self, msgs: torch.Tensor) -> torch.Tensor:
+    def update_params(self, params=None, packed=None):
+        """After an optimiser step: hand in the new pytree (re-packed here) or an already packed table whose contents
+        changed in place; the next step folds the parameters again."""
+        if params is not None:
+            self.packed = vvit.pack_params(self.vit_cfg, params)
+        elif packed is not None:
+            self.packed = packed
+        self.params_version += 1
+
+    def step(self, msgs: torch.Tensor, stat_agent_ids=None, keep_trades: bool = True) -> torch.Tensor:
+        """Two library calls, 1 + 1 + 2L + 1 kernel launches, no allocation and no torch kernel: the env-step outputs live in
+        buffers that are rewritten in place (``self.last`` is valid until the next step)."""
         c = self.vit_cfg
         # the order-book kernel renders the raster directly as the encoder's patch matrix (no patchify pass in between)
         self.state, out = venv.step(self.cfg, self.state, msgs, n_levels=self.n_levels, want_obs=True,
-                                    image_hw=(c.img_h, c.img_w), image_dtype=torch.bfloat16, inplace=True, image_patch=c.patch)
+                                    image_hw=(c.img_h, c.img_w), image_dtype=torch.bfloat16, inplace=True, image_patch=c.patch,
+                                    stat_agent_ids=stat_agent_ids, keep_trades=keep_trades, buffers=self._bufs)
         self.last = out
-        # the parameters are fixed for the lifetime of this engine (a new one is built after an optimiser update)
-        return self.encoder.apply_packed(self.packed, out.image, params_unchanged=True, patches=True)
+        if self._feat is None:
+            self._feat = torch.empty((self.E, c.dim), dtype=torch.float32, device=self.device)
+        # folded parameters are reused until update_params() bumps the version
+        return self.encoder.apply_packed(self.packed, out.image, params_version=self.params_version, patches=True, out=self._feat)
 
     def last_image(self) -> torch.Tensor:
         """The last step's raster as the reference-shaped [E,H,W,2] image (a view-permutation of the patch matrix)."""

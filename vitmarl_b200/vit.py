@@ -125,11 +125,13 @@ class ViTEncoder:
 
     def __init__(self, cfg: ViTConfig = VIT_TINY_8):
         self.cfg = cfg
-        self._packed_src = None
-        self._packed = None
+        self._packed = None              # table packed by the last apply() (what vjp() differentiates)
         self._ws = None
         self._ws_shape = None
-        self._fold_key = None
+        self._fold_key = None            # (workspace, batch, caller's params_version) of the folded parameters left in the workspace
+        # per-call switches handed to the library with every launch (the library keeps no global state): set e.g.
+        # ``enc.options.fused = 0`` for the unfused kernel sequence or ``enc.options.timing = timing.handle``
+        self.options = _capi.VitOptions.defaults()
 
     # ---- flax-like surface -------------------------------------------------------------------------
     def init(self, seed: int = 0, x: Optional[torch.Tensor] = None, device="cuda") -> Dict:
@@ -137,15 +139,11 @@ class ViTEncoder:
 
     def apply(self, variables: Dict, x: torch.Tensor, *, train: bool = False) -> torch.Tensor:
         """x: [B,H,W,C] (bf16, or any dtype castable to it).  train=True keeps the activations
-        needed by :meth:`vjp` in the workspace."""
-        packed = self._get_packed(variables["params"])
-        return self.apply_packed(packed, x, train=train)
-
-    # ---- packed fast path (what the rollout / bench use: no per-call re-packing) -----------------------
-    def _get_packed(self, params: Dict):
-        if self._packed_src is not params:
-            self._packed, self._packed_src = pack_params(self.cfg, params), params
-        return self._packed
+        needed by :meth:`vjp` in the workspace.  The fp32 pytree is re-packed (cast to the bf16 / fp32 table of the C ABI)
+        on EVERY call: an optimiser that updates the master tensors in place keeps the same dict object, so caching on
+        identity would serve stale weights.  Loops that know when their parameters change use :meth:`apply_packed`."""
+        self._packed = pack_params(self.cfg, variables["params"])
+        return self.apply_packed(self._packed, x, train=train)
 
     def _shape(self, B: int) -> _capi.VitShape:
         c = self.cfg
@@ -160,19 +158,20 @@ class ViTEncoder:
         return self._ws
 
     def apply_packed(self, packed, x: torch.Tensor, *, train: bool = False, out: Optional[torch.Tensor] = None,
-                     params_unchanged: bool = False, patches: bool = False) -> torch.Tensor:
-        """``patches=True`` (inference only): ``x`` is already the patch matrix ``[B, T, P*P*C]`` bf16 (the fused env step
+                     params_version: Optional[int] = None, patches: bool = False) -> torch.Tensor:
+        """``patches=True``: ``x`` is already the patch matrix ``[B, T, P*P*C]`` bf16 (the fused env step
         renders it that way, ``env.step(..., image_patch=P)``) and the patchify pass is skipped.
-        ``params_unchanged=True`` (inference only) tells the library that the CONTENTS of ``packed`` are the same as in the
-        previous call, so the folded parameters it left in the workspace are reused (the rollout loop between two optimiser
-        updates).  It is honoured only when that previous call used the same workspace, batch size and table."""
+        ``params_version`` (inference only) is a caller-owned generation counter of the CONTENTS of ``packed`` (bump it after
+        every optimiser step / in-place update).  When it equals the version of the previous call -- and that call used the
+        same workspace and batch size -- the folded parameters left in the workspace are reused (the rollout loop between
+        two optimiser updates); ``None`` (default) always folds again.  Nothing is keyed on Python object identity."""
         if not x.is_cuda:
             raise _capi.VitmarlError(_capi.ENODEVICE, "ViT input must be a CUDA tensor (there is no CPU fallback)")
         c = self.cfg
         if patches:
             want = (c.tokens, c.patch * c.patch * c.channels)
-            if train or x.dim() != 3 or tuple(x.shape[1:]) != want or x.dtype != torch.bfloat16:
-                raise _capi.VitmarlError(_capi.EINVAL, f"patches=True is for inference on a bf16 patch matrix [B,{want[0]},{want[1]}], got {tuple(x.shape)}")
+            if x.dim() != 3 or tuple(x.shape[1:]) != want or x.dtype != torch.bfloat16:
+                raise _capi.VitmarlError(_capi.EINVAL, f"patches=True takes a bf16 patch matrix [B,{want[0]},{want[1]}], got {tuple(x.shape)}")
         elif x.dim() != 4 or tuple(x.shape[1:]) != (c.img_h, c.img_w, c.channels):
             raise _capi.VitmarlError(_capi.EINVAL, f"expected x [B,{c.img_h},{c.img_w},{c.channels}], got {tuple(x.shape)}")
         x = x.to(torch.bfloat16).contiguous()
@@ -181,26 +180,42 @@ class ViTEncoder:
         ws = self._workspace(shape, train, x.device)
         y = out if out is not None else torch.empty((B, c.dim), dtype=torch.float32, device=x.device)
         ptrs = (ctypes.c_void_p * len(packed))(*[t.data_ptr() for t in packed])
-        key = (ws.data_ptr(), B, id(packed))
-        mode = 1 if train else (2 if (params_unchanged and self._fold_key == key) else 0)
+        key = (ws.data_ptr(), B, params_version)
+        mode = 1 if train else (2 if (params_version is not None and self._fold_key == key) else 0)
         if patches:
             mode |= _capi.VIT_INPUT_PATCHES
-        rc = _capi.lib().vitmarl_vit_fwd(torch.cuda.current_stream().cuda_stream, ctypes.byref(shape), ptrs, x.data_ptr(),
-                                         y.data_ptr(), ws.data_ptr(), ws.numel(), mode)
+        rc = _capi.lib().vitmarl_vit_fwd_ex(torch.cuda.current_stream().cuda_stream, ctypes.byref(shape), ptrs, x.data_ptr(),
+                                            y.data_ptr(), ws.data_ptr(), ws.numel(), mode, ctypes.byref(self.options))
         _capi.check(rc)
-        self._fold_key = None if train else key          # a training pass lays the workspace out differently
+        self._fold_key = None if (train or params_version is None) else key   # a training pass lays the workspace out differently
         self._ws_shape = (B, train)
         return y
 
     def vjp(self, variables: Dict, dy: torch.Tensor, *, want_dx: bool = False):
         """Gradients w.r.t. the flax pytree (and optionally the input) for the last
         ``apply(..., train=True)`` call: the pullback of ``jax.vjp(module.apply, ...)``."""
-        packed = self._get_packed(variables["params"])
-        grads, dx = self.vjp_packed(packed, dy, want_dx=want_dx)
+        if self._packed is None:
+            raise _capi.VitmarlError(_capi.EINVAL, "vjp needs a preceding apply(..., train=True)")
+        grads, dx = self.vjp_packed(self._packed, dy, want_dx=want_dx)      # the table the forward pass ran on
         g = unpack_grads(self.cfg, grads)
         return (g, dx) if want_dx else g
 
-    def vjp_packed(self, packed, dy: torch.Tensor, *, want_dx: bool = False, grads=None):
+    def num_buckets(self) -> int:
+        """Gradient buckets of the backward pass (depth + 2), in completion order: encoder_norm, block L-1 .. block 0,
+        patch_embed + pos_embed."""
+        return self.cfg.depth + 2
+
+    def bucket_param_ranges(self):
+        """[(first, last+1)] index ranges into the packed table for each bucket of :meth:`num_buckets`."""
+        L = self.cfg.depth
+        return [(3 + 12 * L, 5 + 12 * L)] + [(3 + 12 * l, 15 + 12 * l) for l in range(L - 1, -1, -1)] + [(0, 3)]
+
+    def vjp_packed(self, packed, dy: torch.Tensor, *, want_dx: bool = False, grads=None, flat: Optional[torch.Tensor] = None,
+                   bucket_events=None, accumulate: bool = False):
+        """``grads``: fp32 tensors to write into (default: fresh ones).  ``flat``: the ONE buffer those tensors are views of
+        (zeroed with a single memset).  ``bucket_events``: ``torch.cuda.Event`` per bucket (:meth:`num_buckets`), recorded on the
+        current stream as soon as that bucket's gradients are final -- ``parallel.GradAllReducer`` hangs the per-bucket
+        all-reduce behind them.  ``accumulate=True`` adds this call's gradients to the contents of ``grads`` (micro-batches)."""
         if self._ws_shape is None or not self._ws_shape[1]:
             raise _capi.VitmarlError(_capi.EINVAL, "vjp needs a preceding apply(..., train=True)")
         B = self._ws_shape[0]
@@ -212,7 +227,18 @@ class ViTEncoder:
         dx = torch.empty((B, c.img_h, c.img_w, c.channels), dtype=torch.bfloat16, device=dy.device) if want_dx else None
         ptrs = (ctypes.c_void_p * len(packed))(*[t.data_ptr() for t in packed])
         gptrs = (ctypes.c_void_p * len(grads))(*[t.data_ptr() for t in grads])
-        rc = _capi.lib().vitmarl_vit_bwd(torch.cuda.current_stream().cuda_stream, ctypes.byref(shape), ptrs, self._ws.data_ptr(),
-                                         self._ws.numel(), dy.data_ptr(), gptrs, dx.data_ptr() if want_dx else None)
+        opt = _capi.VitOptions.defaults(fused=self.options.fused, gemm_2cta=self.options.gemm_2cta, pdl=self.options.pdl,
+                                        attn_flags=self.options.attn_flags, timing=self.options.timing)
+        opt.accumulate = 1 if accumulate else 0
+        if flat is not None:
+            opt.grads_flat, opt.grads_flat_bytes = flat.data_ptr(), flat.numel() * flat.element_size()
+        evs = None
+        if bucket_events is not None:
+            if len(bucket_events) != self.num_buckets():
+                raise _capi.VitmarlError(_capi.EINVAL, f"bucket_events: need {self.num_buckets()} events")
+            evs = (ctypes.c_void_p * len(bucket_events))(*[e.cuda_event for e in bucket_events])
+            opt.bucket_events = ctypes.cast(evs, ctypes.c_void_p)
+        rc = _capi.lib().vitmarl_vit_bwd_ex(torch.cuda.current_stream().cuda_stream, ctypes.byref(shape), ptrs, self._ws.data_ptr(),
+                                            self._ws.numel(), dy.data_ptr(), gptrs, dx.data_ptr() if want_dx else None, ctypes.byref(opt))
         _capi.check(rc)
         return grads, dx
