@@ -310,44 +310,48 @@ def extra_allreduce(dist, world: int):
 
 def extra_train_step_dp(dist, world: int, B: int = 8192):
     """Data-parallel ViT-Tiny/8 training step at the configs[4] minibatch shape: forward + backward over B images per GPU with the
-    bucketed gradient pmean hung behind the backward's events, against the same step without any collective -> the EXPOSED
-    collective time per minibatch (max over ranks)."""
+    gradient pmean hung behind the backward's events, against the same step without any collective -> the EXPOSED collective time
+    per minibatch (max over ranks), for three bucket policies: one all-reduce after the last block, two groups, one per block."""
     import torch
     from vitmarl_b200 import parallel, vit
     cfg = vit.VIT_TINY_8
     enc = vit.ViTEncoder(cfg)
     packed = vit.pack_params(cfg, vit.init_params(cfg, 0, "cuda"))
-    red = parallel.GradAllReducer([t.shape for t in packed], device="cuda", bucket_ranges=enc.bucket_param_ranges())
     g = torch.Generator(device="cpu").manual_seed(dist.get_rank())
     x = (torch.rand(B, cfg.tokens, cfg.patch_dim, generator=g) < 0.3).to(torch.bfloat16).cuda()
     dy = torch.randn(B, cfg.dim, generator=g).cuda()
+    res = {"images_per_gpu": B}
+    base = None
+    for name, groups in (("no_collective", None), ("pmean_1_group", 1), ("pmean_2_groups", 2), ("pmean_per_block_14", 0)):
+        red = parallel.GradAllReducer([t.shape for t in packed], device="cuda", bucket_ranges=enc.bucket_param_ranges(),
+                                      n_groups=groups if groups is not None else 1)
 
-    def step(collective: bool):
-        enc.apply_packed(packed, x, train=True, patches=True)
-        enc.vjp_packed(packed, dy, grads=red.grads(), flat=red.flat, bucket_events=red.events if collective else None)
-        if collective:
-            red.allreduce_mean(async_op=True)
-            red.swap()
-            red.wait()
-
-    res = {}
-    for name, coll in (("no_collective", False), ("with_pmean", True)):
+        def step():
+            enc.apply_packed(packed, x, train=True, patches=True)
+            enc.vjp_packed(packed, dy, grads=red.grads(), flat=red.flat, bucket_events=red.events if groups is not None else None)
+            if groups is not None:
+                red.allreduce_mean(async_op=True)
+                red.swap()
+                red.wait()
         for _ in range(3):
-            step(coll)
+            step()
         dist.barrier(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n = 5
         e0.record()
         for _ in range(n):
-            step(coll)
+            step()
         e1.record()
         dist.barrier(); torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / n], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         res[name + "_ms"] = float(t)
-    res["exposed_collective_us_per_minibatch_step"] = (res["with_pmean_ms"] - res["no_collective_ms"]) * 1e3
-    res["images_per_gpu"] = B
-    del enc, x, red
+        if groups is None:
+            base = float(t)
+        else:
+            res[name + "_exposed_us"] = (float(t) - base) * 1e3
+        del red
+    del enc, x
     torch.cuda.empty_cache()
     return res
 

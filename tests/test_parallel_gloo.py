@@ -21,6 +21,30 @@ def test_shard_envs_partitions_exactly():
         parallel.shard_envs(8, 2, 2)
 
 
+def test_bucket_coalescing():
+    """14 per-block buckets of a ViT-Tiny table coalesced into 1 / 2 / 14 collectives: spans stay contiguous, cover the table
+    once, and every group waits on the event of its last bucket."""
+    from vitmarl_b200 import vit
+    cfg = vit.VIT_TINY_8
+    shapes = [torch.Size(s) for s in _tiny_shapes(cfg)]
+    ranges = vit.ViTEncoder(cfg).bucket_param_ranges()
+    for n, want in ((0, 14), (14, 14), (1, 1), (2, 2), (3, 3)):
+        red = parallel.GradAllReducer(shapes, device="cpu", bucket_ranges=ranges, n_groups=n, double_buffer=False)
+        assert len(red.groups) == want
+        assert sum(hi - lo for lo, hi, _ in red.groups) == red.flat.numel()
+        assert red.groups[-1][2] == 13 and [g[2] for g in red.groups] == sorted(g[2] for g in red.groups)
+    two = parallel.GradAllReducer(shapes, device="cpu", bucket_ranges=ranges, n_groups=2, double_buffer=False).groups
+    assert two[0][1] == red.flat.numel() and two[1][0] == 0 and two[0][0] == two[1][1]      # [tail of the table], then [head]
+
+
+def _tiny_shapes(cfg):
+    D, K, T, H = cfg.dim, cfg.patch_dim, cfg.tokens, cfg.mlp_dim
+    out = [(D, K), (D,), (T, D)]
+    for _ in range(cfg.depth):
+        out += [(D,), (D,), (3 * D, D), (3 * D,), (D, D), (D,), (D,), (D,), (H, D), (H,), (D, H), (D,)]
+    return out + [(D,), (D,)]
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)

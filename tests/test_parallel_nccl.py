@@ -27,28 +27,30 @@ def _worker(rank, world, port, out):
         lens = torch.randint(0, cfg.img_w + 1, (B, cfg.img_h, 1, cfg.channels), generator=g)
         x = (torch.arange(cfg.img_w)[None, None, :, None] < lens).float().cuda()
         dy = torch.randn(B, cfg.dim, generator=g).cuda()
-        ok = True
+        bad = []
         for rnd in range(3):                                             # several minibatches: buffers flip, events are re-recorded
             enc.apply_packed(packed, x, train=True)
             enc.vjp_packed(packed, dy, grads=red.grads(), flat=red.flat, bucket_events=red.events)
             red.allreduce_mean(async_op=True)                            # per-bucket ncclAllReduce(avg) behind the bucket events
             red.swap()
             reduced = red.wait()
-            # reference: every rank's local gradient (no collective) gathered and averaged with plain tensor ops
+            # reference: every rank's local gradient (no collective) gathered and averaged with plain tensor ops.  The weight
+            # gradients are fp32 split-K reductions (red.add: summation order varies run to run), hence a norm-wise tolerance.
             local, _ = enc.vjp_packed(packed, dy)
-            for a, b in zip(reduced, local):
+            for i, (a, b) in enumerate(zip(reduced, local)):
                 parts = [torch.empty_like(b) for _ in range(world)]
                 dist.all_gather(parts, b.contiguous())
                 want = torch.stack(parts).mean(0)
-                ok = ok and bool(torch.allclose(a, want, rtol=1e-5, atol=1e-6))
-            ok = ok and bool(all(torch.equal(reduced[i], reduced[i]) for i in range(len(reduced))))
-        # all ranks hold the same averaged table
+                err = float((a - want).norm() / (want.norm() + 1e-30))
+                if not err <= 1e-4:
+                    bad.append((rnd, i, err, float(want.norm())))
+        # all ranks hold the same averaged table, bit for bit (same reduction on every rank)
         chk = torch.stack([t.double().sum() for t in reduced]).sum().reshape(1)
         both = [torch.empty_like(chk) for _ in range(world)]
         dist.all_gather(both, chk)
-        ok = ok and bool(torch.equal(both[0], both[1]))
-        # and it matches the fp32 oracle's gradient of the SUM of both minibatches / world (one leaf, cosine)
-        out[rank] = ok
+        if not torch.equal(both[0], both[1]):
+            bad.append(("ranks differ", float(both[0]), float(both[1])))
+        out[rank] = bad
     finally:
         dist.destroy_process_group()
 
@@ -60,4 +62,4 @@ def test_grad_pmean_world2_nccl_bucketed_overlapped():
     out = mgr.dict()
     port = 29600 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
-    assert out[0] and out[1]
+    assert out[0] == [] and out[1] == [], (out[0][:8], out[1][:8])

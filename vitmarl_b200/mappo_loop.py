@@ -7,9 +7,10 @@
     update  : ``epochs`` passes over the S*E stored observations in ``minibatches`` minibatches
               (ippo_rnn_JAXMARL.py:470-475: value_and_grad per minibatch).  A minibatch = ViT forward+backward over its images
               in micro-batches whose gradients ACCUMULATE in the flat fp32 table inside the library (no eager add/copy
-              kernels), then the pmean of that table (ippo_rnn_JAXMARL_pmap.py:564-565) as per-block NCCL all-reduce(avg)
-              buckets on a side stream, each hung behind the CUDA event the last micro-batch's backward records when that
-              block's gradients are final.  The flat table is double buffered, so the next minibatch starts at once.
+              kernels), then the pmean of that table (ippo_rnn_JAXMARL_pmap.py:564-565) as NCCL all-reduce(avg) on a side
+              stream, hung behind the CUDA events the last micro-batch's backward records (``pmean_groups``: 1 = one
+              collective when the last block's gradients are final -- measured best on NVLink for this 21.5 MB table, see
+              bench.py extra / DESIGN.md; 0 = one per transformer block, overlapping the rest of the backward pass).
 
 The policy head, PPO loss and optimiser are boundary-only rows of SURVEY.md 8a (A13-A14): dL/d(encoding) is synthetic and the
 parameters are not changed, but every encoder FLOP, every byte and every collective of the iteration is there."""
@@ -26,7 +27,7 @@ __all__ = ["MappoLoop"]
 class MappoLoop:
     def __init__(self, envs_per_gpu: int = 8192, rollout_steps: int = 128, epochs: int = 4, minibatches: int = 16, micro: int = 8192,
                  msgs_per_step: int = 13, vit_cfg: vit.ViTConfig = vit.VIT_TINY_8, rank: int = 0, world: int = 1,
-                 agent_ids=(-100, -101)):
+                 agent_ids=(-100, -101), pmean_groups: int = 1):
         self.E, self.S, self.M = envs_per_gpu, rollout_steps, msgs_per_step
         self.epochs, self.minibatches = epochs, minibatches
         self.world, self.rank = world, rank
@@ -43,7 +44,8 @@ class MappoLoop:
         self.eng = rollout.RolloutEncoder(self.cfg, c, params, E, M)
         self.enc = vit.ViTEncoder(c)                                                    # training path (own workspace)
         self.packed = vit.pack_params(c, params)
-        self.red = parallel.GradAllReducer([t.shape for t in self.packed], device="cuda", bucket_ranges=self.enc.bucket_param_ranges())
+        self.red = parallel.GradAllReducer([t.shape for t in self.packed], device="cuda", bucket_ranges=self.enc.bucket_param_ranges(),
+                                           n_groups=pmean_groups)
         self.traj = torch.empty((S, E, c.tokens, c.patch_dim), dtype=torch.bfloat16, device="cuda")    # patch matrices, as rendered
         self.feats = torch.empty((S, E, c.dim), dtype=torch.float32, device="cuda")
         self.stats = torch.empty((S, E, len(self.agent_ids), 8), dtype=torch.int32, device="cuda")

@@ -56,7 +56,8 @@ class GradAllReducer:
       would race with the in-flight all-reduce).  ``wait()`` makes the compute stream wait for the reduction of the buffer
       it was started on and returns that buffer's views."""
 
-    def __init__(self, shapes: Sequence[torch.Size], device="cuda", group=None, bucket_ranges=None, double_buffer: bool = True):
+    def __init__(self, shapes: Sequence[torch.Size], device="cuda", group=None, bucket_ranges=None, double_buffer: bool = True,
+                 n_groups: int = 0):
         self.group = group
         dev = torch.device(device)
         self.cuda = dev.type == "cuda"
@@ -79,6 +80,11 @@ class GradAllReducer:
             bucket_ranges = [(0, len(shapes))]
         self.bucket_ranges = [(int(a), int(b)) for a, b in bucket_ranges]
         self.bucket_spans = [(offs[a], offs[b]) for a, b in self.bucket_ranges]      # element spans in the flat buffer
+        # Collectives actually issued: consecutive buckets (in completion order) coalesced into `n_groups` all-reduces of roughly
+        # equal size, each hung behind the event of its LAST bucket (0 = one all-reduce per bucket).  Measured on B200/NVLink
+        # (bench.py extra, profiles/): the 21.5 MB ViT-Tiny table reduces in ~70 us, while every collective that overlaps the
+        # backward costs the persistent compute kernels a straggler wave -- so few, large groups beat per-block buckets here.
+        self.groups = self._coalesce(n_groups)
         self.events = None
         if self.cuda:
             self.events = [torch.cuda.Event() for _ in self.bucket_ranges]
@@ -88,6 +94,26 @@ class GradAllReducer:
         self._pending = None
         # NCCL reduces with ncclAvg; gloo (CPU tests) has no AVG -> sum, then scale
         self._avg = self.cuda and dist.is_initialized() and dist.get_backend(group) == "nccl"
+
+    def _coalesce(self, n_groups: int):
+        spans = self.bucket_spans
+        if n_groups <= 0 or n_groups >= len(spans):
+            return [(lo, hi, b) for b, (lo, hi) in enumerate(spans)]
+        total = sum(hi - lo for lo, hi in spans)
+        groups, lo_g, hi_g, acc, made = [], None, None, 0, 0
+        for b, (lo, hi) in enumerate(spans):
+            lo_g = lo if lo_g is None else min(lo_g, lo)
+            hi_g = hi if hi_g is None else max(hi_g, hi)
+            acc += hi - lo
+            last = b == len(spans) - 1
+            if last or (made < n_groups - 1 and acc >= total * (made + 1) / n_groups):
+                groups.append((lo_g, hi_g, b))
+                lo_g = hi_g = None
+                made += 1
+        covered = sum(hi - lo for lo, hi, _ in groups)
+        if covered != total:          # buckets of a group must be contiguous in the flat buffer (they are, in table order)
+            raise ValueError("bucket_ranges are not contiguous in completion order; cannot coalesce")
+        return groups
 
     # ---- buffers -------------------------------------------------------------------------------------------------
     @property
@@ -120,14 +146,14 @@ class GradAllReducer:
             if not use_events:
                 self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
-                for b, (lo, hi) in enumerate(self.bucket_spans):
+                for lo, hi, b in self.groups:
                     if hi <= lo:
                         continue
                     if use_events:
                         self.stream.wait_event(self.events[b])
                     self._work.append(dist.all_reduce(flat[lo:hi], op=op, group=self.group, async_op=True))
         else:
-            for lo, hi in self.bucket_spans:
+            for lo, hi, _ in self.groups:
                 if hi > lo:
                     self._work.append(dist.all_reduce(flat[lo:hi], op=op, group=self.group, async_op=True))
         if not async_op:
