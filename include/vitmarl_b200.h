@@ -307,6 +307,22 @@ void vitmarl_timing_destroy(void* timing);
 int vitmarl_timing_reset(void* timing);
 int vitmarl_timing_read(void* timing, double* ms8, long long* n8, double* flops);
 
+/* ---- policy head behind the encoder ------------------------------------------------ */
+
+/* The Dense / GRU pieces of ActorCriticRNN.__call__(hidden, (obs, dones)) (jaxrl/MARL/ippo_rnn_JAXMARL.py:48-115), fp32:
+ *   y[R,N] = act( [x0 | x1] . W + bias ),  x0 [R,K0] (row pitch ldx0), x1 [R,K1] or NULL (K1 = 0), W [K0+K1, N] in the flax Dense
+ *   kernel layout [in, out], bias [N] or NULL.  The two-source form is the first Dense on concat(vector observation, ViT encoding). */
+#define VITMARL_ACT_NONE 0
+#define VITMARL_ACT_RELU 1
+int vitmarl_dense_f32(void* stream, int R, int K0, int K1, int N, const float* x0, int ldx0, const float* x1, int ldx1,
+                      const float* W, const float* bias, int act, float* y, int ldy);
+/* flax.linen.GRUCell step with the ScannedRNN reset (ippo_rnn_JAXMARL.py:48-66): rows with reset[r] != 0 start from a zero carry.
+ *   gi [R,3H] = x . [W_ir | W_iz | W_in] + [b_ir | b_iz | b_in],  gh [R,3H] = h . [W_hr | W_hz | W_hn] (no bias),  b_hn [H],
+ *   r = sigmoid(gi_r + gh_r), z = sigmoid(gi_z + gh_z), n = tanh(gi_n + r * (gh_n + b_hn)), h_out = (1 - z) n + z h.
+ * reset: uint8 [R] or NULL; h_out may alias h. */
+int vitmarl_gru_cell_f32(void* stream, int R, int H, const float* gi, const float* gh, const float* b_hn, const float* h,
+                         const uint8_t* reset, float* h_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,3 +35,21 @@ def test_stream_format_mixture_and_determinism():
     assert (np.diff(np.sort(lim[:, 4])) >= 0).all() and (lim[:, 4] == lim[:, 5]).all()
     rows = synth.lobster_csv_rows(m[0, :3])
     assert len(rows) == 3 and len(rows[0]) == 6 and "." in rows[0][0]
+
+
+def test_ffi_shim_source_is_guarded_and_names_the_abi():
+    """csrc/ffi/vitmarl_ffi.cc (jax.ffi handlers) must compile to an empty translation unit where the XLA FFI headers are absent
+    (this image) and bind exactly the C-ABI entry points the header declares."""
+    import os, re, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "vitmarl_b200", "csrc", "ffi", "vitmarl_ffi.cc")
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", src])
+    text = open(src).read()
+    header = open(os.path.join(root, "include", "vitmarl_b200.h")).read()
+    for fn in set(re.findall(r"\b(vitmarl_[a-z0-9_]+)\(", text)):
+        assert re.search(r"\b" + fn + r"\s*\(", header), fn
+    from vitmarl_b200 import _build
+    if _build.xla_ffi_include_dir() is None:
+        import pytest
+        with pytest.raises(RuntimeError):
+            _build.build_ffi()

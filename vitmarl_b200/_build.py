@@ -69,5 +69,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def xla_ffi_include_dir():
+    """Directory holding xla/ffi/api/ffi.h when JAX / jaxlib is installed, else None (this image: None)."""
+    try:
+        import jax.ffi
+        return jax.ffi.include_dir()
+    except Exception:
+        return None
+
+
+def build_ffi(include_dir: str = None) -> str:
+    """Compile csrc/ffi/vitmarl_ffi.cc (the XLA FFI handlers) against the library; only possible where the XLA FFI headers
+    exist.  Returns the .so path, or raises if the headers are missing."""
+    include_dir = include_dir or xla_ffi_include_dir()
+    if not include_dir or not os.path.exists(os.path.join(include_dir, "xla", "ffi", "api", "ffi.h")):
+        raise RuntimeError("XLA FFI headers not found (JAX is not installed): the jax.ffi shim cannot be built here")
+    build()
+    out = os.path.join(LIB_DIR, "libvitmarl_ffi.so")
+    src = os.path.join(CSRC, "ffi", "vitmarl_ffi.cc")
+    cmd = [_nvcc(), "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-I", include_dir, src, "-o", out,
+           "-L", LIB_DIR, "-lvitmarl_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
