@@ -219,6 +219,12 @@ int vitmarl_gemm_bf16(void* stream, int M, int N, int K,
  * (A [K,M], B [K,N] bf16 row-major; colsum may be NULL); flags as vitmarl_gemm_bf16. */
 int vitmarl_debug_gemm_dw(void* stream, int M, int N, int K, const void* A, const void* B, float* C, float* colsum, int flags);
 
+/* The attention core of the unfused encoder path on its own (test / measurement hook; TMA + tcgen05 + TMEM, csrc/attention_tc.cu):
+ * 64 tokens per image, head dim 64.  qkv [B*64, 3*64*heads] bf16 (q | k | v, head-major), out / dout [B*64, 64*heads],
+ * dqkv like qkv.  forward: out = softmax(q k^T / 8) v per (image, head); backward: dqkv from (qkv, dout). */
+int vitmarl_attention_fwd(void* stream, int B, int heads, const void* qkv, void* out);
+int vitmarl_attention_bwd(void* stream, int B, int heads, const void* qkv, const void* dout, void* dqkv);
+
 /* Shape of the encoder (docs/VIT_SPEC.md): pre-LN ViT, learned position embedding, no class
  * token, final LayerNorm then mean pool -> [B, dim].  Requires (H/P)*(W/P) == 64 tokens and
  * head dim 64 (ViT-Tiny/8 @ 64x64: dim 192, heads 3; ViT-S/16 @ 128x128: dim 384, heads 6). */

@@ -115,6 +115,8 @@ SIGNATURES = {
     "vitmarl_timing_destroy": (None, [_P]),
     "vitmarl_timing_reset": (_I, [_P]),
     "vitmarl_timing_read": (_I, [_P, _P, _P, _P]),
+    "vitmarl_attention_fwd": (_I, [_P, _I, _I, _P, _P]),
+    "vitmarl_attention_bwd": (_I, [_P, _I, _I, _P, _P, _P]),
     "vitmarl_dense_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _P, _I]),
     "vitmarl_gru_cell_f32": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "vitmarl_debug_gemm_dw": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _I]),

@@ -39,3 +39,14 @@ extern "C" int vitmarl_gemm_bf16(void* stream, int M, int N, int K, const void* 
   if (epi < 0 || epi > 4) return VITMARL_EINVAL;
   return vitmarl::launch_gemm(static_cast<cudaStream_t>(stream), g);
 }
+
+extern "C" int vitmarl_attention_fwd(void* stream, int B, int heads, const void* qkv, void* out) {
+  if (!qkv || !out) return VITMARL_EINVAL;
+  return vitmarl::launch_attention(static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), B, heads);
+}
+
+extern "C" int vitmarl_attention_bwd(void* stream, int B, int heads, const void* qkv, const void* dout, void* dqkv) {
+  if (!qkv || !dout || !dqkv) return VITMARL_EINVAL;
+  return vitmarl::launch_attention_bwd(static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout),
+                                       static_cast<__nv_bfloat16*>(dqkv), B, heads);
+}
