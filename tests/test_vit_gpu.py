@@ -74,12 +74,20 @@ def test_forward_matches_fp32_oracle(cfg, B):
                                    (vit.VIT_TINY_8, 296),
                                    (vit.VIT_TINY_8, 333),       # ragged: last pair tile half empty
                                    (vit.VIT_SMALL_16, 296)])
-def test_backward_matches_autograd(cfg, B):
+@pytest.mark.parametrize("fused", [1, 0])
+def test_backward_matches_autograd(cfg, B, fused):
+    """fused=1 (default): at D = 192 the MLP half of every block runs through the fused forward kernel and the fused backward
+    kernel (recompute from the block input); fused=0: the unfused kernel sequence with saved activations.  Other widths take
+    the unfused sequence either way."""
+    if fused == 0 and cfg.dim != 192:
+        pytest.skip("same path as fused=1 at this width")
     params = _perturbed_params(cfg, 3)
     x = _images(B, cfg, 1)
     dy = torch.randn(B, cfg.dim, generator=torch.Generator().manual_seed(1)).cuda()
     enc = vit.ViTEncoder(cfg)
-    enc.apply({"params": params}, x, train=True)
+    enc.options.fused = fused
+    y_tr = enc.apply({"params": params}, x, train=True)
+    assert _rel(y_tr, VO.vit_forward(cfg, params, x)) <= ACT_TOL
     grads, dx = enc.vjp({"params": params}, dy, want_dx=True)
     torch.cuda.synchronize()
     _, ref, ref_dx = VO.vit_value_and_grad(cfg, params, x, dy, want_dx=True)

@@ -1,0 +1,446 @@
+// Fused BACKWARD of the transformer MLP block for D = 192 / hidden 768 (ViT-Tiny), training path:
+//     forward (fused_mlp2.cu):  out = x + FC2( gelu_tanh( FC1( LN(x) ) ) )        saved: x only
+//     this kernel, per 128-token tile, from (x, dY = d out):
+//         xhat  = (x - mean) * rstd                                  -> global (B operand of the dW1' product)
+//         hpre  = xhat . W1'^T + b1'           (recomputed, W1' = W1 diag(gamma), b1' = b1 + W1 beta: vit_fold.cu)
+//         h2    = 2 gelu(hpre)                                       -> global (B operand of dW2 = 1/2 dY^T h2)
+//         dhpre = (dY . W2h) * 2 gelu'(hpre)   (W2h = W2 / 2)        -> global (A operand of dW1' = dhpre^T xhat; column sums = db1')
+//         dxhat = dhpre . W1'
+//         dx    = dY + rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat))     -> global
+// Nothing of the forward's [tokens, 768] activations is saved: the MLP half of a training step moves 24 instead of 42
+// [tokens, 192]-sized units through HBM.  The two weight-gradient products stay separate launches of gemm2_dw_kernel (a dW
+// accumulator for one 128-wide hidden chunk alone is 2 x 192 TMEM columns); LayerNorm-parameter and unfolded-weight gradients
+// follow from dW1' / db1' in mlp_bwd_unfold_kernel below.
+//
+// The kernel is HBM-bound on writing h2 and dhpre (590 KB per tile against ~14 k tensor cycles), so the structure is kept
+// simple: one CTA per SM, 128-token tiles, hidden dimension in 12 chunks of 64:
+//     FC1(c):  acc1[c&1] = xhat[smem] . W1'[c]^T            (SS, N = 64, K = 192)
+//     G(c):    accD[c&1] = dY[smem] . W2h[:, c]             (SS, N = 64, K = 192, B read MN-major)
+//     epilogue: h2, dhpre from (acc1, accD); dhpre -> TMEM over accD (bf16 pairs) and, with h2, -> global through a staging tile
+//     X(c):    acc3 += dhpre[tmem] . W1'[c]                 (TS, N = 192, K = 64; the SAME W1' stage read MN-major)
+// issue order FC1(c+1), G(c+1), X(c): the tensor pipe works on the next chunk while the epilogue warps run the GELU maths.
+// Warp roles (384 threads): 0 x / dY tile loads, 1 TMEM allocator + MMA issuer, 2 weight ring, 3 TMA stores, 4-11 epilogue
+// (thread = (token row, half)): LayerNorm, chunk epilogue on 32 of the 64 chunk columns, LayerNorm backward on 96 of 192 columns.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tc_common.cuh"
+#include "vit_kernels.h"
+#include "../../include/vitmarl_b200.h"
+
+namespace vitmarl {
+
+namespace fmb {
+constexpr int D = 192, HID = 768, HC = 64, NCHUNK = HID / HC, TM = 128;
+constexpr int KB_X = D / 64;                       // 3 K-blocks of the token operands
+constexpr int KBLK = TM * 128;                     // [128 x 64] bf16 = 16 KB
+constexpr int X_BYTES = KB_X * KBLK;               // 48 KB
+constexpr int W1_BYTES = HC * D * 2;               // [64 x 192] as 3 K-blocks of [64 x 64] = 24 KB
+constexpr int W2_BYTES = D * HC * 2;               // [192 x 64] = 24 KB
+constexpr int STAGE_BYTES = W1_BYTES + W2_BYTES;   // 48 KB
+constexpr int NSW = 2;
+constexpr int OFF_X = 0;                           // x -> xhat (in place) -> dx staging
+constexpr int OFF_DY = OFF_X + X_BYTES;
+constexpr int OFF_W = OFF_DY + X_BYTES;
+constexpr int OFF_STG = OFF_W + NSW * STAGE_BYTES; // one [128 x 64] staging tile (h2, then dhpre, of a chunk)
+constexpr int OFF_BAR = OFF_STG + TM * HC * 2;
+constexpr int OFF_MISC = OFF_BAR + 256;
+constexpr int MISC_BYTES = 128 * 2 * 8 + HID * 2;  // row partials [128][2] float2, b1' (bf16)
+constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;
+constexpr int W_LOAD = 0, W_MMA = 1, W_WRING = 2, W_STORE = 3, W_E0 = 4, N_E = 8;
+constexpr int THREADS = 32 * (W_E0 + N_E);         // 384
+constexpr int TMEM_COLS = 512;
+constexpr int COL_A1 = 0, COL_AD = 128, COL_A3 = 256;   // acc1[2] @ 0, 64 ; accD[2] @ 128, 192 ; acc3 @ 256..447
+enum { B_XFULL = 0, B_DYFULL, B_XNREADY, B_XFREE, B_DYFREE, B_OUTREADY, B_ACC3FULL, B_ACC3FREE, B_STGFULL, B_STGFREE,
+       B_ACCFULL, B_HREADY = B_ACCFULL + 2, B_WFULL = B_HREADY + 2, B_WEMPTY = B_WFULL + NSW, B_TMEMSLOT = B_WEMPTY + NSW, B_COUNT };
+static_assert(B_COUNT * 8 <= 256, "barrier area");
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+}  // namespace fmb
+
+struct FusedMlpBwdParams {
+  int M;
+  const uint16_t* b1p;          // [HID] folded FC1 bias, bf16
+  float eps;
+};
+
+__global__ void __launch_bounds__(fmb::THREADS, 1)
+fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmW1,
+                     const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmXH, const __grid_constant__ CUtensorMap tmH,
+                     const __grid_constant__ CUtensorMap tmDH, const __grid_constant__ CUtensorMap tmDX, const FusedMlpBwdParams p) {
+  using namespace fmb;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
+  auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
+  float2* part = reinterpret_cast<float2*>(sptr + OFF_MISC);                       // [128][2]
+  uint16_t* s_b1 = reinterpret_cast<uint16_t*>(sptr + OFF_MISC + 128 * 2 * 8);     // [HID] bf16
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (p.M + TM - 1) / TM;
+  const int nt = (int)blockIdx.x < num_tiles ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  auto tile_row = [&](int j) { return ((int)blockIdx.x + j * (int)gridDim.x) * TM; };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmDY); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmXH); tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmDH); tma_prefetch_desc(&tmDX);
+    mbar_init(bar(B_XFULL), 1); mbar_init(bar(B_DYFULL), 1); mbar_init(bar(B_XNREADY), N_E); mbar_init(bar(B_XFREE), 1);
+    mbar_init(bar(B_DYFREE), N_E); mbar_init(bar(B_OUTREADY), N_E); mbar_init(bar(B_ACC3FULL), 1); mbar_init(bar(B_ACC3FREE), N_E);
+    mbar_init(bar(B_STGFULL), N_E); mbar_init(bar(B_STGFREE), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(B_ACCFULL + i), 1); mbar_init(bar(B_HREADY + i), N_E); }
+    for (int i = 0; i < NSW; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
+    fence_mbar_init();
+  }
+  if (warp == W_MMA) tmem_alloc<TMEM_COLS>(bar(B_TMEMSLOT));
+  for (int i = threadIdx.x; i < HID; i += THREADS) s_b1[i] = p.b1p[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(bar(B_TMEMSLOT)));
+
+  if (warp == W_LOAD) {
+    // =============================== x / dY tiles ===============================
+    if (lane == 0) {
+      for (int j = 0; j < nt; ++j) {
+        mbar_wait_guard(bar(B_XFREE), (j & 1) ^ 1);            // the dx store of tile j-1 has read the x buffer
+        mbar_arrive_expect_tx(bar(B_XFULL), X_BYTES);
+        for (int kb = 0; kb < KB_X; ++kb) tma_load_2d(sbase + OFF_X + kb * KBLK, &tmX, kb * 64, tile_row(j), bar(B_XFULL));
+        mbar_wait_guard(bar(B_DYFREE), (j & 1) ^ 1);           // the LayerNorm-backward epilogue of tile j-1 has read dY
+        mbar_arrive_expect_tx(bar(B_DYFULL), X_BYTES);
+        for (int kb = 0; kb < KB_X; ++kb) tma_load_2d(sbase + OFF_DY + kb * KBLK, &tmDY, kb * 64, tile_row(j), bar(B_DYFULL));
+      }
+    }
+  } else if (warp == W_WRING) {
+    // =============================== weight ring: stage = W1'[c] (K-blocks) + W2h[:, c] ===============================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int g = 0; g < nt * NCHUNK; ++g) {
+        const int c = g % NCHUNK;
+        mbar_wait_guard(bar(B_WEMPTY + s), ph ^ 1);
+        mbar_arrive_expect_tx(bar(B_WFULL + s), STAGE_BYTES);
+        const uint32_t dst = sbase + OFF_W + s * STAGE_BYTES;
+        for (int kb = 0; kb < KB_X; ++kb) tma_load_2d(dst + kb * (HC * 128), &tmW1, kb * 64, c * HC, bar(B_WFULL + s));
+        tma_load_2d(dst + W1_BYTES, &tmW2, c * HC, 0, bar(B_WFULL + s));
+        if (++s == NSW) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == W_MMA) {
+    // =============================== MMA issuer ===============================
+    if (nt > 0) {
+      constexpr uint32_t id_fc1 = umma_idesc_bf16(TM, HC, false, false);
+      constexpr uint32_t id_g = umma_idesc_bf16(TM, HC, false, true);        // B = W2h[:, c] read MN-major (rows = output features of FC2)
+      constexpr uint32_t id_x = umma_idesc_bf16(TM, D, false, true);         // B = W1'[c] read MN-major (rows = hidden units of the chunk)
+      int s_f = 0; uint32_t ph_f = 0;     // ring position of the next FC1 / G pair
+      int s_x = 0;                        // ring position of the next X product
+      int g_f = 0;                        // global chunk counter of FC1 / G
+      auto fc1g = [&](int j) {
+        const uint32_t b = g_f & 1;
+        mbar_wait_guard(bar(B_WFULL + s_f), ph_f);
+        tc_fence_after();
+        const uint32_t w1 = sbase + OFF_W + s_f * STAGE_BYTES, w2 = w1 + W1_BYTES;
+        const uint32_t lax = umma_desc_lo(sbase + OFF_X), lay = umma_desc_lo(sbase + OFF_DY);
+        const uint32_t lb1 = umma_desc_lo(w1), lb2 = umma_desc_lo(w2, 8192);
+        if (elect_one()) {
+#pragma unroll
+          for (int kb = 0; kb < KB_X; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + COL_A1 + b * HC, umma_desc_from_lo(lax + kb * (KBLK >> 4) + 2 * k), umma_desc_from_lo(lb1 + kb * ((HC * 128) >> 4) + 2 * k),
+                        id_fc1, (kb | k) ? 1u : 0u);
+#pragma unroll
+          for (int kb = 0; kb < KB_X; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + COL_AD + b * HC, umma_desc_from_lo(lay + kb * (KBLK >> 4) + 2 * k), umma_desc_from_lo(lb2 + (kb * 4 + k) * 128),
+                        id_g, (kb | k) ? 1u : 0u);
+          umma_commit(bar(B_ACCFULL + b));
+        }
+        __syncwarp();
+        if (++s_f == NSW) { s_f = 0; ph_f ^= 1; }
+        ++g_f;
+      };
+      int g_x = 0;
+      for (int j = 0; j < nt; ++j) {
+        mbar_wait_guard(bar(B_XNREADY), j & 1);               // xhat of tile j in place
+        mbar_wait_guard(bar(B_DYFULL), j & 1);
+        tc_fence_after();
+        fc1g(j);
+        for (int c = 0; c < NCHUNK; ++c, ++g_x) {
+          if (c + 1 < NCHUNK) fc1g(j);                        // next chunk's products run under this chunk's epilogue
+          const uint32_t b = g_x & 1;
+          mbar_wait_guard(bar(B_HREADY + b), (g_x >> 1) & 1);
+          if (c == 0) mbar_wait_guard(bar(B_ACC3FREE), (j & 1) ^ 1);     // previous tile's LayerNorm-backward epilogue drained acc3
+          tc_fence_after();
+          const uint32_t lb = umma_desc_lo(sbase + OFF_W + s_x * STAGE_BYTES, 8192);
+          const uint32_t ta = tmem_base + COL_AD + b * HC;     // dhpre packed: K step kk -> columns (kk >> 1) * 32 + (kk & 1) * 8
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16_ts(tmem_base + COL_A3, ta + (kk >> 1) * 32 + (kk & 1) * 8, umma_desc_from_lo(lb + kk * 128), id_x, (c | kk) ? 1u : 0u);
+            umma_commit(bar(B_WEMPTY + s_x));
+            if (c == NCHUNK - 1) umma_commit(bar(B_ACC3FULL));
+          }
+          __syncwarp();
+          if (++s_x == NSW) s_x = 0;
+        }
+      }
+    }
+  } else if (warp == W_STORE) {
+    // =============================== TMA stores ===============================
+    if (lane == 0) {
+      uint32_t stg = 0;                                       // staging hand-over counter (2 per chunk)
+      for (int j = 0; j < nt; ++j) {
+        mbar_wait_guard(bar(B_XNREADY), j & 1);
+        for (int kb = 0; kb < KB_X; ++kb) tma_store_2d(&tmXH, sbase + OFF_X + kb * KBLK, kb * 64, tile_row(j));
+        bulk_commit();
+        bulk_wait_read0();
+        for (int c = 0; c < NCHUNK; ++c) {
+          for (int which = 0; which < 2; ++which, ++stg) {
+            mbar_wait_guard(bar(B_STGFULL), stg & 1);
+            tma_store_2d(which ? &tmDH : &tmH, sbase + OFF_STG, c * HC, tile_row(j));
+            bulk_commit();
+            bulk_wait_read0();
+            mbar_arrive(bar(B_STGFREE));
+          }
+        }
+        mbar_wait_guard(bar(B_OUTREADY), j & 1);
+        for (int kb = 0; kb < KB_X; ++kb) tma_store_2d(&tmDX, sbase + OFF_X + kb * KBLK, kb * 64, tile_row(j));
+        bulk_commit();
+        bulk_wait_read0();
+        mbar_arrive(bar(B_XFREE));
+      }
+      bulk_wait0();
+    }
+  } else if (warp >= W_E0) {
+    // =============================== epilogue warps: thread = (token row, half) ===============================
+    const int quad = warp & 3, half = (warp - W_E0) >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t tm_lane = (uint32_t)(quad * 32) << 16;
+    const uint32_t sw = (uint32_t)(row & 7);
+    const int col0 = half * 96;
+    uint32_t g = 0, stg = 0;
+    for (int j = 0; j < nt; ++j) {
+      // ---- LayerNorm (scale / shift folded into W1' / b1'): x -> xhat in place ----
+      float rstd;
+      {
+        uint8_t* xb = sptr + OFF_X;
+        mbar_wait_guard(bar(B_XFULL), j & 1);
+        uint4 v[12];
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const int col = col0 + i * 8, kb = col >> 6, c8 = (col & 63) >> 3;
+          v[i] = *reinterpret_cast<const uint4*>(xb + kb * KBLK + row * 128 + ((c8 ^ sw) << 4));
+          stats_bf16x2(v[i].x, s, q); stats_bf16x2(v[i].y, s, q); stats_bf16x2(v[i].z, s, q); stats_bf16x2(v[i].w, s, q);
+        }
+        part[row * 2 + half] = make_float2(s, q);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float2 o = part[row * 2 + (half ^ 1)];
+        s += o.x; q += o.y;
+        const float mean = s * (1.0f / D);
+        const float var = fmaxf(q * (1.0f / D) - mean * mean, 0.f);
+        const uint32_t rstd_b = pack_bf16(rsqrtf(var + p.eps), 0.f);      // (the forward normalises with the bf16-rounded rstd)
+        rstd = bf16_lo(rstd_b);
+        const float nmr = -mean * rstd;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const int col = col0 + i * 8, kb = col >> 6, c8 = (col & 63) >> 3;
+          v[i].x = norm_bf16x2(v[i].x, rstd_b, nmr); v[i].y = norm_bf16x2(v[i].y, rstd_b, nmr);
+          v[i].z = norm_bf16x2(v[i].z, rstd_b, nmr); v[i].w = norm_bf16x2(v[i].w, rstd_b, nmr);
+          *reinterpret_cast<uint4*>(xb + kb * KBLK + row * 128 + ((c8 ^ sw) << 4)) = v[i];
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_XNREADY));
+        asm volatile("bar.sync 1, 256;" ::: "memory");        // `part` reuse safety
+      }
+      // ---- chunk epilogues ----
+      for (int c = 0; c < NCHUNK; ++c, ++g) {
+        const uint32_t b = g & 1;
+        mbar_wait_guard(bar(B_ACCFULL + b), (g >> 1) & 1);
+        tc_fence_after();
+        uint32_t a1[32], ad[32];
+        tmem_ld_32x32(tmem_base + tm_lane + COL_A1 + b * HC + half * 32, a1);
+        tmem_ld_32x32(tmem_base + tm_lane + COL_AD + b * HC + half * 32, ad);
+        tmem_ld_wait();
+        const uint32_t* bias = reinterpret_cast<const uint32_t*>(s_b1 + c * HC + half * 32);
+        uint32_t hw[16], dw[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t bw = bias[i];
+          float h[2], d[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float x = __uint_as_float(a1[2 * i + e]) + (e ? bf16_hi(bw) : bf16_lo(bw));
+            const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+            const float x2 = x * x;
+            const float t = tanh_approx(k0 * x * fmaf(k1, x2, 1.0f));
+            const float opt = 1.0f + t;
+            h[e] = x * opt;                                                       // 2 gelu(x)
+            const float g2 = fmaf(x * (1.0f - t * t), k0 * fmaf(3.0f * k1, x2, 1.0f), opt);   // 2 gelu'(x)
+            d[e] = __uint_as_float(ad[2 * i + e]) * g2;
+          }
+          hw[i] = pack_bf16(h[0], h[1]);
+          dw[i] = pack_bf16(d[0], d[1]);
+        }
+        // dhpre (bf16 pairs) over the first 16 of this thread's own 32 accD columns: the A operand of X(c)
+        tmem_st_32x16(tmem_base + tm_lane + COL_AD + b * HC + half * 32, dw);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_HREADY + b));
+        // h2, then dhpre, through the one staging tile to global
+        uint8_t* st = sptr + OFF_STG + row * 128;
+#pragma unroll
+        for (int which = 0; which < 2; ++which, ++stg) {
+          mbar_wait_guard(bar(B_STGFREE), (stg & 1) ^ 1);
+          const uint32_t* src = which ? dw : hw;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            *reinterpret_cast<uint4*>(st + ((((uint32_t)(half * 4 + q4)) ^ sw) << 4)) = make_uint4(src[4 * q4], src[4 * q4 + 1], src[4 * q4 + 2], src[4 * q4 + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(B_STGFULL));
+        }
+      }
+      // ---- LayerNorm backward: dx = dY + rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)) ----
+      {
+        mbar_wait_guard(bar(B_ACC3FULL), j & 1);
+        tc_fence_after();
+        uint8_t* xb = sptr + OFF_X;
+        const uint8_t* yb = sptr + OFF_DY;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int g3 = 0; g3 < 3; ++g3) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + tm_lane + COL_A3 + col0 + g3 * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int col = col0 + g3 * 32 + 8 * i, kb = col >> 6, c8 = (col & 63) >> 3;
+            const uint4 xv = *reinterpret_cast<const uint4*>(xb + kb * KBLK + row * 128 + ((((uint32_t)c8) ^ sw) << 4));
+            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float d0 = __uint_as_float(r[8 * i + 2 * e]), d1 = __uint_as_float(r[8 * i + 2 * e + 1]);
+              s1 += d0 + d1;
+              s2 = fmaf(d0, bf16_lo(xw[e]), fmaf(d1, bf16_hi(xw[e]), s2));
+            }
+          }
+        }
+        part[row * 2 + half] = make_float2(s1, s2);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float2 o = part[row * 2 + (half ^ 1)];
+        const float m1 = (s1 + o.x) * (1.0f / D), m2 = (s2 + o.y) * (1.0f / D);
+#pragma unroll
+        for (int g3 = 0; g3 < 3; ++g3) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + tm_lane + COL_A3 + col0 + g3 * 32, r);
+          tmem_ld_wait();
+          if (g3 == 2) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(B_ACC3FREE));      // accumulator drained: the next tile's X(0) may overwrite it
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int col = col0 + g3 * 32 + 8 * i, kb = col >> 6, c8 = (col & 63) >> 3;
+            const uint32_t off = kb * KBLK + row * 128 + ((((uint32_t)c8) ^ sw) << 4);
+            const uint4 xv = *reinterpret_cast<const uint4*>(xb + off);
+            const uint4 yv = *reinterpret_cast<const uint4*>(yb + off);
+            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, yw[4] = {yv.x, yv.y, yv.z, yv.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float d0 = __uint_as_float(r[8 * i + 2 * e]), d1 = __uint_as_float(r[8 * i + 2 * e + 1]);
+              const float o0 = fmaf(rstd, d0 - m1 - bf16_lo(xw[e]) * m2, bf16_lo(yw[e]));
+              const float o1 = fmaf(rstd, d1 - m1 - bf16_hi(xw[e]) * m2, bf16_hi(yw[e]));
+              ow[e] = pack_bf16(o0, o1);
+            }
+            *reinterpret_cast<uint4*>(xb + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);     // dx staged over xhat, in place
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(bar(B_DYFREE)); mbar_arrive(bar(B_OUTREADY)); }
+        asm volatile("bar.sync 1, 256;" ::: "memory");        // `part` reuse safety
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc_fence_after();
+    tmem_dealloc<fmb::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---- unfolding the gradients of the folded parameters (vit_fold.cu): W' = c W diag(gamma), b' = c (b + W beta) ----
+//     dW[o, i] += c gamma[i] dW'[o, i];   dgamma[i] += c sum_o dW'[o, i] W[o, i];   dbeta[i] += c sum_o db'[o] W[o, i];   db[o] += c db'[o]
+// One CTA per 64-row slab of W (rows o), 256 threads: thread = (row group, column); column sums through shared memory atomics.
+__global__ void __launch_bounds__(256) unfold_grads_kernel(int N, int K, float c, const __nv_bfloat16* __restrict__ W, const float* __restrict__ gamma,
+                                                            const float* __restrict__ dWf, const float* __restrict__ dbf, float* __restrict__ dW,
+                                                            float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float red[];   // [2][K]
+  for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int o0 = blockIdx.x * 64;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const float gm = gamma ? gamma[i] : 1.0f;
+    float sg = 0.f, sb = 0.f;
+    for (int o = o0; o < min(o0 + 64, N); ++o) {
+      const float w = __bfloat162float(W[(size_t)o * K + i]);
+      const float g = dWf[(size_t)o * K + i];
+      dW[(size_t)o * K + i] += c * gm * g;
+      sg = fmaf(g, w, sg);
+      if (dbf) sb = fmaf(dbf[o], w, sb);
+    }
+    red[i] = c * sg; red[K + i] = c * sb;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + i, red[i]);
+    if (dbeta && dbf) atomicAdd(dbeta + i, red[K + i]);
+  }
+  if (db && dbf)
+    for (int o = o0 + threadIdx.x; o < min(o0 + 64, N); o += blockDim.x) db[o] += c * dbf[o];
+}
+
+int launch_unfold_grads(cudaStream_t s, int N, int K, float c, const __nv_bfloat16* W, const float* gamma, const float* dWf, const float* dbf,
+                        float* dW, float* db, float* dgamma, float* dbeta) {
+  if (N <= 0 || K <= 0) return VITMARL_OK;
+  unfold_grads_kernel<<<(N + 63) / 64, 256, 2 * K * sizeof(float), s>>>(N, K, c, W, gamma, dWf, dbf, dW, db, dgamma, dbeta);
+  return check_cuda(cudaGetLastError());
+}
+
+bool fused_mlp_bwd_supported(int D, int hidden) { return D == fmb::D && hidden == fmb::HID; }
+
+// x, dy [M, D] bf16;  w1f [HID, D] bf16 folded, b1p [HID] bf16 folded, w2h [D, HID] bf16 = W2 / 2  (vit_fold.cu)
+// outputs: xhat [M, D], h2 [M, HID] (= 2 gelu(hpre)), dh [M, HID] (= d hpre), dx [M, D]   (dx may alias dy: each tile's dy is read before its dx is written)
+int launch_fused_mlp_bwd(cudaStream_t stream, const __nv_bfloat16* x, const __nv_bfloat16* dy, const __nv_bfloat16* w1f, const __nv_bfloat16* b1p,
+                         const __nv_bfloat16* w2h, __nv_bfloat16* xhat, __nv_bfloat16* h2, __nv_bfloat16* dh, __nv_bfloat16* dx, int M, int D,
+                         int hidden, float eps) {
+  using namespace fmb;
+  if (D != fmb::D || hidden != HID) { set_last_error("fused_mlp_bwd: only D=192, hidden=768"); return VITMARL_EINVAL; }
+  if (M <= 0) return VITMARL_OK;
+  CUtensorMap tmX, tmDY, tmW1, tmW2, tmXH, tmH, tmDH, tmDX;
+  int rc;
+  if ((rc = make_tmap_2d_bf16(&tmX, x, M, D, (uint64_t)D * 2, TM, 64))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmDY, dy, M, D, (uint64_t)D * 2, TM, 64))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmXH, xhat, M, D, (uint64_t)D * 2, TM, 64))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmDX, dx, M, D, (uint64_t)D * 2, TM, 64))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmH, h2, M, HID, (uint64_t)HID * 2, TM, 64))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmDH, dh, M, HID, (uint64_t)HID * 2, TM, 64))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmW1, w1f, HID, D, (uint64_t)D * 2, HC, 64))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmW2, w2h, fmb::D, HID, (uint64_t)HID * 2, fmb::D, 64))) return rc;
+  FusedMlpBwdParams p{M, reinterpret_cast<const uint16_t*>(b1p), eps};
+  cudaError_t e = cudaFuncSetAttribute(fused_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) return check_cuda(e);
+  const int tiles = (M + TM - 1) / TM;
+  fused_mlp_bwd_kernel<<<min(tiles, num_sms()), THREADS, SMEM_BYTES, stream>>>(tmX, tmDY, tmW1, tmW2, tmXH, tmH, tmDH, tmDX, p);
+  return check_cuda(cudaGetLastError());
+}
+
+}  // namespace vitmarl

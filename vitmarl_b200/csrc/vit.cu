@@ -69,11 +69,15 @@ static size_t param_elems(const Dims& d, int idx, bool* is_matrix) {
 // ---- workspace layout -------------------------------------------------------------------------
 struct Ws {
   size_t patches, x, xm, ln1, ln2, qkv, att, hpre, hact, st1, st2, stf, dA, dB, dC, dH, dQKV, fold, pos_tile, total;
+  size_t bxhat, bh2, bdh, dwf;          // fused MLP backward (training, D = 192): per-layer scratch reused by every layer
   size_t sz_md, sz_mh, sz_mq, sz_st;   // per-layer strides (bytes)
   size_t sz_fold, f_w1, f_b1, f_w2, f_wqkv, f_bq, f_bv, f_bo;   // inference: folded parameters per layer (vit_fold.cu), offsets within a layer's slot
 };
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
-static Ws layout(const Dims& d, bool save) {
+// fused_train: the training path runs the MLP half of every block through the fused forward / backward kernels (no per-layer
+// LN2 / FC1 / GELU activations are kept)
+static bool train_fusable(const Dims& d) { return fused_mlp2_supported(d.D, d.mlp) && fused_mlp_bwd_supported(d.D, d.mlp) && d.L * 5 <= 64; }
+static Ws layout(const Dims& d, bool save, bool fused_train = false) {
   Ws w{};
   const size_t M = (size_t)d.M;
   w.sz_md = al(M * d.D * 2); w.sz_mh = al(M * d.mlp * 2); w.sz_mq = al(M * 3 * d.D * 2); w.sz_st = al(M * 2 * 4);
@@ -84,20 +88,27 @@ static Ws layout(const Dims& d, bool save) {
   w.x = take(w.sz_md * (save ? d.L + 1 : 1));
   w.xm = save ? take(w.sz_md * nl) : w.x;          // inference: residual stream updated in place
   w.ln1 = take(w.sz_md * nl);
-  w.ln2 = save ? take(w.sz_md * nl) : w.ln1;
+  const bool mlp_saved = !(save && fused_train);
+  w.ln2 = save ? (mlp_saved ? take(w.sz_md * nl) : 0) : w.ln1;
   w.qkv = take(w.sz_mq * nl);
   w.att = take(w.sz_md * nl);
-  w.hact = take(w.sz_mh * nl);
-  w.hpre = save ? take(w.sz_mh * nl) : 0;
+  w.hact = mlp_saved ? take(w.sz_mh * nl) : 0;
+  w.hpre = (save && mlp_saved) ? take(w.sz_mh * nl) : 0;
   w.st1 = save ? take(w.sz_st * nl) : 0;
-  w.st2 = save ? take(w.sz_st * nl) : 0;
+  w.st2 = (save && mlp_saved) ? take(w.sz_st * nl) : 0;
   w.stf = save ? take(w.sz_st) : 0;
   if (save) {
     w.dA = take(w.sz_md); w.dB = take(w.sz_md); w.dC = take(w.sz_md);
-    w.dH = take(w.sz_mh); w.dQKV = take(w.sz_mq);
+    w.dQKV = take(w.sz_mq);
+    if (mlp_saved) {
+      w.dH = take(w.sz_mh);
+    } else {
+      w.bxhat = take(w.sz_md); w.bh2 = take(w.sz_mh); w.bdh = take(w.sz_mh);
+      w.dwf = take((size_t)d.mlp * d.D * 4 + (size_t)d.mlp * 4);
+    }
   }
   w.pos_tile = take((size_t)128 * d.D * 2);           // bf16 position-embedding tile (addend of the patch-embedding GEMM)
-  if (!save) {
+  if (!save || fused_train) {
     size_t o = 0;
     auto slot = [&](size_t bytes) { size_t r = o; o += al(bytes); return r; };
     w.f_w1 = slot((size_t)d.mlp * d.D * 2); w.f_b1 = slot((size_t)d.mlp * 2); w.f_w2 = slot((size_t)d.D * d.mlp * 2);
@@ -171,7 +182,8 @@ static GemmDesc gd(int M, int N, int K, const bf16* A, int lda, bool amn, const 
 
 static int vit_forward(cudaStream_t st, const RunOpts& o, const Dims& d, const void* const* prm, const bf16* x, float* y, uint8_t* ws, bool save,
                        bool reuse_folded = false, bool x_is_patches = false) {
-  const Ws w = layout(d, save);
+  const bool fused_train = save && o.fused == 1 && train_fusable(d);
+  const Ws w = layout(d, save, fused_train);
   const int M = d.M, D = d.D;
   auto PB = [&](int i) { return static_cast<const bf16*>(prm[i]); };
   auto PF = [&](int i) { return static_cast<const float*>(prm[i]); };
@@ -193,7 +205,7 @@ static int vit_forward(cudaStream_t st, const RunOpts& o, const Dims& d, const v
 
   // inference: fold LayerNorm scale/shift, the GELU 1/2, the softmax scale and the K / V biases into the projections
   // (vit_fold.cu), all layers in two launches (the second one needs the folded V bias of the first)
-  const bool fuse_mlp2 = !save && o.fused == 1 && fused_mlp2_supported(D, d.mlp) && d.L * 5 <= 64;
+  const bool fuse_mlp2 = ((!save && o.fused == 1 && fused_mlp2_supported(D, d.mlp) && d.L * 5 <= 64) || fused_train);
   const bool fuse_attn2 = !save && o.fused == 1 && fused_attn2_supported(D, d.heads, d.T) && d.L * 5 <= 64;
   auto FW = [&](int l, size_t o) { return reinterpret_cast<bf16*>(ws + w.fold + (size_t)l * w.sz_fold + o); };
   auto FF = [&](int l, size_t o) { return reinterpret_cast<float*>(ws + w.fold + (size_t)l * w.sz_fold + o); };
@@ -253,7 +265,8 @@ static int vit_forward(cudaStream_t st, const RunOpts& o, const Dims& d, const v
     }
     }
     if (fuse_mlp2) {
-      // inference: LN2 + FC1 + GELU + FC2 + residual in one CTA-pair kernel on the folded parameters
+      // LN2 + FC1 + GELU + FC2 + residual in one CTA-pair kernel on the folded parameters (inference: in place; training: XM(l) ->
+      // X(l+1) out of place -- the block input is all the fused backward kernel needs)
       VM_TRY(timed(st, o, CAT_FUSED_MLP, 4.0 * M * D * d.mlp, [&] {
         return launch_fused_mlp2(st, XM(l), X(l + 1), FW(l, w.f_w1), FW(l, w.f_b1), FW(l, w.f_w2), PF(p_layer(l, L_FC2_B)), M, D, d.mlp, d.eps, o.fo);
       }));
@@ -277,7 +290,8 @@ static int vit_forward(cudaStream_t st, const RunOpts& o, const Dims& d, const v
 }
 
 static int vit_backward(cudaStream_t st, const RunOpts& o, const Dims& d, const void* const* prm, uint8_t* ws, const float* dy, void* const* dprm, bf16* dx) {
-  const Ws w = layout(d, true);
+  const bool fused_train = o.fused == 1 && train_fusable(d);       // must match the forward pass that filled the workspace
+  const Ws w = layout(d, true, fused_train);
   const int M = d.M, D = d.D, H = d.mlp;
   auto PB = [&](int i) { return static_cast<const bf16*>(prm[i]); };
   auto PF = [&](int i) { return static_cast<const float*>(prm[i]); };
@@ -324,9 +338,9 @@ static int vit_backward(cudaStream_t st, const RunOpts& o, const Dims& d, const 
   // dW[out,in] += dY^T . Xin   (both operands MN-major over the token dimension; split-K red.add)
   // db[out] += column sums of dY: handed to the same launch (the CTA-pair weight-gradient kernel folds it into its main loop as
   // one more MMA against a tile of ones, so dY is not read a second time; other shapes run the separate column-sum pass)
-  auto dW = [&](float* dw, float* db, const bf16* dY, int n_out, const bf16* Xin, int n_in) {
+  auto dW = [&](float* dw, float* db, const bf16* dY, int n_out, const bf16* Xin, int n_in, float scale = 1.0f) {
     GemmDesc g = gd(n_out, n_in, M, dY, n_out, true, Xin, n_in, true, dw, n_in, EPI_ATOMIC_F32);
-    g.colsum_a = db; g.allow_2cta = o.two_cta;
+    g.colsum_a = db; g.allow_2cta = o.two_cta; g.out_scale = scale;
     return timed(st, o, CAT_GEMM_DW, 2.0 * g.M * g.N * g.K, [&] { return launch_gemm(st, g); });
   };
   // dXin[M,n_in] = dY[M,n_out] . W[n_out,n_in]   (W read as the MN-major B operand)
@@ -340,11 +354,31 @@ static int vit_backward(cudaStream_t st, const RunOpts& o, const Dims& d, const 
   VM_TRY(bucket_done(0));
   for (int l = d.L - 1; l >= 0; --l) {
     // ---- MLP branch: x_{l+1} = xm + fc2(gelu(fc1(ln2(xm))))
+    if (fused_train) {
+      // one kernel recomputes the block from its input and produces dXM plus the operands of the two weight-gradient products
+      bf16* bxhat = reinterpret_cast<bf16*>(ws + w.bxhat);
+      bf16* bh2 = reinterpret_cast<bf16*>(ws + w.bh2);
+      bf16* bdh = reinterpret_cast<bf16*>(ws + w.bdh);
+      float* dwf = reinterpret_cast<float*>(ws + w.dwf);
+      float* dbf = dwf + (size_t)H * D;
+      auto FWl = [&](size_t off) { return reinterpret_cast<bf16*>(ws + w.fold + (size_t)l * w.sz_fold + off); };
+      VM_TRY(timed(st, o, CAT_FUSED_MLP, 6.0 * M * D * H, [&] {
+        return launch_fused_mlp_bwd(st, XM(l), dA, FWl(w.f_w1), FWl(w.f_b1), FWl(w.f_w2), bxhat, bh2, bdh, dB, M, D, H, d.eps);
+      }));
+      VM_TRY(dW(G(p_layer(l, L_FC2_W)), G(p_layer(l, L_FC2_B)), dA, D, bh2, H, 0.5f));       // h2 = 2 gelu(hpre)
+      { cudaError_t e = cudaMemsetAsync(dwf, 0, ((size_t)H * D + H) * sizeof(float), st); if (e != cudaSuccess) return check_cuda(e); }
+      VM_TRY(dW(dwf, dbf, bdh, H, bxhat, D));                                                  // gradients w.r.t. the FOLDED W1' / b1'
+      VM_TRY(timed(st, o, CAT_OTHER, 0, [&] {
+        return launch_unfold_grads(st, H, D, 1.0f, PB(p_layer(l, L_FC1_W)), PF(p_layer(l, L_LN2_G)), dwf, dbf, G(p_layer(l, L_FC1_W)),
+                                   G(p_layer(l, L_FC1_B)), G(p_layer(l, L_LN2_G)), G(p_layer(l, L_LN2_B)));
+      }));
+    } else {
     VM_TRY(dW(G(p_layer(l, L_FC2_W)), G(p_layer(l, L_FC2_B)), dA, D, HACT(l), H));
     VM_TRY(dXg(dH, dA, D, PB(p_layer(l, L_FC2_W)), H, EPI_MUL_GELU_GRAD, HPRE(l)));
     VM_TRY(dW(G(p_layer(l, L_FC1_W)), G(p_layer(l, L_FC1_B)), dH, H, LN2(l), D));
     VM_TRY(dXg(dC, dH, H, PB(p_layer(l, L_FC1_W)), D, EPI_STORE_BF16, nullptr));
     VM_TRY(timed(st, o, CAT_LAYERNORM, 0, [&] { return launch_layernorm_bwd(st, XM(l), PF(p_layer(l, L_LN2_G)), ST2(l), dC, dA, dB, G(p_layer(l, L_LN2_G)), G(p_layer(l, L_LN2_B)), M, D); }));
+    }
     // ---- attention branch: xm = x_l + out(attn(qkv(ln1(x_l))))
     VM_TRY(dW(G(p_layer(l, L_OUT_W)), G(p_layer(l, L_OUT_B)), dB, D, ATT(l), D));
     VM_TRY(dXg(dC, dB, D, PB(p_layer(l, L_OUT_W)), D, EPI_STORE_BF16, nullptr));
@@ -387,7 +421,9 @@ extern "C" long long vitmarl_vit_param_elems(const VitmarlVitShape* s, int index
 extern "C" size_t vitmarl_vit_workspace_bytes(const VitmarlVitShape* s, int save_for_bwd) {
   Dims d;
   if (get_dims(s, d)) return 0;
-  return layout(d, save_for_bwd == 1).total;
+  const bool save = save_for_bwd == 1;
+  const size_t a = layout(d, save, false).total, b = layout(d, save, save && train_fusable(d)).total;
+  return a > b ? a : b;       // either training layout (fused / unfused MLP half, VitmarlVitOptions::fused) fits
 }
 
 static RunOpts resolve(const VitmarlVitOptions* v) {
@@ -415,7 +451,7 @@ extern "C" int vitmarl_vit_fwd_ex(void* stream, const VitmarlVitShape* s, const 
   save_for_bwd &= ~VITMARL_VIT_INPUT_PATCHES;
   const bool save = save_for_bwd == 1;
   if (x_is_patches && (reinterpret_cast<uintptr_t>(x) & 15)) { set_last_error("vit_fwd: patch-matrix input must be 16-byte aligned"); return VITMARL_EINVAL; }
-  if (workspace_bytes < layout(d, save).total) { set_last_error("vit_fwd: workspace too small"); return VITMARL_EINVAL; }
+  if (workspace_bytes < vitmarl_vit_workspace_bytes(s, save ? 1 : 0)) { set_last_error("vit_fwd: workspace too small"); return VITMARL_EINVAL; }
   return vit_forward(static_cast<cudaStream_t>(stream), resolve(opt), d, params, static_cast<const bf16*>(x), y, static_cast<uint8_t*>(workspace), save,
                      save_for_bwd == 2, x_is_patches);
 }
@@ -431,7 +467,7 @@ extern "C" int vitmarl_vit_bwd_ex(void* stream, const VitmarlVitShape* s, const 
   VM_TRY(get_dims(s, d));
   if (d.B == 0) return VITMARL_OK;
   if (!params || !workspace || !dy || !dparams) return VITMARL_EINVAL;
-  if (workspace_bytes < layout(d, true).total) { set_last_error("vit_bwd: workspace too small"); return VITMARL_EINVAL; }
+  if (workspace_bytes < vitmarl_vit_workspace_bytes(s, 1)) { set_last_error("vit_bwd: workspace too small"); return VITMARL_EINVAL; }
   return vit_backward(static_cast<cudaStream_t>(stream), resolve(opt), d, params, static_cast<uint8_t*>(workspace), dy, dparams, static_cast<bf16*>(dx));
 }
 

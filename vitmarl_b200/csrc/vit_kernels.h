@@ -78,6 +78,18 @@ int launch_fused_mlp2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16
                       const __nv_bfloat16* w2h, const float* b2, int M, int D, int hidden, float eps, const FusedOpts& o);
 bool fused_mlp2_supported(int D, int hidden);
 
+// Fused BACKWARD of the MLP block on the same folded parameters (fused_mlp_bwd.cu): from the block input x and dy = d(out) it
+// recomputes the block and writes xhat [M,D], h2 = 2 gelu(hpre) [M,hidden], dh = d(hpre) [M,hidden] (operands of the two
+// weight-gradient products) and dx [M,D] (may alias dy).
+int launch_fused_mlp_bwd(cudaStream_t stream, const __nv_bfloat16* x, const __nv_bfloat16* dy, const __nv_bfloat16* w1f, const __nv_bfloat16* b1p,
+                         const __nv_bfloat16* w2h, __nv_bfloat16* xhat, __nv_bfloat16* h2, __nv_bfloat16* dh, __nv_bfloat16* dx, int M, int D,
+                         int hidden, float eps);
+bool fused_mlp_bwd_supported(int D, int hidden);
+// gradients of folded parameters W' = c W diag(gamma), b' = c (b + W beta) back to (W, b, gamma, beta), all accumulated (+=):
+// dWf [N,K] / dbf [N] fp32 are the gradients w.r.t. W' / b' (dbf, db, dbeta may be null; gamma null = ones)
+int launch_unfold_grads(cudaStream_t s, int N, int K, float c, const __nv_bfloat16* W, const float* gamma, const float* dWf, const float* dbf,
+                        float* dW, float* db, float* dgamma, float* dbeta);
+
 // Second-generation fused attention block on FOLDED parameters (vit_fold.cu): wqkvf = Wqkv.diag(gamma) with the Q rows scaled
 // by log2(e)/8, bqp = bf16 folded Q bias, bof = bo + Wo.(bv + Wv.beta).  `out` may alias `x`
 int launch_fused_attn2(cudaStream_t stream, const __nv_bfloat16* x, __nv_bfloat16* out, const __nv_bfloat16* wqkvf, const __nv_bfloat16* bqp,
