@@ -369,7 +369,7 @@ static int vit_backward(cudaStream_t st, const RunOpts& o, const Dims& d, const 
       { cudaError_t e = cudaMemsetAsync(dwf, 0, ((size_t)H * D + H) * sizeof(float), st); if (e != cudaSuccess) return check_cuda(e); }
       VM_TRY(dW(dwf, dbf, bdh, H, bxhat, D));                                                  // gradients w.r.t. the FOLDED W1' / b1'
       VM_TRY(timed(st, o, CAT_OTHER, 0, [&] {
-        return launch_unfold_grads(st, H, D, 1.0f, PB(p_layer(l, L_FC1_W)), PF(p_layer(l, L_LN2_G)), dwf, dbf, G(p_layer(l, L_FC1_W)),
+        return launch_unfold_grads(st, H, D, 1.0f, PB(p_layer(l, L_FC1_W)), PF(p_layer(l, L_LN2_G)), PF(p_layer(l, L_LN2_B)), dwf, dbf, G(p_layer(l, L_FC1_W)),
                                    G(p_layer(l, L_FC1_B)), G(p_layer(l, L_LN2_G)), G(p_layer(l, L_LN2_B)));
       }));
     } else {

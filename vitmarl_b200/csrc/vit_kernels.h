@@ -87,8 +87,8 @@ int launch_fused_mlp_bwd(cudaStream_t stream, const __nv_bfloat16* x, const __nv
 bool fused_mlp_bwd_supported(int D, int hidden);
 // gradients of folded parameters W' = c W diag(gamma), b' = c (b + W beta) back to (W, b, gamma, beta), all accumulated (+=):
 // dWf [N,K] / dbf [N] fp32 are the gradients w.r.t. W' / b' (dbf, db, dbeta may be null; gamma null = ones)
-int launch_unfold_grads(cudaStream_t s, int N, int K, float c, const __nv_bfloat16* W, const float* gamma, const float* dWf, const float* dbf,
-                        float* dW, float* db, float* dgamma, float* dbeta);
+int launch_unfold_grads(cudaStream_t s, int N, int K, float c, const __nv_bfloat16* W, const float* gamma, const float* beta, const float* dWf,
+                        const float* dbf, float* dW, float* db, float* dgamma, float* dbeta);
 
 // Second-generation fused attention block on FOLDED parameters (vit_fold.cu): wqkvf = Wqkv.diag(gamma) with the Q rows scaled
 // by log2(e)/8, bqp = bf16 folded Q bias, bof = bo + Wo.(bv + Wv.beta).  `out` may alias `x`
