@@ -14,11 +14,16 @@
 //
 // The kernel is HBM-bound on writing h2 and dhpre (590 KB per tile against ~14 k tensor cycles), so the structure is kept
 // simple: one CTA per SM, 128-token tiles, hidden dimension in 12 chunks of 64:
-//     FC1(c):  acc1[c&1] = xhat[smem] . W1'[c]^T            (SS, N = 64, K = 192)
+//     FC1(c):  acc1      = xhat[tmem] . W1'[c]^T            (TS, N = 64, K = 192; LayerNorm writes xhat straight into tensor memory)
 //     G(c):    accD[c&1] = dY[smem] . W2h[:, c]             (SS, N = 64, K = 192, B read MN-major)
-//     epilogue: h2, dhpre from (acc1, accD); dhpre -> TMEM over accD (bf16 pairs) and, with h2, -> global through a staging tile
+//     epilogue: h2, dhpre from (acc1, accD); dhpre -> TMEM over accD (bf16 pairs) and, with h2, -> global through two staging tiles
 //     X(c):    acc3 += dhpre[tmem] . W1'[c]                 (TS, N = 192, K = 64; the SAME W1' stage read MN-major)
 // issue order FC1(c+1), G(c+1), X(c): the tensor pipe works on the next chunk while the epilogue warps run the GELU maths.
+// Shared memory (216 KB): the x tile is dead once xhat is in tensor memory and stored, so its 48 KB become the two chunk staging
+// tiles; that leaves room for a 3-deep W1' ring (a stage lives from its load to X(c): ~7 k cycles against ~2 k per chunk) next to
+// a 2-deep W2h ring (a stage only lives until G(c) retires).  (First version: x as a shared-memory operand, ONE staging tile and a
+// 2-deep combined ring -- 0.98 ms per launch at 4096 tiles, bound by the epilogue warps waiting on the staging hand-over and by
+// the ring's chain latency.)
 // Warp roles (384 threads): 0 x / dY tile loads, 1 TMEM allocator + MMA issuer, 2 weight ring, 3 TMA stores, 4-11 epilogue
 // (thread = (token row, half)): LayerNorm, chunk epilogue on 32 of the 64 chunk columns, LayerNorm backward on 96 of 192 columns.
 #include <cuda.h>
@@ -39,22 +44,24 @@ constexpr int KBLK = TM * 128;                     // [128 x 64] bf16 = 16 KB
 constexpr int X_BYTES = KB_X * KBLK;               // 48 KB
 constexpr int W1_BYTES = HC * D * 2;               // [64 x 192] as 3 K-blocks of [64 x 64] = 24 KB
 constexpr int W2_BYTES = D * HC * 2;               // [192 x 64] = 24 KB
-constexpr int STAGE_BYTES = W1_BYTES + W2_BYTES;   // 48 KB
-constexpr int NSW = 2;
-constexpr int OFF_X = 0;                           // x -> xhat (in place) -> dx staging
-constexpr int OFF_DY = OFF_X + X_BYTES;
-constexpr int OFF_W = OFF_DY + X_BYTES;
-constexpr int OFF_STG = OFF_W + NSW * STAGE_BYTES; // one [128 x 64] staging tile (h2, then dhpre, of a chunk)
-constexpr int OFF_BAR = OFF_STG + TM * HC * 2;
+constexpr int NS1 = 3, NS2 = 2;                    // W1' stages live from FC1(c) to X(c) (load + FC1 + epilogue + X ~ 7 k cycles): 3 deep;
+                                                   // W2h stages only until G(c) has retired: 2 deep
+constexpr int OFF_X = 0;                           // x landing tile -> xhat (in place; copied to TMEM and stored) -> the two chunk staging tiles
+constexpr int OFF_STG = OFF_X;                     // h2 tile @ +0, dhpre tile @ +16 KB  (aliases the dead x tile during the chunk loop)
+constexpr int OFF_DY = OFF_X + X_BYTES;            // dY tile (A operand of G) -> dx staging in place
+constexpr int OFF_W1 = OFF_DY + X_BYTES;
+constexpr int OFF_W2 = OFF_W1 + NS1 * W1_BYTES;
+constexpr int OFF_BAR = OFF_W2 + NS2 * W2_BYTES;
 constexpr int OFF_MISC = OFF_BAR + 256;
 constexpr int MISC_BYTES = 128 * 2 * 8 + HID * 2;  // row partials [128][2] float2, b1' (bf16)
 constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;
 constexpr int W_LOAD = 0, W_MMA = 1, W_WRING = 2, W_STORE = 3, W_E0 = 4, N_E = 8;
 constexpr int THREADS = 32 * (W_E0 + N_E);         // 384
 constexpr int TMEM_COLS = 512;
-constexpr int COL_A1 = 0, COL_AD = 128, COL_A3 = 256;   // acc1[2] @ 0, 64 ; accD[2] @ 128, 192 ; acc3 @ 256..447
-enum { B_XFULL = 0, B_DYFULL, B_XNREADY, B_XFREE, B_DYFREE, B_OUTREADY, B_ACC3FULL, B_ACC3FREE, B_STGFULL, B_STGFREE,
-       B_ACCFULL, B_HREADY = B_ACCFULL + 2, B_WFULL = B_HREADY + 2, B_WEMPTY = B_WFULL + NSW, B_TMEMSLOT = B_WEMPTY + NSW, B_COUNT };
+constexpr int COL_XN = 0, COL_A1 = 96, COL_AD = 160, COL_A3 = 288;   // xhat (bf16 pairs) 0..95 | acc1 96..159 | accD[2] 160..287 | acc3 288..479
+enum { B_XFULL = 0, B_DYFULL, B_XNREADY, B_XSTORED, B_XFREE, B_DYFREE, B_OUTREADY, B_ACC3FULL, B_ACC3FREE, B_A1FREE,
+       B_STGFULL, B_STGFREE = B_STGFULL + 2, B_ACCFULL = B_STGFREE + 2, B_HREADY = B_ACCFULL + 2,
+       B_W1FULL = B_HREADY + 2, B_W1EMPTY = B_W1FULL + NS1, B_W2FULL = B_W1EMPTY + NS1, B_W2EMPTY = B_W2FULL + NS2, B_TMEMSLOT = B_W2EMPTY + NS2, B_COUNT };
 static_assert(B_COUNT * 8 <= 256, "barrier area");
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 }  // namespace fmb
@@ -85,11 +92,14 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmDY); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmXH); tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmDH); tma_prefetch_desc(&tmDX);
-    mbar_init(bar(B_XFULL), 1); mbar_init(bar(B_DYFULL), 1); mbar_init(bar(B_XNREADY), N_E); mbar_init(bar(B_XFREE), 1);
-    mbar_init(bar(B_DYFREE), N_E); mbar_init(bar(B_OUTREADY), N_E); mbar_init(bar(B_ACC3FULL), 1); mbar_init(bar(B_ACC3FREE), N_E);
-    mbar_init(bar(B_STGFULL), N_E); mbar_init(bar(B_STGFREE), 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(bar(B_ACCFULL + i), 1); mbar_init(bar(B_HREADY + i), N_E); }
-    for (int i = 0; i < NSW; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
+    mbar_init(bar(B_XFULL), 1); mbar_init(bar(B_DYFULL), 1); mbar_init(bar(B_XNREADY), N_E); mbar_init(bar(B_XSTORED), 1); mbar_init(bar(B_XFREE), 1);
+    mbar_init(bar(B_DYFREE), 1); mbar_init(bar(B_OUTREADY), N_E); mbar_init(bar(B_ACC3FULL), 1); mbar_init(bar(B_ACC3FREE), N_E);
+    mbar_init(bar(B_A1FREE), N_E);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(B_STGFULL + i), N_E); mbar_init(bar(B_STGFREE + i), 1); mbar_init(bar(B_ACCFULL + i), 1); mbar_init(bar(B_HREADY + i), N_E);
+    }
+    for (int i = 0; i < NS1; ++i) { mbar_init(bar(B_W1FULL + i), 1); mbar_init(bar(B_W1EMPTY + i), 1); }
+    for (int i = 0; i < NS2; ++i) { mbar_init(bar(B_W2FULL + i), 1); mbar_init(bar(B_W2EMPTY + i), 1); }
     fence_mbar_init();
   }
   if (warp == W_MMA) tmem_alloc<TMEM_COLS>(bar(B_TMEMSLOT));
@@ -104,112 +114,124 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     // =============================== x / dY tiles ===============================
     if (lane == 0) {
       for (int j = 0; j < nt; ++j) {
-        mbar_wait_guard(bar(B_XFREE), (j & 1) ^ 1);            // the dx store of tile j-1 has read the x buffer
+        mbar_wait_guard(bar(B_XFREE), (j & 1) ^ 1);            // the last chunk stores of tile j-1 have read the staging tiles (= this buffer)
         mbar_arrive_expect_tx(bar(B_XFULL), X_BYTES);
         for (int kb = 0; kb < KB_X; ++kb) tma_load_2d(sbase + OFF_X + kb * KBLK, &tmX, kb * 64, tile_row(j), bar(B_XFULL));
-        mbar_wait_guard(bar(B_DYFREE), (j & 1) ^ 1);           // the LayerNorm-backward epilogue of tile j-1 has read dY
+        mbar_wait_guard(bar(B_DYFREE), (j & 1) ^ 1);           // the dx store of tile j-1 has read the dY buffer
         mbar_arrive_expect_tx(bar(B_DYFULL), X_BYTES);
         for (int kb = 0; kb < KB_X; ++kb) tma_load_2d(sbase + OFF_DY + kb * KBLK, &tmDY, kb * 64, tile_row(j), bar(B_DYFULL));
       }
     }
   } else if (warp == W_WRING) {
-    // =============================== weight ring: stage = W1'[c] (K-blocks) + W2h[:, c] ===============================
+    // =============================== weight rings: W1'[c] (3 K-blocks of [64 x 64]) and W2h[:, c] ([192 x 64]) ===============================
     if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
+      int s1 = 0, s2 = 0; uint32_t ph1 = 0, ph2 = 0;
       for (int g = 0; g < nt * NCHUNK; ++g) {
         const int c = g % NCHUNK;
-        mbar_wait_guard(bar(B_WEMPTY + s), ph ^ 1);
-        mbar_arrive_expect_tx(bar(B_WFULL + s), STAGE_BYTES);
-        const uint32_t dst = sbase + OFF_W + s * STAGE_BYTES;
-        for (int kb = 0; kb < KB_X; ++kb) tma_load_2d(dst + kb * (HC * 128), &tmW1, kb * 64, c * HC, bar(B_WFULL + s));
-        tma_load_2d(dst + W1_BYTES, &tmW2, c * HC, 0, bar(B_WFULL + s));
-        if (++s == NSW) { s = 0; ph ^= 1; }
+        mbar_wait_guard(bar(B_W2EMPTY + s2), ph2 ^ 1);
+        mbar_arrive_expect_tx(bar(B_W2FULL + s2), W2_BYTES);
+        tma_load_2d(sbase + OFF_W2 + s2 * W2_BYTES, &tmW2, c * HC, 0, bar(B_W2FULL + s2));
+        if (++s2 == NS2) { s2 = 0; ph2 ^= 1; }
+        mbar_wait_guard(bar(B_W1EMPTY + s1), ph1 ^ 1);
+        mbar_arrive_expect_tx(bar(B_W1FULL + s1), W1_BYTES);
+        for (int kb = 0; kb < KB_X; ++kb) tma_load_2d(sbase + OFF_W1 + s1 * W1_BYTES + kb * (HC * 128), &tmW1, kb * 64, c * HC, bar(B_W1FULL + s1));
+        if (++s1 == NS1) { s1 = 0; ph1 ^= 1; }
       }
     }
   } else if (warp == W_MMA) {
     // =============================== MMA issuer ===============================
     if (nt > 0) {
-      constexpr uint32_t id_fc1 = umma_idesc_bf16(TM, HC, false, false);
+      constexpr uint32_t id_fc1 = umma_idesc_bf16(TM, HC, false, false);     // A = xhat in tensor memory
       constexpr uint32_t id_g = umma_idesc_bf16(TM, HC, false, true);        // B = W2h[:, c] read MN-major (rows = output features of FC2)
       constexpr uint32_t id_x = umma_idesc_bf16(TM, D, false, true);         // B = W1'[c] read MN-major (rows = hidden units of the chunk)
-      int s_f = 0; uint32_t ph_f = 0;     // ring position of the next FC1 / G pair
-      int s_x = 0;                        // ring position of the next X product
-      int g_f = 0;                        // global chunk counter of FC1 / G
-      auto fc1g = [&](int j) {
+      int s1f = 0, s2f = 0; uint32_t ph1f = 0, ph2f = 0;   // ring positions of the next FC1 / G
+      int s1x = 0;                                          // ring position of the next X product
+      uint32_t g_f = 0;                                     // global chunk counter of FC1 / G
+      auto fc1g = [&]() {
         const uint32_t b = g_f & 1;
-        mbar_wait_guard(bar(B_WFULL + s_f), ph_f);
+        // acc1 is single-buffered: the epilogue of the previous chunk drains it first thing
+        mbar_wait_guard(bar(B_A1FREE), (g_f & 1) ^ 1);
+        mbar_wait_guard(bar(B_W1FULL + s1f), ph1f);
         tc_fence_after();
-        const uint32_t w1 = sbase + OFF_W + s_f * STAGE_BYTES, w2 = w1 + W1_BYTES;
-        const uint32_t lax = umma_desc_lo(sbase + OFF_X), lay = umma_desc_lo(sbase + OFF_DY);
-        const uint32_t lb1 = umma_desc_lo(w1), lb2 = umma_desc_lo(w2, 8192);
+        const uint32_t lb1 = umma_desc_lo(sbase + OFF_W1 + s1f * W1_BYTES);
         if (elect_one()) {
 #pragma unroll
           for (int kb = 0; kb < KB_X; ++kb)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + COL_A1 + b * HC, umma_desc_from_lo(lax + kb * (KBLK >> 4) + 2 * k), umma_desc_from_lo(lb1 + kb * ((HC * 128) >> 4) + 2 * k),
-                        id_fc1, (kb | k) ? 1u : 0u);
+              umma_bf16_ts(tmem_base + COL_A1, tmem_base + COL_XN + (kb * 4 + k) * 8, umma_desc_from_lo(lb1 + kb * ((HC * 128) >> 4) + 2 * k), id_fc1,
+                           (kb | k) ? 1u : 0u);
+        }
+        __syncwarp();
+        mbar_wait_guard(bar(B_W2FULL + s2f), ph2f);
+        tc_fence_after();
+        const uint32_t lay = umma_desc_lo(sbase + OFF_DY), lb2 = umma_desc_lo(sbase + OFF_W2 + s2f * W2_BYTES, 8192);
+        if (elect_one()) {
 #pragma unroll
           for (int kb = 0; kb < KB_X; ++kb)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16(tmem_base + COL_AD + b * HC, umma_desc_from_lo(lay + kb * (KBLK >> 4) + 2 * k), umma_desc_from_lo(lb2 + (kb * 4 + k) * 128),
                         id_g, (kb | k) ? 1u : 0u);
+          umma_commit(bar(B_W2EMPTY + s2f));                   // W2h[:, c] is dead once G(c) has retired
           umma_commit(bar(B_ACCFULL + b));
         }
         __syncwarp();
-        if (++s_f == NSW) { s_f = 0; ph_f ^= 1; }
+        if (++s1f == NS1) { s1f = 0; ph1f ^= 1; }
+        if (++s2f == NS2) { s2f = 0; ph2f ^= 1; }
         ++g_f;
       };
-      int g_x = 0;
+      uint32_t g_x = 0;
       for (int j = 0; j < nt; ++j) {
-        mbar_wait_guard(bar(B_XNREADY), j & 1);               // xhat of tile j in place
+        mbar_wait_guard(bar(B_XNREADY), j & 1);               // xhat of tile j is in tensor memory
         mbar_wait_guard(bar(B_DYFULL), j & 1);
         tc_fence_after();
-        fc1g(j);
+        fc1g();
         for (int c = 0; c < NCHUNK; ++c, ++g_x) {
-          if (c + 1 < NCHUNK) fc1g(j);                        // next chunk's products run under this chunk's epilogue
+          if (c + 1 < NCHUNK) fc1g();                         // next chunk's products run under this chunk's epilogue
           const uint32_t b = g_x & 1;
           mbar_wait_guard(bar(B_HREADY + b), (g_x >> 1) & 1);
           if (c == 0) mbar_wait_guard(bar(B_ACC3FREE), (j & 1) ^ 1);     // previous tile's LayerNorm-backward epilogue drained acc3
           tc_fence_after();
-          const uint32_t lb = umma_desc_lo(sbase + OFF_W + s_x * STAGE_BYTES, 8192);
+          const uint32_t lb = umma_desc_lo(sbase + OFF_W1 + s1x * W1_BYTES, 8192);
           const uint32_t ta = tmem_base + COL_AD + b * HC;     // dhpre packed: K step kk -> columns (kk >> 1) * 32 + (kk & 1) * 8
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
               umma_bf16_ts(tmem_base + COL_A3, ta + (kk >> 1) * 32 + (kk & 1) * 8, umma_desc_from_lo(lb + kk * 128), id_x, (c | kk) ? 1u : 0u);
-            umma_commit(bar(B_WEMPTY + s_x));
+            umma_commit(bar(B_W1EMPTY + s1x));
             if (c == NCHUNK - 1) umma_commit(bar(B_ACC3FULL));
           }
           __syncwarp();
-          if (++s_x == NSW) s_x = 0;
+          if (++s1x == NS1) s1x = 0;
         }
       }
     }
   } else if (warp == W_STORE) {
     // =============================== TMA stores ===============================
     if (lane == 0) {
-      uint32_t stg = 0;                                       // staging hand-over counter (2 per chunk)
+      uint32_t g = 0;
       for (int j = 0; j < nt; ++j) {
         mbar_wait_guard(bar(B_XNREADY), j & 1);
         for (int kb = 0; kb < KB_X; ++kb) tma_store_2d(&tmXH, sbase + OFF_X + kb * KBLK, kb * 64, tile_row(j));
         bulk_commit();
         bulk_wait_read0();
-        for (int c = 0; c < NCHUNK; ++c) {
-          for (int which = 0; which < 2; ++which, ++stg) {
-            mbar_wait_guard(bar(B_STGFULL), stg & 1);
-            tma_store_2d(which ? &tmDH : &tmH, sbase + OFF_STG, c * HC, tile_row(j));
+        mbar_arrive(bar(B_XSTORED));                          // the x tile is dead: its memory becomes the two staging tiles
+        for (int c = 0; c < NCHUNK; ++c, ++g) {
+          for (int which = 0; which < 2; ++which) {
+            mbar_wait_guard(bar(B_STGFULL + which), g & 1);
+            tma_store_2d(which ? &tmDH : &tmH, sbase + OFF_STG + which * (TM * HC * 2), c * HC, tile_row(j));
             bulk_commit();
             bulk_wait_read0();
-            mbar_arrive(bar(B_STGFREE));
+            mbar_arrive(bar(B_STGFREE + which));
           }
         }
+        mbar_arrive(bar(B_XFREE));                             // staging tiles read: the next tile's x may land
         mbar_wait_guard(bar(B_OUTREADY), j & 1);
-        for (int kb = 0; kb < KB_X; ++kb) tma_store_2d(&tmDX, sbase + OFF_X + kb * KBLK, kb * 64, tile_row(j));
+        for (int kb = 0; kb < KB_X; ++kb) tma_store_2d(&tmDX, sbase + OFF_DY + kb * KBLK, kb * 64, tile_row(j));
         bulk_commit();
         bulk_wait_read0();
-        mbar_arrive(bar(B_XFREE));
+        mbar_arrive(bar(B_DYFREE));
       }
       bulk_wait0();
     }
@@ -220,9 +242,9 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const uint32_t tm_lane = (uint32_t)(quad * 32) << 16;
     const uint32_t sw = (uint32_t)(row & 7);
     const int col0 = half * 96;
-    uint32_t g = 0, stg = 0;
+    uint32_t g = 0;
     for (int j = 0; j < nt; ++j) {
-      // ---- LayerNorm (scale / shift folded into W1' / b1'): x -> xhat in place ----
+      // ---- LayerNorm (scale / shift folded into W1' / b1'): x -> xhat in place (for the store) and into tensor memory (FC1's A operand) ----
       float rstd;
       {
         uint8_t* xb = sptr + OFF_X;
@@ -244,17 +266,30 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         const uint32_t rstd_b = pack_bf16(rsqrtf(var + p.eps), 0.f);      // (the forward normalises with the bf16-rounded rstd)
         rstd = bf16_lo(rstd_b);
         const float nmr = -mean * rstd;
+        uint32_t w[48];
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
           const int col = col0 + i * 8, kb = col >> 6, c8 = (col & 63) >> 3;
           v[i].x = norm_bf16x2(v[i].x, rstd_b, nmr); v[i].y = norm_bf16x2(v[i].y, rstd_b, nmr);
           v[i].z = norm_bf16x2(v[i].z, rstd_b, nmr); v[i].w = norm_bf16x2(v[i].w, rstd_b, nmr);
           *reinterpret_cast<uint4*>(xb + kb * KBLK + row * 128 + ((c8 ^ sw) << 4)) = v[i];
+          w[4 * i] = v[i].x; w[4 * i + 1] = v[i].y; w[4 * i + 2] = v[i].z; w[4 * i + 3] = v[i].w;
         }
+        // xhat as bf16 pairs: columns col0/2 .. col0/2 + 48 of XN (the previous tile's FC1 products retired before its ACC3FULL)
+#pragma unroll
+        for (int t3 = 0; t3 < 3; ++t3) {                      // three 16-column stores (column offsets are multiples of 16)
+          uint32_t w16[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w16[i] = w[t3 * 16 + i];
+          tmem_st_32x16(tmem_base + tm_lane + COL_XN + half * 48 + t3 * 16, w16);
+        }
+        tmem_st_wait();
         fence_proxy_async_smem();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_XNREADY));
         asm volatile("bar.sync 1, 256;" ::: "memory");        // `part` reuse safety
+        mbar_wait_guard(bar(B_XSTORED), j & 1);               // the xhat store has read the tile: it may now be overwritten by the staging tiles
       }
       // ---- chunk epilogues ----
       for (int c = 0; c < NCHUNK; ++c, ++g) {
@@ -262,9 +297,12 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         mbar_wait_guard(bar(B_ACCFULL + b), (g >> 1) & 1);
         tc_fence_after();
         uint32_t a1[32], ad[32];
-        tmem_ld_32x32(tmem_base + tm_lane + COL_A1 + b * HC + half * 32, a1);
+        tmem_ld_32x32(tmem_base + tm_lane + COL_A1 + half * 32, a1);
         tmem_ld_32x32(tmem_base + tm_lane + COL_AD + b * HC + half * 32, ad);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_A1FREE));            // acc1 drained: FC1 of the next chunk may overwrite it
         const uint32_t* bias = reinterpret_cast<const uint32_t*>(s_b1 + c * HC + half * 32);
         uint32_t hw[16], dw[16];
 #pragma unroll
@@ -276,41 +314,50 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             const float x = __uint_as_float(a1[2 * i + e]) + (e ? bf16_hi(bw) : bf16_lo(bw));
             const float k0 = 0.7978845608028654f, k1 = 0.044715f;
             const float x2 = x * x;
-            const float t = tanh_approx(k0 * x * fmaf(k1, x2, 1.0f));
+            const float t = tanh_approx(x * fmaf(k0 * k1, x2, k0));
             const float opt = 1.0f + t;
             h[e] = x * opt;                                                       // 2 gelu(x)
-            const float g2 = fmaf(x * (1.0f - t * t), k0 * fmaf(3.0f * k1, x2, 1.0f), opt);   // 2 gelu'(x)
+            const float g2 = fmaf(x * fmaf(-t, t, 1.0f), fmaf(3.0f * k0 * k1, x2, k0), opt);   // 2 gelu'(x)
             d[e] = __uint_as_float(ad[2 * i + e]) * g2;
           }
           hw[i] = pack_bf16(h[0], h[1]);
           dw[i] = pack_bf16(d[0], d[1]);
         }
         // dhpre (bf16 pairs) over the first 16 of this thread's own 32 accD columns: the A operand of X(c)
+        tc_fence_after();
         tmem_st_32x16(tmem_base + tm_lane + COL_AD + b * HC + half * 32, dw);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_HREADY + b));
-        // h2, then dhpre, through the one staging tile to global
-        uint8_t* st = sptr + OFF_STG + row * 128;
+        // h2 and dhpre to global through their staging tiles (the store warp drains them while the next chunk is computed)
 #pragma unroll
-        for (int which = 0; which < 2; ++which, ++stg) {
-          mbar_wait_guard(bar(B_STGFREE), (stg & 1) ^ 1);
+        for (int which = 0; which < 2; ++which) {
+          mbar_wait_guard(bar(B_STGFREE + which), (g & 1) ^ 1);
+          uint8_t* st = sptr + OFF_STG + which * (TM * HC * 2) + row * 128;
           const uint32_t* src = which ? dw : hw;
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4)
             *reinterpret_cast<uint4*>(st + ((((uint32_t)(half * 4 + q4)) ^ sw) << 4)) = make_uint4(src[4 * q4], src[4 * q4 + 1], src[4 * q4 + 2], src[4 * q4 + 3]);
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar(B_STGFULL));
+          if (lane == 0) mbar_arrive(bar(B_STGFULL + which));
         }
       }
-      // ---- LayerNorm backward: dx = dY + rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)) ----
+      // ---- LayerNorm backward: dx = dY + rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)), staged over dY in place ----
       {
         mbar_wait_guard(bar(B_ACC3FULL), j & 1);
         tc_fence_after();
-        uint8_t* xb = sptr + OFF_X;
-        const uint8_t* yb = sptr + OFF_DY;
+        uint8_t* yb = sptr + OFF_DY;
+        uint32_t xh[48];                                      // this thread's xhat (bf16 pairs) back from tensor memory
+#pragma unroll
+        for (int t3 = 0; t3 < 3; ++t3) {
+          uint32_t w16[16];
+          tmem_ld_32x16(tmem_base + tm_lane + COL_XN + half * 48 + t3 * 16, w16);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) xh[t3 * 16 + i] = w16[i];
+        }
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int g3 = 0; g3 < 3; ++g3) {
@@ -318,16 +365,11 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           tmem_ld_32x32(tmem_base + tm_lane + COL_A3 + col0 + g3 * 32, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int col = col0 + g3 * 32 + 8 * i, kb = col >> 6, c8 = (col & 63) >> 3;
-            const uint4 xv = *reinterpret_cast<const uint4*>(xb + kb * KBLK + row * 128 + ((((uint32_t)c8) ^ sw) << 4));
-            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float d0 = __uint_as_float(r[8 * i + 2 * e]), d1 = __uint_as_float(r[8 * i + 2 * e + 1]);
-              s1 += d0 + d1;
-              s2 = fmaf(d0, bf16_lo(xw[e]), fmaf(d1, bf16_hi(xw[e]), s2));
-            }
+          for (int i = 0; i < 16; ++i) {
+            const float d0 = __uint_as_float(r[2 * i]), d1 = __uint_as_float(r[2 * i + 1]);
+            const uint32_t xw = xh[g3 * 16 + i];
+            s1 += d0 + d1;
+            s2 = fmaf(d0, bf16_lo(xw), fmaf(d1, bf16_hi(xw), s2));
           }
         }
         part[row * 2 + half] = make_float2(s1, s2);
@@ -342,29 +384,29 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           if (g3 == 2) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(B_ACC3FREE));      // accumulator drained: the next tile's X(0) may overwrite it
+            if (lane == 0) mbar_arrive(bar(B_ACC3FREE));      // accumulator (and XN) drained: the next tile may overwrite them
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int col = col0 + g3 * 32 + 8 * i, kb = col >> 6, c8 = (col & 63) >> 3;
             const uint32_t off = kb * KBLK + row * 128 + ((((uint32_t)c8) ^ sw) << 4);
-            const uint4 xv = *reinterpret_cast<const uint4*>(xb + off);
             const uint4 yv = *reinterpret_cast<const uint4*>(yb + off);
-            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, yw[4] = {yv.x, yv.y, yv.z, yv.w};
+            const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
             uint32_t ow[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
+              const uint32_t xw = xh[g3 * 16 + 4 * i + e];
               const float d0 = __uint_as_float(r[8 * i + 2 * e]), d1 = __uint_as_float(r[8 * i + 2 * e + 1]);
-              const float o0 = fmaf(rstd, d0 - m1 - bf16_lo(xw[e]) * m2, bf16_lo(yw[e]));
-              const float o1 = fmaf(rstd, d1 - m1 - bf16_hi(xw[e]) * m2, bf16_hi(yw[e]));
+              const float o0 = fmaf(rstd, d0 - m1 - bf16_lo(xw) * m2, bf16_lo(yw[e]));
+              const float o1 = fmaf(rstd, d1 - m1 - bf16_hi(xw) * m2, bf16_hi(yw[e]));
               ow[e] = pack_bf16(o0, o1);
             }
-            *reinterpret_cast<uint4*>(xb + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);     // dx staged over xhat, in place
+            *reinterpret_cast<uint4*>(yb + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);     // dx staged over dY, in place
           }
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) { mbar_arrive(bar(B_DYFREE)); mbar_arrive(bar(B_OUTREADY)); }
+        if (lane == 0) mbar_arrive(bar(B_OUTREADY));
         asm volatile("bar.sync 1, 256;" ::: "memory");        // `part` reuse safety
       }
     }
