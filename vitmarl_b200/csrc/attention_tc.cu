@@ -64,6 +64,7 @@ struct AttnTcParams {
   int tiles;      // 128-token row tiles (ceil(B / 2))
   int heads;
   int D;
+  float* dbqkv;   // backward: [3 D] += column sums of dqkv (nullable)
 };
 
 __global__ void __launch_bounds__(atf::THREADS, 1)
@@ -251,7 +252,8 @@ constexpr int OFF_P = OFF_RING + NST * STAGE_BYTES;     // P  [128 i x 128 j] bf
 constexpr int OFF_DS = OFF_P + 2 * TILE;                // dz [128 i x 128 j] bf16;                       later the dQ | dK staging tiles
 constexpr int OFF_BAR = OFF_DS + 2 * TILE;
 constexpr int OFF_MISC = OFF_BAR + 256;
-constexpr int MISC_BYTES = 128 * 2 * 8 + 128 * 2 * 4;   // (max, sum) partials [128][2] float2, delta partials [128][2] float
+constexpr int MAX_HEADS_CS = 8;                         // bias-gradient column sums are kept per CTA for up to 8 heads (ViT-Tiny 3, ViT-S 6)
+constexpr int MISC_BYTES = 128 * 2 * 8 + 128 * 2 * 4 + MAX_HEADS_CS * 192 * 4;   // (max, sum) partials, delta partials, column sums [heads][dq|dk|dv][64]
 constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;
 constexpr int W_LOAD = 0, W_MMA = 1, W_STORE = 2, W_C0 = 4, N_C = 12;    // 12 compute warps: softmax-backward on 8 of them, gradient epilogues on all
 constexpr int THREADS = 32 * (W_C0 + N_C);         // 512
@@ -272,6 +274,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
   float2* sm_part = reinterpret_cast<float2*>(sptr + OFF_MISC);
   float* dl_part = reinterpret_cast<float*>(sptr + OFF_MISC + 128 * 2 * 8);
+  float* s_cs = dl_part + 128 * 2;                                                  // [heads][3][64]
+  const bool want_cs = p.dbqkv != nullptr && p.heads <= MAX_HEADS_CS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int items = p.tiles * p.heads;
@@ -286,6 +290,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     fence_mbar_init();
   }
   if (warp == W_MMA) tmem_alloc<TMEM_COLS>(bar(B_TMEMSLOT));
+  for (int i = threadIdx.x; i < MAX_HEADS_CS * 192; i += THREADS) s_cs[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -461,6 +466,24 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_STAGED));
+      if (want_cs) {
+        // QKV bias gradient: column sums over the warp's 32 token rows (transposing butterfly), per CTA in shared memory
+        const int h = item_of(n) % p.heads;
+        float cs[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cs[i] = __uint_as_float(r0[i]);
+        atomicAdd(&s_cs[(h * 3 + grp) * 64 + lane], warp_colsum32(cs, lane));
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cs[i] = __uint_as_float(r1[i]);
+        atomicAdd(&s_cs[(h * 3 + grp) * 64 + 32 + lane], warp_colsum32(cs, lane));
+      }
+    }
+    if (want_cs) {
+      asm volatile("bar.sync 3, 384;" ::: "memory");         // the 12 compute warps
+      for (int i = threadIdx.x - W_C0 * 32; i < p.heads * 192; i += N_C * 32) {
+        const int h = i / 192, part = (i % 192) / 64, c = i % 64;
+        atomicAdd(p.dbqkv + part * p.D + h * 64 + c, s_cs[i]);
+      }
     }
   }
   tc_fence_before();
@@ -486,7 +509,7 @@ int launch_attention(cudaStream_t s, const __nv_bfloat16* qkv, __nv_bfloat16* ou
   CUtensorMap tmQKV, tmOut;
   if ((rc = make_tmap_2d_bf16(&tmQKV, qkv, M, 3 * D, (uint64_t)3 * D * 2, TM, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmOut, out, M, D, (uint64_t)D * 2, TM, 64))) return rc;
-  AttnTcParams p{(M + TM - 1) / TM, heads, D};
+  AttnTcParams p{(M + TM - 1) / TM, heads, D, nullptr};
   cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return check_cuda(e);
   const int grid = min(p.tiles * heads, num_sms());
@@ -495,7 +518,7 @@ int launch_attention(cudaStream_t s, const __nv_bfloat16* qkv, __nv_bfloat16* ou
 }
 
 // qkv, dout [B*64, D] -> dqkv [B*64, 3*D]
-int launch_attention_bwd(cudaStream_t s, const __nv_bfloat16* qkv, const __nv_bfloat16* dout, __nv_bfloat16* dqkv, int B, int heads) {
+int launch_attention_bwd(cudaStream_t s, const __nv_bfloat16* qkv, const __nv_bfloat16* dout, __nv_bfloat16* dqkv, int B, int heads, float* dbqkv) {
   using namespace atb;
   int rc = attn_check(B, heads);
   if (rc || B == 0) return rc;
@@ -504,12 +527,14 @@ int launch_attention_bwd(cudaStream_t s, const __nv_bfloat16* qkv, const __nv_bf
   if ((rc = make_tmap_2d_bf16(&tmQKV, qkv, M, 3 * D, (uint64_t)3 * D * 2, TM, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmDO, dout, M, D, (uint64_t)D * 2, TM, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmDQKV, dqkv, M, 3 * D, (uint64_t)3 * D * 2, TM, 64))) return rc;
-  AttnTcParams p{(M + TM - 1) / TM, heads, D};
+  AttnTcParams p{(M + TM - 1) / TM, heads, D, heads <= MAX_HEADS_CS ? dbqkv : nullptr};
   cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return check_cuda(e);
   const int grid = min(p.tiles * heads, num_sms());
   attn_tc_bwd_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(tmQKV, tmDO, tmDQKV, p);
-  return check_cuda(cudaGetLastError());
+  if ((rc = check_cuda(cudaGetLastError()))) return rc;
+  if (dbqkv && heads > MAX_HEADS_CS) return launch_colsum(s, dqkv, dbqkv, M, 3 * D);     // beyond the per-CTA table: a separate pass
+  return VITMARL_OK;
 }
 
 }  // namespace vitmarl

@@ -53,7 +53,7 @@ constexpr int OFF_W1 = OFF_DY + X_BYTES;
 constexpr int OFF_W2 = OFF_W1 + NS1 * W1_BYTES;
 constexpr int OFF_BAR = OFF_W2 + NS2 * W2_BYTES;
 constexpr int OFF_MISC = OFF_BAR + 256;
-constexpr int MISC_BYTES = 128 * 2 * 8 + HID * 2;  // row partials [128][2] float2, b1' (bf16)
+constexpr int MISC_BYTES = 128 * 2 * 8 + HID * 2 + (HID + D) * 4;  // row partials [128][2] float2, b1' (bf16), column sums of dhpre [HID] and dx [D] (fp32)
 constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;
 constexpr int W_LOAD = 0, W_MMA = 1, W_WRING = 2, W_STORE = 3, W_E0 = 4, N_E = 8;
 constexpr int THREADS = 32 * (W_E0 + N_E);         // 384
@@ -70,6 +70,8 @@ struct FusedMlpBwdParams {
   int M;
   const uint16_t* b1p;          // [HID] folded FC1 bias, bf16
   float eps;
+  float* dbf;                   // [HID] += column sums of dhpre  (gradient of the folded FC1 bias; nullable)
+  float* dbx;                   // [D]   += column sums of dx     (the bias gradient of whatever produced this block's input; nullable)
 };
 
 __global__ void __launch_bounds__(fmb::THREADS, 1)
@@ -83,6 +85,7 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
   float2* part = reinterpret_cast<float2*>(sptr + OFF_MISC);                       // [128][2]
   uint16_t* s_b1 = reinterpret_cast<uint16_t*>(sptr + OFF_MISC + 128 * 2 * 8);     // [HID] bf16
+  float* s_cs = reinterpret_cast<float*>(sptr + OFF_MISC + 128 * 2 * 8 + HID * 2);  // [HID + D] per-CTA column sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (p.M + TM - 1) / TM;
@@ -104,6 +107,7 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   }
   if (warp == W_MMA) tmem_alloc<TMEM_COLS>(bar(B_TMEMSLOT));
   for (int i = threadIdx.x; i < HID; i += THREADS) s_b1[i] = p.b1p[i];
+  for (int i = threadIdx.x; i < HID + D; i += THREADS) s_cs[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -217,15 +221,20 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         bulk_commit();
         bulk_wait_read0();
         mbar_arrive(bar(B_XSTORED));                          // the x tile is dead: its memory becomes the two staging tiles
+        // rolling hand-over: a store stays in flight while the next staging tile is awaited; a tile is handed back as soon as
+        // the store issued before the newest one has read it (cp.async.bulk.wait_group.read 1)
+        int pending = -1;                                     // staging tile of the newest store whose read is not yet confirmed
         for (int c = 0; c < NCHUNK; ++c, ++g) {
           for (int which = 0; which < 2; ++which) {
             mbar_wait_guard(bar(B_STGFULL + which), g & 1);
             tma_store_2d(which ? &tmDH : &tmH, sbase + OFF_STG + which * (TM * HC * 2), c * HC, tile_row(j));
             bulk_commit();
-            bulk_wait_read0();
-            mbar_arrive(bar(B_STGFREE + which));
+            if (pending >= 0) { bulk_wait_read1(); mbar_arrive(bar(B_STGFREE + pending)); }
+            pending = which;
           }
         }
+        bulk_wait_read0();
+        mbar_arrive(bar(B_STGFREE + pending));
         mbar_arrive(bar(B_XFREE));                             // staging tiles read: the next tile's x may land
         mbar_wait_guard(bar(B_OUTREADY), j & 1);
         for (int kb = 0; kb < KB_X; ++kb) tma_store_2d(&tmDX, sbase + OFF_DY + kb * KBLK, kb * 64, tile_row(j));
@@ -305,6 +314,7 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         if (lane == 0) mbar_arrive(bar(B_A1FREE));            // acc1 drained: FC1 of the next chunk may overwrite it
         const uint32_t* bias = reinterpret_cast<const uint32_t*>(s_b1 + c * HC + half * 32);
         uint32_t hw[16], dw[16];
+        float dcs[32];                                        // this row's dhpre (fp32) for the bias-gradient column sums
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const uint32_t bw = bias[i];
@@ -322,6 +332,7 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           }
           hw[i] = pack_bf16(h[0], h[1]);
           dw[i] = pack_bf16(d[0], d[1]);
+          dcs[2 * i] = d[0]; dcs[2 * i + 1] = d[1];
         }
         // dhpre (bf16 pairs) over the first 16 of this thread's own 32 accD columns: the A operand of X(c)
         tc_fence_after();
@@ -330,6 +341,8 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_HREADY + b));
+        // db1' : column sums of dhpre over the warp's 32 rows (transposing butterfly), accumulated per CTA in shared memory
+        if (p.dbf) atomicAdd(&s_cs[c * HC + half * 32 + lane], warp_colsum32(dcs, lane));
         // h2 and dhpre to global through their staging tiles (the store warp drains them while the next chunk is computed)
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
@@ -386,6 +399,7 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_ACC3FREE));      // accumulator (and XN) drained: the next tile may overwrite them
           }
+          float ocs[32];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int col = col0 + g3 * 32 + 8 * i, kb = col >> 6, c8 = (col & 63) >> 3;
@@ -400,15 +414,24 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
               const float o0 = fmaf(rstd, d0 - m1 - bf16_lo(xw) * m2, bf16_lo(yw[e]));
               const float o1 = fmaf(rstd, d1 - m1 - bf16_hi(xw) * m2, bf16_hi(yw[e]));
               ow[e] = pack_bf16(o0, o1);
+              ocs[8 * i + 2 * e] = o0; ocs[8 * i + 2 * e + 1] = o1;
             }
             *reinterpret_cast<uint4*>(yb + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);     // dx staged over dY, in place
           }
+          if (p.dbx) atomicAdd(&s_cs[HID + col0 + g3 * 32 + lane], warp_colsum32(ocs, lane));
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_OUTREADY));
         asm volatile("bar.sync 1, 256;" ::: "memory");        // `part` reuse safety
       }
+    }
+    // per-CTA column sums -> global (one fp32 reduction per column per CTA)
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (nt > 0) {
+      const int t = threadIdx.x - W_E0 * 32;
+      if (p.dbf) for (int i = t; i < HID; i += N_E * 32) atomicAdd(p.dbf + i, s_cs[i]);
+      if (p.dbx) for (int i = t; i < D; i += N_E * 32) atomicAdd(p.dbx + i, s_cs[HID + i]);
     }
   }
   tc_fence_before();
@@ -462,9 +485,11 @@ bool fused_mlp_bwd_supported(int D, int hidden) { return D == fmb::D && hidden =
 
 // x, dy [M, D] bf16;  w1f [HID, D] bf16 folded, b1p [HID] bf16 folded, w2h [D, HID] bf16 = W2 / 2  (vit_fold.cu)
 // outputs: xhat [M, D], h2 [M, HID] (= 2 gelu(hpre)), dh [M, HID] (= d hpre), dx [M, D]   (dx may alias dy: each tile's dy is read before its dx is written)
+// dbf [HID] += column sums of dh, dbx [D] += column sums of dx (fp32, nullable): the two bias gradients that would otherwise each cost
+// a pass over a [M, .] gradient
 int launch_fused_mlp_bwd(cudaStream_t stream, const __nv_bfloat16* x, const __nv_bfloat16* dy, const __nv_bfloat16* w1f, const __nv_bfloat16* b1p,
                          const __nv_bfloat16* w2h, __nv_bfloat16* xhat, __nv_bfloat16* h2, __nv_bfloat16* dh, __nv_bfloat16* dx, int M, int D,
-                         int hidden, float eps) {
+                         int hidden, float eps, float* dbf, float* dbx) {
   using namespace fmb;
   if (D != fmb::D || hidden != HID) { set_last_error("fused_mlp_bwd: only D=192, hidden=768"); return VITMARL_EINVAL; }
   if (M <= 0) return VITMARL_OK;
@@ -478,7 +503,7 @@ int launch_fused_mlp_bwd(cudaStream_t stream, const __nv_bfloat16* x, const __nv
   if ((rc = make_tmap_2d_bf16(&tmDH, dh, M, HID, (uint64_t)HID * 2, TM, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmW1, w1f, HID, D, (uint64_t)D * 2, HC, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmW2, w2h, fmb::D, HID, (uint64_t)HID * 2, fmb::D, 64))) return rc;
-  FusedMlpBwdParams p{M, reinterpret_cast<const uint16_t*>(b1p), eps};
+  FusedMlpBwdParams p{M, reinterpret_cast<const uint16_t*>(b1p), eps, dbf, dbx};
   cudaError_t e = cudaFuncSetAttribute(fused_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return check_cuda(e);
   const int tiles = (M + TM - 1) / TM;

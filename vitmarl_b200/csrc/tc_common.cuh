@@ -345,6 +345,22 @@ __device__ __forceinline__ uint32_t norm_bf16x2(uint32_t w, uint32_t rstd_b, flo
   return pack_bf16(a, b);
 }
 
+// Column sums over the 32 lanes of a warp for 32 per-lane values (lane = row, v[i] = column i): a transposing butterfly --
+// 31 shuffles + 31 adds instead of 32 x 5; afterwards lane l holds sum_rows v[l] in v[0].
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float keep = up ? v[i + s] : v[i];
+      const float send = up ? v[i] : v[i + s];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 #endif  // __CUDACC__

@@ -362,12 +362,15 @@ static int vit_backward(cudaStream_t st, const RunOpts& o, const Dims& d, const 
       float* dwf = reinterpret_cast<float*>(ws + w.dwf);
       float* dbf = dwf + (size_t)H * D;
       auto FWl = [&](size_t off) { return reinterpret_cast<bf16*>(ws + w.fold + (size_t)l * w.sz_fold + off); };
+      { cudaError_t e = cudaMemsetAsync(dwf, 0, ((size_t)H * D + H) * sizeof(float), st); if (e != cudaSuccess) return check_cuda(e); }
+      // (the kernel also reduces two bias gradients while the tiles are on chip: db1' = column sums of dhpre, and the output-
+      // projection bias gradient = column sums of dXM -- neither costs a pass over a [tokens, .] gradient any more)
       VM_TRY(timed(st, o, CAT_FUSED_MLP, 6.0 * M * D * H, [&] {
-        return launch_fused_mlp_bwd(st, XM(l), dA, FWl(w.f_w1), FWl(w.f_b1), FWl(w.f_w2), bxhat, bh2, bdh, dB, M, D, H, d.eps);
+        return launch_fused_mlp_bwd(st, XM(l), dA, FWl(w.f_w1), FWl(w.f_b1), FWl(w.f_w2), bxhat, bh2, bdh, dB, M, D, H, d.eps, dbf,
+                                    G(p_layer(l, L_OUT_B)));
       }));
       VM_TRY(dW(G(p_layer(l, L_FC2_W)), G(p_layer(l, L_FC2_B)), dA, D, bh2, H, 0.5f));       // h2 = 2 gelu(hpre)
-      { cudaError_t e = cudaMemsetAsync(dwf, 0, ((size_t)H * D + H) * sizeof(float), st); if (e != cudaSuccess) return check_cuda(e); }
-      VM_TRY(dW(dwf, dbf, bdh, H, bxhat, D));                                                  // gradients w.r.t. the FOLDED W1' / b1'
+      VM_TRY(dW(dwf, nullptr, bdh, H, bxhat, D));                                              // gradient w.r.t. the FOLDED W1'
       VM_TRY(timed(st, o, CAT_OTHER, 0, [&] {
         return launch_unfold_grads(st, H, D, 1.0f, PB(p_layer(l, L_FC1_W)), PF(p_layer(l, L_LN2_G)), PF(p_layer(l, L_LN2_B)), dwf, dbf, G(p_layer(l, L_FC1_W)),
                                    G(p_layer(l, L_FC1_B)), G(p_layer(l, L_LN2_G)), G(p_layer(l, L_LN2_B)));
@@ -380,10 +383,11 @@ static int vit_backward(cudaStream_t st, const RunOpts& o, const Dims& d, const 
     VM_TRY(timed(st, o, CAT_LAYERNORM, 0, [&] { return launch_layernorm_bwd(st, XM(l), PF(p_layer(l, L_LN2_G)), ST2(l), dC, dA, dB, G(p_layer(l, L_LN2_G)), G(p_layer(l, L_LN2_B)), M, D); }));
     }
     // ---- attention branch: xm = x_l + out(attn(qkv(ln1(x_l))))
-    VM_TRY(dW(G(p_layer(l, L_OUT_W)), G(p_layer(l, L_OUT_B)), dB, D, ATT(l), D));
+    VM_TRY(dW(G(p_layer(l, L_OUT_W)), fused_train ? nullptr : G(p_layer(l, L_OUT_B)), dB, D, ATT(l), D));
     VM_TRY(dXg(dC, dB, D, PB(p_layer(l, L_OUT_W)), D, EPI_STORE_BF16, nullptr));
-    VM_TRY(timed(st, o, CAT_ATTENTION, 0, [&] { return launch_attention_bwd(st, QKV(l), dC, dQKV, d.B, d.heads); }));
-    VM_TRY(dW(G(p_layer(l, L_QKV_W)), G(p_layer(l, L_QKV_B)), dQKV, 3 * D, LN1(l), D));
+    // (the attention backward kernel reduces the QKV bias gradient -- column sums of dQKV -- from its gradient tiles)
+    VM_TRY(timed(st, o, CAT_ATTENTION, 0, [&] { return launch_attention_bwd(st, QKV(l), dC, dQKV, d.B, d.heads, G(p_layer(l, L_QKV_B))); }));
+    VM_TRY(dW(G(p_layer(l, L_QKV_W)), nullptr, dQKV, 3 * D, LN1(l), D));
     VM_TRY(dXg(dC, dQKV, 3 * D, PB(p_layer(l, L_QKV_W)), D, EPI_STORE_BF16, nullptr));
     VM_TRY(timed(st, o, CAT_LAYERNORM, 0, [&] { return launch_layernorm_bwd(st, X(l), PF(p_layer(l, L_LN1_G)), ST1(l), dC, dB, dA, G(p_layer(l, L_LN1_G)), G(p_layer(l, L_LN1_B)), M, D); }));
     VM_TRY(bucket_done(1 + (d.L - 1 - l)));

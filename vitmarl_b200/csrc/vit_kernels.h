@@ -56,7 +56,9 @@ int launch_layernorm_bwd(cudaStream_t s, const __nv_bfloat16* x, const float* ga
 
 // multi-head self-attention over T = 64 tokens, head dim 64: qkv [B*64, 3*D] (q | k | v, head-major) -> out [B*64, D]
 int launch_attention(cudaStream_t s, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int heads);
-int launch_attention_bwd(cudaStream_t s, const __nv_bfloat16* qkv, const __nv_bfloat16* dout, __nv_bfloat16* dqkv, int B, int heads);
+// dbqkv [3*D] fp32 (nullable): += column sums of dqkv (the QKV bias gradient), reduced inside the kernel
+int launch_attention_bwd(cudaStream_t s, const __nv_bfloat16* qkv, const __nv_bfloat16* dout, __nv_bfloat16* dqkv, int B, int heads,
+                         float* dbqkv = nullptr);
 
 // y[B,D] (fp32) = mean_t LN(x[B*T,D]); saves stats[M,2]
 int launch_final_ln_pool(cudaStream_t s, const __nv_bfloat16* x, const float* gamma, const float* beta, float* y, float* stats,
@@ -83,7 +85,7 @@ bool fused_mlp2_supported(int D, int hidden);
 // weight-gradient products) and dx [M,D] (may alias dy).
 int launch_fused_mlp_bwd(cudaStream_t stream, const __nv_bfloat16* x, const __nv_bfloat16* dy, const __nv_bfloat16* w1f, const __nv_bfloat16* b1p,
                          const __nv_bfloat16* w2h, __nv_bfloat16* xhat, __nv_bfloat16* h2, __nv_bfloat16* dh, __nv_bfloat16* dx, int M, int D,
-                         int hidden, float eps);
+                         int hidden, float eps, float* dbf, float* dbx);
 bool fused_mlp_bwd_supported(int D, int hidden);
 // gradients of folded parameters W' = c W diag(gamma), b' = c (b + W beta) back to (W, b, gamma, beta), all accumulated (+=):
 // dWf [N,K] / dbf [N] fp32 are the gradients w.r.t. W' / b' (dbf, db, dbeta may be null; gamma null = ones)
