@@ -72,7 +72,9 @@ struct FusedMlpBwdParams {
   float eps;
   float* dbf;                   // [HID] += column sums of dhpre  (gradient of the folded FC1 bias; nullable)
   float* dbx;                   // [D]   += column sums of dx     (the bias gradient of whatever produced this block's input; nullable)
+  long long* dbg;               // optional clock64 timeline of CTA 0, its second tile (null in production)
 };
+#define FMB_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && j == 1 && lane == 0) p.dbg[(slot)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(fmb::THREADS, 1)
 fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmW1,
@@ -151,11 +153,15 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       int s1f = 0, s2f = 0; uint32_t ph1f = 0, ph2f = 0;   // ring positions of the next FC1 / G
       int s1x = 0;                                          // ring position of the next X product
       uint32_t g_f = 0;                                     // global chunk counter of FC1 / G
-      auto fc1g = [&]() {
+      auto fc1g = [&](int j) {
         const uint32_t b = g_f & 1;
+        const int cc = (int)(g_f % NCHUNK);
+        FMB_STAMP(100 + 6 * cc);
         // acc1 is single-buffered: the epilogue of the previous chunk drains it first thing
         mbar_wait_guard(bar(B_A1FREE), (g_f & 1) ^ 1);
+        FMB_STAMP(101 + 6 * cc);
         mbar_wait_guard(bar(B_W1FULL + s1f), ph1f);
+        FMB_STAMP(102 + 6 * cc);
         tc_fence_after();
         const uint32_t lb1 = umma_desc_lo(sbase + OFF_W1 + s1f * W1_BYTES);
         if (elect_one()) {
@@ -168,6 +174,7 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
         __syncwarp();
         mbar_wait_guard(bar(B_W2FULL + s2f), ph2f);
+        FMB_STAMP(103 + 6 * cc);
         tc_fence_after();
         const uint32_t lay = umma_desc_lo(sbase + OFF_DY), lb2 = umma_desc_lo(sbase + OFF_W2 + s2f * W2_BYTES, 8192);
         if (elect_one()) {
@@ -190,11 +197,13 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         mbar_wait_guard(bar(B_XNREADY), j & 1);               // xhat of tile j is in tensor memory
         mbar_wait_guard(bar(B_DYFULL), j & 1);
         tc_fence_after();
-        fc1g();
+        fc1g(j);
         for (int c = 0; c < NCHUNK; ++c, ++g_x) {
-          if (c + 1 < NCHUNK) fc1g();                         // next chunk's products run under this chunk's epilogue
+          if (c + 1 < NCHUNK) fc1g(j);                        // next chunk's products run under this chunk's epilogue
           const uint32_t b = g_x & 1;
+          FMB_STAMP(104 + 6 * c);
           mbar_wait_guard(bar(B_HREADY + b), (g_x >> 1) & 1);
+          FMB_STAMP(105 + 6 * c);
           if (c == 0) mbar_wait_guard(bar(B_ACC3FREE), (j & 1) ^ 1);     // previous tile's LayerNorm-backward epilogue drained acc3
           tc_fence_after();
           const uint32_t lb = umma_desc_lo(sbase + OFF_W1 + s1x * W1_BYTES, 8192);
@@ -221,20 +230,17 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         bulk_commit();
         bulk_wait_read0();
         mbar_arrive(bar(B_XSTORED));                          // the x tile is dead: its memory becomes the two staging tiles
-        // rolling hand-over: a store stays in flight while the next staging tile is awaited; a tile is handed back as soon as
-        // the store issued before the newest one has read it (cp.async.bulk.wait_group.read 1)
-        int pending = -1;                                     // staging tile of the newest store whose read is not yet confirmed
+        // both staging tiles of a chunk are handed over together: two stores in one bulk group, handed back once both are read
         for (int c = 0; c < NCHUNK; ++c, ++g) {
-          for (int which = 0; which < 2; ++which) {
-            mbar_wait_guard(bar(B_STGFULL + which), g & 1);
-            tma_store_2d(which ? &tmDH : &tmH, sbase + OFF_STG + which * (TM * HC * 2), c * HC, tile_row(j));
-            bulk_commit();
-            if (pending >= 0) { bulk_wait_read1(); mbar_arrive(bar(B_STGFREE + pending)); }
-            pending = which;
-          }
+          mbar_wait_guard(bar(B_STGFULL + 0), g & 1);
+          mbar_wait_guard(bar(B_STGFULL + 1), g & 1);
+          tma_store_2d(&tmH, sbase + OFF_STG, c * HC, tile_row(j));
+          tma_store_2d(&tmDH, sbase + OFF_STG + TM * HC * 2, c * HC, tile_row(j));
+          bulk_commit();
+          bulk_wait_read0();
+          mbar_arrive(bar(B_STGFREE + 0));
+          mbar_arrive(bar(B_STGFREE + 1));
         }
-        bulk_wait_read0();
-        mbar_arrive(bar(B_STGFREE + pending));
         mbar_arrive(bar(B_XFREE));                             // staging tiles read: the next tile's x may land
         mbar_wait_guard(bar(B_OUTREADY), j & 1);
         for (int kb = 0; kb < KB_X; ++kb) tma_store_2d(&tmDX, sbase + OFF_DY + kb * KBLK, kb * 64, tile_row(j));
@@ -257,7 +263,9 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       float rstd;
       {
         uint8_t* xb = sptr + OFF_X;
+        if (warp == W_E0) FMB_STAMP(0);
         mbar_wait_guard(bar(B_XFULL), j & 1);
+        if (warp == W_E0) FMB_STAMP(1);
         uint4 v[12];
         float s = 0.f, q = 0.f;
 #pragma unroll
@@ -298,12 +306,14 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_XNREADY));
         asm volatile("bar.sync 1, 256;" ::: "memory");        // `part` reuse safety
-        mbar_wait_guard(bar(B_XSTORED), j & 1);               // the xhat store has read the tile: it may now be overwritten by the staging tiles
+        if (warp == W_E0) FMB_STAMP(2);
       }
       // ---- chunk epilogues ----
       for (int c = 0; c < NCHUNK; ++c, ++g) {
         const uint32_t b = g & 1;
+        if (warp == W_E0) FMB_STAMP(10 + 4 * c);
         mbar_wait_guard(bar(B_ACCFULL + b), (g >> 1) & 1);
+        if (warp == W_E0) FMB_STAMP(11 + 4 * c);
         tc_fence_after();
         uint32_t a1[32], ad[32];
         tmem_ld_32x32(tmem_base + tm_lane + COL_A1 + half * 32, a1);
@@ -341,25 +351,32 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_HREADY + b));
-        // db1' : column sums of dhpre over the warp's 32 rows (transposing butterfly), accumulated per CTA in shared memory
-        if (p.dbf) atomicAdd(&s_cs[c * HC + half * 32 + lane], warp_colsum32(dcs, lane));
-        // h2 and dhpre to global through their staging tiles (the store warp drains them while the next chunk is computed)
+        if (warp == W_E0) FMB_STAMP(12 + 4 * c);
+        // h2 and dhpre to global through their staging tiles (the store warp drains them while the next chunk is computed).
+        // The tiles alias the x tile: before the first write of a tile the xhat store must have read it.
+        if (c == 0) { mbar_wait_guard(bar(B_XSTORED), j & 1); if (warp == W_E0) FMB_STAMP(3); }
+        mbar_wait_guard(bar(B_STGFREE + 0), (g & 1) ^ 1);
+        mbar_wait_guard(bar(B_STGFREE + 1), (g & 1) ^ 1);
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
-          mbar_wait_guard(bar(B_STGFREE + which), (g & 1) ^ 1);
           uint8_t* st = sptr + OFF_STG + which * (TM * HC * 2) + row * 128;
           const uint32_t* src = which ? dw : hw;
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4)
             *reinterpret_cast<uint4*>(st + ((((uint32_t)(half * 4 + q4)) ^ sw) << 4)) = make_uint4(src[4 * q4], src[4 * q4 + 1], src[4 * q4 + 2], src[4 * q4 + 3]);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(B_STGFULL + which));
         }
+        fence_proxy_async_smem();                             // one fence for both tiles
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(bar(B_STGFULL + 0)); mbar_arrive(bar(B_STGFULL + 1)); }
+        // db1' : column sums of dhpre over the warp's 32 rows (transposing butterfly), accumulated per CTA in shared memory
+        if (p.dbf) atomicAdd(&s_cs[c * HC + half * 32 + lane], warp_colsum32(dcs, lane));
+        if (warp == W_E0) FMB_STAMP(13 + 4 * c);
       }
       // ---- LayerNorm backward: dx = dY + rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)), staged over dY in place ----
       {
+        if (warp == W_E0) FMB_STAMP(70);
         mbar_wait_guard(bar(B_ACC3FULL), j & 1);
+        if (warp == W_E0) FMB_STAMP(71);
         tc_fence_after();
         uint8_t* yb = sptr + OFF_DY;
         uint32_t xh[48];                                      // this thread's xhat (bf16 pairs) back from tensor memory
@@ -423,6 +440,7 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_OUTREADY));
+        if (warp == W_E0) FMB_STAMP(72);
         asm volatile("bar.sync 1, 256;" ::: "memory");        // `part` reuse safety
       }
     }
@@ -489,7 +507,7 @@ bool fused_mlp_bwd_supported(int D, int hidden) { return D == fmb::D && hidden =
 // a pass over a [M, .] gradient
 int launch_fused_mlp_bwd(cudaStream_t stream, const __nv_bfloat16* x, const __nv_bfloat16* dy, const __nv_bfloat16* w1f, const __nv_bfloat16* b1p,
                          const __nv_bfloat16* w2h, __nv_bfloat16* xhat, __nv_bfloat16* h2, __nv_bfloat16* dh, __nv_bfloat16* dx, int M, int D,
-                         int hidden, float eps, float* dbf, float* dbx) {
+                         int hidden, float eps, float* dbf, float* dbx, long long* dbg) {
   using namespace fmb;
   if (D != fmb::D || hidden != HID) { set_last_error("fused_mlp_bwd: only D=192, hidden=768"); return VITMARL_EINVAL; }
   if (M <= 0) return VITMARL_OK;
@@ -503,7 +521,7 @@ int launch_fused_mlp_bwd(cudaStream_t stream, const __nv_bfloat16* x, const __nv
   if ((rc = make_tmap_2d_bf16(&tmDH, dh, M, HID, (uint64_t)HID * 2, TM, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmW1, w1f, HID, D, (uint64_t)D * 2, HC, 64))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmW2, w2h, fmb::D, HID, (uint64_t)HID * 2, fmb::D, 64))) return rc;
-  FusedMlpBwdParams p{M, reinterpret_cast<const uint16_t*>(b1p), eps, dbf, dbx};
+  FusedMlpBwdParams p{M, reinterpret_cast<const uint16_t*>(b1p), eps, dbf, dbx, dbg};
   cudaError_t e = cudaFuncSetAttribute(fused_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return check_cuda(e);
   const int tiles = (M + TM - 1) / TM;

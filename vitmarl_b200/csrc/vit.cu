@@ -367,7 +367,7 @@ static int vit_backward(cudaStream_t st, const RunOpts& o, const Dims& d, const 
       // projection bias gradient = column sums of dXM -- neither costs a pass over a [tokens, .] gradient any more)
       VM_TRY(timed(st, o, CAT_FUSED_MLP, 6.0 * M * D * H, [&] {
         return launch_fused_mlp_bwd(st, XM(l), dA, FWl(w.f_w1), FWl(w.f_b1), FWl(w.f_w2), bxhat, bh2, bdh, dB, M, D, H, d.eps, dbf,
-                                    G(p_layer(l, L_OUT_B)));
+                                    G(p_layer(l, L_OUT_B)), o.fo.dbg);
       }));
       VM_TRY(dW(G(p_layer(l, L_FC2_W)), G(p_layer(l, L_FC2_B)), dA, D, bh2, H, 0.5f));       // h2 = 2 gelu(hpre)
       VM_TRY(dW(dwf, nullptr, bdh, H, bxhat, D));                                              // gradient w.r.t. the FOLDED W1'

@@ -85,7 +85,7 @@ bool fused_mlp2_supported(int D, int hidden);
 // weight-gradient products) and dx [M,D] (may alias dy).
 int launch_fused_mlp_bwd(cudaStream_t stream, const __nv_bfloat16* x, const __nv_bfloat16* dy, const __nv_bfloat16* w1f, const __nv_bfloat16* b1p,
                          const __nv_bfloat16* w2h, __nv_bfloat16* xhat, __nv_bfloat16* h2, __nv_bfloat16* dh, __nv_bfloat16* dx, int M, int D,
-                         int hidden, float eps, float* dbf, float* dbx);
+                         int hidden, float eps, float* dbf, float* dbx, long long* dbg = nullptr);
 bool fused_mlp_bwd_supported(int D, int hidden);
 // gradients of folded parameters W' = c W diag(gamma), b' = c (b + W beta) back to (W, b, gamma, beta), all accumulated (+=):
 // dWf [N,K] / dbf [N] fp32 are the gradients w.r.t. W' / b' (dbf, db, dbeta may be null; gamma null = ones)

@@ -228,7 +228,8 @@ class ViTEncoder:
         ptrs = (ctypes.c_void_p * len(packed))(*[t.data_ptr() for t in packed])
         gptrs = (ctypes.c_void_p * len(grads))(*[t.data_ptr() for t in grads])
         opt = _capi.VitOptions.defaults(fused=self.options.fused, gemm_2cta=self.options.gemm_2cta, pdl=self.options.pdl,
-                                        attn_flags=self.options.attn_flags, timing=self.options.timing)
+                                        attn_flags=self.options.attn_flags, timing=self.options.timing,
+                                        debug_timeline=self.options.debug_timeline)
         opt.accumulate = 1 if accumulate else 0
         if flat is not None:
             opt.grads_flat, opt.grads_flat_bytes = flat.data_ptr(), flat.numel() * flat.element_size()
