@@ -20,6 +20,9 @@ r = lambda i: (t[i] - t0) if t[i] else None
 print("tile: start 0, x landed", r(1), "LN done", r(2), "xhat stored", r(3))
 for c in range(12):
     print(f" c{c:2d} epi: wait_acc {r(10+4*c)} got {r(11+4*c)} hready {r(12+4*c)} staged {r(13+4*c)} | issuer: fc1g start {r(100+6*c)} a1free {r(101+6*c)} w1full {r(102+6*c)} w2full {r(103+6*c)} | X: wait_h {r(104+6*c)} go {r(105+6*c)}")
+for c in (3, 4, 8):
+    b = t[11 + 4 * c]
+    print(f" c{c} detail (from acc got): ld_done {t[200+8*c]-b} math_done {t[201+8*c]-b} st_done {t[202+8*c]-b} hready {t[12+4*c]-b} stgfree {t[203+8*c]-b} sts_done {t[204+8*c]-b} fence_done {t[205+8*c]-b} staged(+colsum) {t[13+4*c]-b}")
 print("final: wait acc3", r(70), "got", r(71), "done", r(72))
 tm = _capi.Timing(); enc.options.timing = tm.handle
 for _ in range(3):

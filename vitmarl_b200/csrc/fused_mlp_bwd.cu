@@ -24,8 +24,8 @@
 // a 2-deep W2h ring (a stage only lives until G(c) retires).  (First version: x as a shared-memory operand, ONE staging tile and a
 // 2-deep combined ring -- 0.98 ms per launch at 4096 tiles, bound by the epilogue warps waiting on the staging hand-over and by
 // the ring's chain latency.)
-// Warp roles (384 threads): 0 x / dY tile loads, 1 TMEM allocator + MMA issuer, 2 weight ring, 3 TMA stores, 4-11 epilogue
-// (thread = (token row, half)): LayerNorm, chunk epilogue on 32 of the 64 chunk columns, LayerNorm backward on 96 of 192 columns.
+// Warp roles (640 threads): 0 x / dY tile loads, 1 TMEM allocator + MMA issuer, 2 weight rings, 3 TMA stores, 4-19 epilogue
+// (thread = (token row, quarter)): LayerNorm, chunk epilogue on 16 of the 64 chunk columns, LayerNorm backward on 48 of 192 columns.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -53,10 +53,10 @@ constexpr int OFF_W1 = OFF_DY + X_BYTES;
 constexpr int OFF_W2 = OFF_W1 + NS1 * W1_BYTES;
 constexpr int OFF_BAR = OFF_W2 + NS2 * W2_BYTES;
 constexpr int OFF_MISC = OFF_BAR + 256;
-constexpr int MISC_BYTES = 128 * 2 * 8 + HID * 2 + (HID + D) * 4;  // row partials [128][2] float2, b1' (bf16), column sums of dhpre [HID] and dx [D] (fp32)
+constexpr int MISC_BYTES = 128 * 4 * 8 + HID * 2 + (HID + D) * 4;  // row partials [128][4] float2, b1' (bf16), column sums of dhpre [HID] and dx [D] (fp32)
 constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;
-constexpr int W_LOAD = 0, W_MMA = 1, W_WRING = 2, W_STORE = 3, W_E0 = 4, N_E = 8;
-constexpr int THREADS = 32 * (W_E0 + N_E);         // 384
+constexpr int W_LOAD = 0, W_MMA = 1, W_WRING = 2, W_STORE = 3, W_E0 = 4, N_E = 16;
+constexpr int THREADS = 32 * (W_E0 + N_E);         // 640
 constexpr int TMEM_COLS = 512;
 constexpr int COL_XN = 0, COL_A1 = 96, COL_AD = 160, COL_A3 = 288;   // xhat (bf16 pairs) 0..95 | acc1 96..159 | accD[2] 160..287 | acc3 288..479
 enum { B_XFULL = 0, B_DYFULL, B_XNREADY, B_XSTORED, B_XFREE, B_DYFREE, B_OUTREADY, B_ACC3FULL, B_ACC3FREE, B_A1FREE,
@@ -85,9 +85,9 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
   auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
-  float2* part = reinterpret_cast<float2*>(sptr + OFF_MISC);                       // [128][2]
-  uint16_t* s_b1 = reinterpret_cast<uint16_t*>(sptr + OFF_MISC + 128 * 2 * 8);     // [HID] bf16
-  float* s_cs = reinterpret_cast<float*>(sptr + OFF_MISC + 128 * 2 * 8 + HID * 2);  // [HID + D] per-CTA column sums
+  float2* part = reinterpret_cast<float2*>(sptr + OFF_MISC);                       // [128][4]
+  uint16_t* s_b1 = reinterpret_cast<uint16_t*>(sptr + OFF_MISC + 128 * 4 * 8);     // [HID] bf16
+  float* s_cs = reinterpret_cast<float*>(sptr + OFF_MISC + 128 * 4 * 8 + HID * 2);  // [HID + D] per-CTA column sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (p.M + TM - 1) / TM;
@@ -207,11 +207,11 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           if (c == 0) mbar_wait_guard(bar(B_ACC3FREE), (j & 1) ^ 1);     // previous tile's LayerNorm-backward epilogue drained acc3
           tc_fence_after();
           const uint32_t lb = umma_desc_lo(sbase + OFF_W1 + s1x * W1_BYTES, 8192);
-          const uint32_t ta = tmem_base + COL_AD + b * HC;     // dhpre packed: K step kk -> columns (kk >> 1) * 32 + (kk & 1) * 8
+          const uint32_t ta = tmem_base + COL_AD + b * HC;     // dhpre packed: K step kk (16 hidden units) -> the first 8 columns of quarter kk
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              umma_bf16_ts(tmem_base + COL_A3, ta + (kk >> 1) * 32 + (kk & 1) * 8, umma_desc_from_lo(lb + kk * 128), id_x, (c | kk) ? 1u : 0u);
+              umma_bf16_ts(tmem_base + COL_A3, ta + kk * 16, umma_desc_from_lo(lb + kk * 128), id_x, (c | kk) ? 1u : 0u);
             umma_commit(bar(B_W1EMPTY + s1x));
             if (c == NCHUNK - 1) umma_commit(bar(B_ACC3FULL));
           }
@@ -251,12 +251,14 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       bulk_wait0();
     }
   } else if (warp >= W_E0) {
-    // =============================== epilogue warps: thread = (token row, half) ===============================
-    const int quad = warp & 3, half = (warp - W_E0) >> 2;
+    // =============================== epilogue warps: thread = (token row, quarter) ===============================
+    // 16 warps (4 per scheduler): the chunk epilogue is ~800 instructions per 32 elements, and with 8 warps it ran at ~0.6 IPC
+    // per scheduler (2 750 cycles per chunk, the kernel's critical path)
+    const int quad = warp & 3, qt = (warp - W_E0) >> 2;       // TMEM lane quadrant; column quarter
     const int row = quad * 32 + lane;
     const uint32_t tm_lane = (uint32_t)(quad * 32) << 16;
     const uint32_t sw = (uint32_t)(row & 7);
-    const int col0 = half * 96;
+    const int col0 = qt * 48;                                  // LayerNorm / LayerNorm-backward columns of this thread
     uint32_t g = 0;
     for (int j = 0; j < nt; ++j) {
       // ---- LayerNorm (scale / shift folded into W1' / b1'): x -> xhat in place (for the store) and into tensor memory (FC1's A operand) ----
@@ -266,67 +268,68 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         if (warp == W_E0) FMB_STAMP(0);
         mbar_wait_guard(bar(B_XFULL), j & 1);
         if (warp == W_E0) FMB_STAMP(1);
-        uint4 v[12];
+        uint4 v[6];
         float s = 0.f, q = 0.f;
 #pragma unroll
-        for (int i = 0; i < 12; ++i) {
+        for (int i = 0; i < 6; ++i) {
           const int col = col0 + i * 8, kb = col >> 6, c8 = (col & 63) >> 3;
           v[i] = *reinterpret_cast<const uint4*>(xb + kb * KBLK + row * 128 + ((c8 ^ sw) << 4));
           stats_bf16x2(v[i].x, s, q); stats_bf16x2(v[i].y, s, q); stats_bf16x2(v[i].z, s, q); stats_bf16x2(v[i].w, s, q);
         }
-        part[row * 2 + half] = make_float2(s, q);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float2 o = part[row * 2 + (half ^ 1)];
-        s += o.x; q += o.y;
+        part[row * 4 + qt] = make_float2(s, q);
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+#pragma unroll
+        for (int k = 1; k < 4; ++k) { const float2 o = part[row * 4 + ((qt + k) & 3)]; s += o.x; q += o.y; }
         const float mean = s * (1.0f / D);
         const float var = fmaxf(q * (1.0f / D) - mean * mean, 0.f);
         const uint32_t rstd_b = pack_bf16(rsqrtf(var + p.eps), 0.f);      // (the forward normalises with the bf16-rounded rstd)
         rstd = bf16_lo(rstd_b);
         const float nmr = -mean * rstd;
-        uint32_t w[48];
+        uint32_t w[24];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) {
+        for (int i = 0; i < 6; ++i) {
           const int col = col0 + i * 8, kb = col >> 6, c8 = (col & 63) >> 3;
           v[i].x = norm_bf16x2(v[i].x, rstd_b, nmr); v[i].y = norm_bf16x2(v[i].y, rstd_b, nmr);
           v[i].z = norm_bf16x2(v[i].z, rstd_b, nmr); v[i].w = norm_bf16x2(v[i].w, rstd_b, nmr);
           *reinterpret_cast<uint4*>(xb + kb * KBLK + row * 128 + ((c8 ^ sw) << 4)) = v[i];
           w[4 * i] = v[i].x; w[4 * i + 1] = v[i].y; w[4 * i + 2] = v[i].z; w[4 * i + 3] = v[i].w;
         }
-        // xhat as bf16 pairs: columns col0/2 .. col0/2 + 48 of XN (the previous tile's FC1 products retired before its ACC3FULL)
+        // xhat as bf16 pairs: columns qt * 24 .. + 24 of XN (the previous tile's FC1 products retired before its ACC3FULL)
 #pragma unroll
-        for (int t3 = 0; t3 < 3; ++t3) {                      // three 16-column stores (column offsets are multiples of 16)
-          uint32_t w16[16];
+        for (int t3 = 0; t3 < 3; ++t3) {
+          uint32_t w8[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) w16[i] = w[t3 * 16 + i];
-          tmem_st_32x16(tmem_base + tm_lane + COL_XN + half * 48 + t3 * 16, w16);
+          for (int i = 0; i < 8; ++i) w8[i] = w[t3 * 8 + i];
+          tmem_st_32x8(tmem_base + tm_lane + COL_XN + qt * 24 + t3 * 8, w8);
         }
         tmem_st_wait();
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_XNREADY));
-        asm volatile("bar.sync 1, 256;" ::: "memory");        // `part` reuse safety
+        asm volatile("bar.sync 1, 512;" ::: "memory");        // `part` reuse safety
         if (warp == W_E0) FMB_STAMP(2);
       }
-      // ---- chunk epilogues ----
+      // ---- chunk epilogues: thread = (row, 16 of the chunk's 64 hidden units) ----
       for (int c = 0; c < NCHUNK; ++c, ++g) {
         const uint32_t b = g & 1;
         if (warp == W_E0) FMB_STAMP(10 + 4 * c);
         mbar_wait_guard(bar(B_ACCFULL + b), (g >> 1) & 1);
         if (warp == W_E0) FMB_STAMP(11 + 4 * c);
         tc_fence_after();
-        uint32_t a1[32], ad[32];
-        tmem_ld_32x32(tmem_base + tm_lane + COL_A1 + half * 32, a1);
-        tmem_ld_32x32(tmem_base + tm_lane + COL_AD + b * HC + half * 32, ad);
+        uint32_t a1[16], ad[16];
+        tmem_ld_32x16(tmem_base + tm_lane + COL_A1 + qt * 16, a1);
+        tmem_ld_32x16(tmem_base + tm_lane + COL_AD + b * HC + qt * 16, ad);
         tmem_ld_wait();
+        if (warp == W_E0) FMB_STAMP(200 + 8 * c);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_A1FREE));            // acc1 drained: FC1 of the next chunk may overwrite it
-        const uint32_t* bias = reinterpret_cast<const uint32_t*>(s_b1 + c * HC + half * 32);
-        uint32_t hw[16], dw[16];
-        float dcs[32];                                        // this row's dhpre (fp32) for the bias-gradient column sums
+        const uint32_t* bias = reinterpret_cast<const uint32_t*>(s_b1 + c * HC + qt * 16);
+        uint32_t hw[8], dw[8];
+        float dcs[16];                                        // this row's dhpre (fp32) for the bias-gradient column sums
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
           const uint32_t bw = bias[i];
           float h[2], d[2];
 #pragma unroll
@@ -344,10 +347,12 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           dw[i] = pack_bf16(d[0], d[1]);
           dcs[2 * i] = d[0]; dcs[2 * i + 1] = d[1];
         }
-        // dhpre (bf16 pairs) over the first 16 of this thread's own 32 accD columns: the A operand of X(c)
+        // dhpre (bf16 pairs) over the first 8 of this thread's own 16 accD columns: K step `qt` of the A operand of X(c)
+        if (warp == W_E0) FMB_STAMP(201 + 8 * c);
         tc_fence_after();
-        tmem_st_32x16(tmem_base + tm_lane + COL_AD + b * HC + half * 32, dw);
+        tmem_st_32x8(tmem_base + tm_lane + COL_AD + b * HC + qt * 16, dw);
         tmem_st_wait();
+        if (warp == W_E0) FMB_STAMP(202 + 8 * c);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_HREADY + b));
@@ -357,19 +362,25 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         if (c == 0) { mbar_wait_guard(bar(B_XSTORED), j & 1); if (warp == W_E0) FMB_STAMP(3); }
         mbar_wait_guard(bar(B_STGFREE + 0), (g & 1) ^ 1);
         mbar_wait_guard(bar(B_STGFREE + 1), (g & 1) ^ 1);
+        if (warp == W_E0) FMB_STAMP(203 + 8 * c);
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
           uint8_t* st = sptr + OFF_STG + which * (TM * HC * 2) + row * 128;
           const uint32_t* src = which ? dw : hw;
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)
-            *reinterpret_cast<uint4*>(st + ((((uint32_t)(half * 4 + q4)) ^ sw) << 4)) = make_uint4(src[4 * q4], src[4 * q4 + 1], src[4 * q4 + 2], src[4 * q4 + 3]);
+          for (int q2 = 0; q2 < 2; ++q2)
+            *reinterpret_cast<uint4*>(st + ((((uint32_t)(qt * 2 + q2)) ^ sw) << 4)) = make_uint4(src[4 * q2], src[4 * q2 + 1], src[4 * q2 + 2], src[4 * q2 + 3]);
         }
+        if (warp == W_E0) FMB_STAMP(204 + 8 * c);
         fence_proxy_async_smem();                             // one fence for both tiles
+        if (warp == W_E0) FMB_STAMP(205 + 8 * c);
         __syncwarp();
         if (lane == 0) { mbar_arrive(bar(B_STGFULL + 0)); mbar_arrive(bar(B_STGFULL + 1)); }
         // db1' : column sums of dhpre over the warp's 32 rows (transposing butterfly), accumulated per CTA in shared memory
-        if (p.dbf) atomicAdd(&s_cs[c * HC + half * 32 + lane], warp_colsum32(dcs, lane));
+        if (p.dbf) {
+          const float cs = warp_colsum16(dcs, lane);
+          if (lane < 16) atomicAdd(&s_cs[c * HC + qt * 16 + lane], cs);
+        }
         if (warp == W_E0) FMB_STAMP(13 + 4 * c);
       }
       // ---- LayerNorm backward: dx = dY + rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)), staged over dY in place ----
@@ -379,54 +390,55 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         if (warp == W_E0) FMB_STAMP(71);
         tc_fence_after();
         uint8_t* yb = sptr + OFF_DY;
-        uint32_t xh[48];                                      // this thread's xhat (bf16 pairs) back from tensor memory
+        uint32_t xh[24];                                      // this thread's xhat (bf16 pairs) back from tensor memory
 #pragma unroll
         for (int t3 = 0; t3 < 3; ++t3) {
-          uint32_t w16[16];
-          tmem_ld_32x16(tmem_base + tm_lane + COL_XN + half * 48 + t3 * 16, w16);
+          uint32_t w8[8];
+          tmem_ld_32x8(tmem_base + tm_lane + COL_XN + qt * 24 + t3 * 8, w8);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) xh[t3 * 16 + i] = w16[i];
+          for (int i = 0; i < 8; ++i) xh[t3 * 8 + i] = w8[i];
         }
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int g3 = 0; g3 < 3; ++g3) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + tm_lane + COL_A3 + col0 + g3 * 32, r);
+          uint32_t r[16];
+          tmem_ld_32x16(tmem_base + tm_lane + COL_A3 + col0 + g3 * 16, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < 8; ++i) {
             const float d0 = __uint_as_float(r[2 * i]), d1 = __uint_as_float(r[2 * i + 1]);
-            const uint32_t xw = xh[g3 * 16 + i];
+            const uint32_t xw = xh[g3 * 8 + i];
             s1 += d0 + d1;
             s2 = fmaf(d0, bf16_lo(xw), fmaf(d1, bf16_hi(xw), s2));
           }
         }
-        part[row * 2 + half] = make_float2(s1, s2);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float2 o = part[row * 2 + (half ^ 1)];
-        const float m1 = (s1 + o.x) * (1.0f / D), m2 = (s2 + o.y) * (1.0f / D);
+        part[row * 4 + qt] = make_float2(s1, s2);
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+#pragma unroll
+        for (int k = 1; k < 4; ++k) { const float2 o = part[row * 4 + ((qt + k) & 3)]; s1 += o.x; s2 += o.y; }
+        const float m1 = s1 * (1.0f / D), m2 = s2 * (1.0f / D);
 #pragma unroll
         for (int g3 = 0; g3 < 3; ++g3) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + tm_lane + COL_A3 + col0 + g3 * 32, r);
+          uint32_t r[16];
+          tmem_ld_32x16(tmem_base + tm_lane + COL_A3 + col0 + g3 * 16, r);
           tmem_ld_wait();
           if (g3 == 2) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_ACC3FREE));      // accumulator (and XN) drained: the next tile may overwrite them
           }
-          float ocs[32];
+          float ocs[16];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int col = col0 + g3 * 32 + 8 * i, kb = col >> 6, c8 = (col & 63) >> 3;
+          for (int i = 0; i < 2; ++i) {
+            const int col = col0 + g3 * 16 + 8 * i, kb = col >> 6, c8 = (col & 63) >> 3;
             const uint32_t off = kb * KBLK + row * 128 + ((((uint32_t)c8) ^ sw) << 4);
             const uint4 yv = *reinterpret_cast<const uint4*>(yb + off);
             const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
             uint32_t ow[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const uint32_t xw = xh[g3 * 16 + 4 * i + e];
+              const uint32_t xw = xh[g3 * 8 + 4 * i + e];
               const float d0 = __uint_as_float(r[8 * i + 2 * e]), d1 = __uint_as_float(r[8 * i + 2 * e + 1]);
               const float o0 = fmaf(rstd, d0 - m1 - bf16_lo(xw) * m2, bf16_lo(yw[e]));
               const float o1 = fmaf(rstd, d1 - m1 - bf16_hi(xw) * m2, bf16_hi(yw[e]));
@@ -435,17 +447,20 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             }
             *reinterpret_cast<uint4*>(yb + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);     // dx staged over dY, in place
           }
-          if (p.dbx) atomicAdd(&s_cs[HID + col0 + g3 * 32 + lane], warp_colsum32(ocs, lane));
+          if (p.dbx) {
+            const float cs = warp_colsum16(ocs, lane);
+            if (lane < 16) atomicAdd(&s_cs[HID + col0 + g3 * 16 + lane], cs);
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_OUTREADY));
         if (warp == W_E0) FMB_STAMP(72);
-        asm volatile("bar.sync 1, 256;" ::: "memory");        // `part` reuse safety
+        asm volatile("bar.sync 1, 512;" ::: "memory");        // `part` reuse safety
       }
     }
     // per-CTA column sums -> global (one fp32 reduction per column per CTA)
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, 512;" ::: "memory");
     if (nt > 0) {
       const int t = threadIdx.x - W_E0 * 32;
       if (p.dbf) for (int i = t; i < HID; i += N_E * 32) atomicAdd(p.dbf + i, s_cs[i]);

@@ -8,9 +8,9 @@
               (ippo_rnn_JAXMARL.py:470-475: value_and_grad per minibatch).  A minibatch = ViT forward+backward over its images
               in micro-batches whose gradients ACCUMULATE in the flat fp32 table inside the library (no eager add/copy
               kernels), then the pmean of that table (ippo_rnn_JAXMARL_pmap.py:564-565) as NCCL all-reduce(avg) on a side
-              stream, hung behind the CUDA events the last micro-batch's backward records (``pmean_groups``: 1 = one
-              collective when the last block's gradients are final -- measured best on NVLink for this 21.5 MB table, see
-              bench.py extra / DESIGN.md; 0 = one per transformer block, overlapping the rest of the backward pass).
+              stream, hung behind the CUDA events the last micro-batch's backward records (``pmean_groups``: 2 = the table in
+              two halves, the first reduced while the lower blocks are still in their backward pass -- measured best on 8 GPUs
+              for this 21.5 MB table, see bench.py extra / DESIGN.md; 0 = one per transformer block; 1 = one collective).
 
 The policy head, PPO loss and optimiser are boundary-only rows of SURVEY.md 8a (A13-A14): dL/d(encoding) is synthetic and the
 parameters are not changed, but every encoder FLOP, every byte and every collective of the iteration is there."""
@@ -27,7 +27,7 @@ __all__ = ["MappoLoop"]
 class MappoLoop:
     def __init__(self, envs_per_gpu: int = 8192, rollout_steps: int = 128, epochs: int = 4, minibatches: int = 16, micro: int = 8192,
                  msgs_per_step: int = 13, vit_cfg: vit.ViTConfig = vit.VIT_TINY_8, rank: int = 0, world: int = 1,
-                 agent_ids=(-100, -101), pmean_groups: int = 1):
+                 agent_ids=(-100, -101), pmean_groups: int = 2):
         self.E, self.S, self.M = envs_per_gpu, rollout_steps, msgs_per_step
         self.epochs, self.minibatches = epochs, minibatches
         self.world, self.rank = world, rank
@@ -121,6 +121,6 @@ class MappoLoop:
                 "envs_total": W * E, "rollout_steps": S, "epochs": self.epochs, "minibatches": self.minibatches, "micro_batch": self.micro,
                 "rollout_s": t_roll, "update_s": t_upd, "rollout_env_steps_per_sec": W * E * S / t_roll,
                 "update_images_per_sec": W * self.epochs * self.total / t_upd,
-                "collectives": self.epochs * self.minibatches * len(self.red.bucket_spans) if W > 1 else 0,
+                "collectives": self.epochs * self.minibatches * len(self.red.groups) if W > 1 else 0,
                 "grad_bytes_per_minibatch": self.red.flat.numel() * 4,
                 "note": "encoder + env + NCCL only: policy head / PPO loss / optimiser are boundary-only rows (synthetic dL/d(encoding))"}
