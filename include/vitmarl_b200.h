@@ -329,6 +329,13 @@ int vitmarl_dense_f32(void* stream, int R, int K0, int K1, int N, const float* x
 int vitmarl_gru_cell_f32(void* stream, int R, int H, const float* gi, const float* gh, const float* b_hn, const float* h,
                          const uint8_t* reset, float* h_out);
 
+/* `_calculate_gae` of the PPO trainers (ippo_rnn_JAXMARL.py:372-394), the reverse scan over the trajectory, for all B = NUM_ENVS *
+ * agents columns at once: reward / value / done [S,B] (time-major, done uint8 = transition.global_done), last_val [B] ->
+ * advantages [S,B], targets = advantages + value [S,B] (nullable).  fp32 with the reference's order of operations, no FMA
+ * contraction: bit-identical to the NumPy restatement of the scan. */
+int vitmarl_gae_f32(void* stream, int S, int B, float gamma, float gae_lambda, const float* reward, const float* value,
+                    const uint8_t* done, const float* last_val, float* advantages, float* targets);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,3 +30,22 @@ def actor_critic(p, hidden, vec, dones, enc=None):
     c = torch.relu(y @ p["Dense_3"]["kernel"] + p["Dense_3"]["bias"])
     value = (c @ p["Dense_4"]["kernel"] + p["Dense_4"]["bias"]).squeeze(-1)
     return h, logits, value
+
+
+def calculate_gae(gamma, gae_lambda, reward, value, done, last_val):
+    """NumPy float32 restatement of `_calculate_gae` (ippo_rnn_JAXMARL.py:372-394): reverse scan, the reference's order of operations.
+    reward / value [S,B] float32, done [S,B] bool, last_val [B] -> advantages, targets."""
+    import numpy as np
+    f = np.float32
+    reward, value, last_val = reward.astype(f), value.astype(f), last_val.astype(f)
+    S = reward.shape[0]
+    gae, next_value = np.zeros_like(last_val), last_val
+    adv = np.empty_like(reward)
+    gamma, lam = f(gamma), f(gae_lambda)
+    for t in range(S - 1, -1, -1):
+        nd = f(1) - done[t].astype(f)
+        delta = reward[t] + gamma * next_value * nd - value[t]
+        gae = delta + gamma * lam * nd * gae
+        adv[t] = gae
+        next_value = value[t]
+    return adv, adv + value

@@ -15,12 +15,20 @@ eng = rollout.RolloutEncoder(cfg, vcfg, params, E, M)
 eng.reset(a, b)
 stream = synth.MessageStream(E, 5)
 for _ in range(2):
-    y = eng.step(torch.from_numpy(stream.next(M)).cuda())
+    y = eng.step(torch.from_numpy(stream.next(M)).cuda(), stat_agent_ids=[-100, 1000001], keep_trades=True)
 enc = vit.ViTEncoder(vcfg)
-x = eng.last.image
+x = eng.last_image()
 enc.apply({"params": params}, x, train=True)
 g = enc.vjp({"params": params}, torch.randn(E, 192, device="cuda"), want_dx=True)
 ct = torch.zeros((E, 2), dtype=torch.int32, device="cuda")
 jaxob.getCancelMsgs(eng.state.ask_raw_orders, -2, 4, -1, ct); jaxob.get_agent_trades(eng.state.trades, 1000001)
+# unfused training path, policy head, GAE
+enc.options.fused = 0
+enc.apply({"params": params}, x, train=True); enc.vjp({"params": params}, torch.randn(E, 192, device="cuda"))
+from vitmarl_b200 import actor_critic
+net = actor_critic.ActorCriticRNN(5, {"FC_DIM_SIZE": 128, "GRU_HIDDEN_DIM": 128}, vit_cfg=vcfg)
+v = net.init(0, 7)
+net.apply(v, net.initialize_carry(E, 128), ((torch.randn(1, E, 7, device="cuda"), eng.last.image[None]), torch.zeros(1, E, dtype=torch.bool, device="cuda")))
+actor_critic.calculate_gae(0.99, 0.95, torch.randn(9, E, device="cuda"), torch.randn(9, E, device="cuda"), torch.zeros(9, E, dtype=torch.bool, device="cuda"), torch.randn(E, device="cuda"))
 torch.cuda.synchronize()
 print("sanitize run ok", float(y.abs().sum()))

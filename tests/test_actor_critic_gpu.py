@@ -61,3 +61,18 @@ def test_vision_wiring_image_and_patch_matrix():
     _, lr3, _ = PO.actor_critic(v2["params"], h0, None, dones,
                                 enc=VO.vit_forward(cfg, v2["params"]["vit"], img.reshape(S * B, cfg.img_h, cfg.img_w, cfg.channels)).reshape(S, B, cfg.dim))
     assert (logits3 - lr3).abs().max().item() <= 2e-2 * max(lr3.abs().max().item(), 1e-3)
+
+
+def test_gae_bit_exact_vs_numpy_scan():
+    """`_calculate_gae` (ippo_rnn_JAXMARL.py:372-394) for NUM_STEPS x (NUM_ENVS * agents) columns in one launch."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    S, B = 128, 777
+    reward = rng.normal(size=(S, B)).astype(np.float32)
+    value = rng.normal(size=(S, B)).astype(np.float32)
+    done = rng.random((S, B)) < 0.05
+    last_val = rng.normal(size=(B,)).astype(np.float32)
+    adv_w, tgt_w = PO.calculate_gae(0.99, 0.95, reward, value, done, last_val)
+    adv, tgt = actor_critic.calculate_gae(0.99, 0.95, torch.from_numpy(reward).cuda(), torch.from_numpy(value).cuda(),
+                                          torch.from_numpy(done).cuda(), torch.from_numpy(last_val).cuda())
+    assert adv.cpu().numpy().tobytes() == adv_w.tobytes() and tgt.cpu().numpy().tobytes() == tgt_w.tobytes()

@@ -118,6 +118,7 @@ SIGNATURES = {
     "vitmarl_attention_fwd": (_I, [_P, _I, _I, _P, _P]),
     "vitmarl_attention_bwd": (_I, [_P, _I, _I, _P, _P, _P]),
     "vitmarl_dense_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _P, _I]),
+    "vitmarl_gae_f32": (_I, [_P, _I, _I, ctypes.c_float, ctypes.c_float, _P, _P, _P, _P, _P, _P]),
     "vitmarl_gru_cell_f32": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "vitmarl_debug_gemm_dw": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _I]),
     "vitmarl_get_cancel_msgs": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _P]),

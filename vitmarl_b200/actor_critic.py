@@ -28,7 +28,7 @@ import torch
 from . import _capi
 from . import vit as vvit
 
-__all__ = ["ActorCriticRNN", "init_head_params"]
+__all__ = ["ActorCriticRNN", "init_head_params", "calculate_gae"]
 
 ACT_NONE, ACT_RELU = 0, 1
 
@@ -146,3 +146,17 @@ class ActorCriticRNN:
         c = _dense(y, f32(p["Dense_3"]["kernel"]), f32(p["Dense_3"]["bias"]), ACT_RELU)
         value = _dense(c, f32(p["Dense_4"]["kernel"]), f32(p["Dense_4"]["bias"]), ACT_NONE)
         return h.clone(), logits.reshape(S, B, -1), value.reshape(S, B)
+
+
+def calculate_gae(gamma: float, gae_lambda: float, reward: torch.Tensor, value: torch.Tensor, done: torch.Tensor, last_val: torch.Tensor):
+    """``_calculate_gae(gamma, gae_lambda, traj_batch, last_val)`` (ippo_rnn_JAXMARL.py:372-394) -> (advantages, targets), all
+    ``[S, B]`` fp32, ``done`` = ``traj_batch.global_done``.  One kernel launch for the whole reverse scan."""
+    if not reward.is_cuda:
+        raise _capi.VitmarlError(_capi.ENODEVICE, "calculate_gae needs CUDA tensors (there is no CPU fallback)")
+    S, B = reward.shape
+    r, v = reward.to(torch.float32).contiguous(), value.to(torch.float32).contiguous()
+    d, lv = done.to(torch.uint8).contiguous(), last_val.to(torch.float32).contiguous()
+    adv, tgt = torch.empty_like(r), torch.empty_like(r)
+    _capi.check(_capi.lib().vitmarl_gae_f32(torch.cuda.current_stream().cuda_stream, S, B, float(gamma), float(gae_lambda), r.data_ptr(),
+                                            v.data_ptr(), d.data_ptr(), lv.data_ptr(), adv.data_ptr(), tgt.data_ptr()))
+    return adv, tgt

@@ -87,9 +87,39 @@ __global__ void __launch_bounds__(256) gru_cell_kernel(int R, int H, const float
   h_out[i] = (1.f - zg) * ng + zg * hp;
 }
 
+// Generalised advantage estimation of the PPO trainers (`_calculate_gae`, ippo_rnn_JAXMARL.py:372-394: a reverse lax.scan over
+// NUM_STEPS): one thread per (env, agent) column walks the trajectory backwards.  Separate IEEE mul / add in the reference's
+// order of operations (no FMA contraction), so the result is bit-identical to the NumPy restatement of the scan.
+//     delta = reward + gamma * next_value * (1 - done) - value;   gae = delta + gamma * lambda * (1 - done) * gae
+__global__ void __launch_bounds__(256) gae_kernel(int S, int B, float gamma, float lambda, const float* __restrict__ reward,
+                                                  const float* __restrict__ value, const uint8_t* __restrict__ done,
+                                                  const float* __restrict__ last_val, float* __restrict__ adv, float* __restrict__ target) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float gae = 0.f, next_value = last_val[b];
+  const float gl = __fmul_rn(gamma, lambda);
+  for (int t = S - 1; t >= 0; --t) {
+    const size_t i = (size_t)t * B + b;
+    const float nd = done[i] ? 0.f : 1.f, v = value[i];
+    const float delta = __fsub_rn(__fadd_rn(reward[i], __fmul_rn(__fmul_rn(gamma, next_value), nd)), v);
+    gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nd), gae));
+    adv[i] = gae;
+    if (target) target[i] = __fadd_rn(gae, v);
+    next_value = v;
+  }
+}
+
 }  // namespace vitmarl
 
 using namespace vitmarl;
+
+extern "C" int vitmarl_gae_f32(void* stream, int S, int B, float gamma, float gae_lambda, const float* reward, const float* value,
+                               const uint8_t* done, const float* last_val, float* advantages, float* targets) {
+  if (S == 0 || B == 0) return VITMARL_OK;
+  if (S < 0 || B < 0 || !reward || !value || !done || !last_val || !advantages) return VITMARL_EINVAL;
+  gae_kernel<<<(B + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, B, gamma, gae_lambda, reward, value, done, last_val, advantages, targets);
+  return check_cuda(cudaGetLastError());
+}
 
 extern "C" int vitmarl_dense_f32(void* stream, int R, int K0, int K1, int N, const float* x0, int ldx0, const float* x1, int ldx1,
                                  const float* W, const float* bias, int act, float* y, int ldy) {
