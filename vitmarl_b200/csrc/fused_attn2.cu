@@ -105,7 +105,7 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     mbar_init(bar(B_XFULL), 1); mbar_init(bar(B_XFREE), N_CV); mbar_init(bar(B_XNREADY), N_CV); mbar_init(bar(B_XNFREE), 1);
     mbar_init(bar(B_QKVFULL), 1); mbar_init(bar(B_QKVEMPTY), N_CV); mbar_init(bar(B_QKREADY), 8); mbar_init(bar(B_VREADY), 4);
     mbar_init(bar(B_SFULL), 1); mbar_init(bar(B_PREADY), N_SM); mbar_init(bar(B_OFULL), 1); mbar_init(bar(B_OCREADY), N_OE);
-    mbar_init(bar(B_PROJFULL), 1); mbar_init(bar(B_PROJEMPTY), N_CV); mbar_init(bar(B_OUTREADY), N_CV); mbar_init(bar(B_OCFREE), 1); mbar_init(bar(B_OCDONE), N_OE); mbar_init(bar(B_SISSUED), 1);
+    mbar_init(bar(B_PROJFULL), 1); mbar_init(bar(B_PROJEMPTY), N_SM); mbar_init(bar(B_OUTREADY), N_SM); mbar_init(bar(B_OCFREE), 1); mbar_init(bar(B_OCDONE), N_OE); mbar_init(bar(B_SISSUED), 1);
     for (int i = 0; i < NSTW; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
     fence_mbar_init();
   }
@@ -351,6 +351,44 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         if (lane == 0) mbar_arrive(bar(B_PREADY));
         if (warp == W_SM0) FA2_STAMP(11 + 4 * h);
       }
+      // ---- final epilogue of tile j: out = proj + bo' (+ x when not in place), thread = (row, 96 of the 192 columns), staged over
+      //      concat(O) (dead once PROJFULL has fired), stored / reduce-added by the IO warp ----
+      {
+        const int col0 = half * 96;
+        const uint32_t sw = (uint32_t)(row & 7);
+        const int grow = tile_row(j) + row;
+        mbar_wait_guard(bar(B_PROJFULL), j & 1);
+        tc_fence_after();
+        if (warp == W_SM0) FA2_STAMP(60);
+        const uint4* gx = reinterpret_cast<const uint4*>(p.x + (size_t)grow * D + col0);
+#pragma unroll
+        for (int g3 = 0; g3 < 3; ++g3) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + tm_lane + COL_PROJ + col0 + g3 * 32, r);
+          tmem_ld_wait();
+          if (g3 == 2) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(B_PROJEMPTY));                      // accumulator drained: the next tile's S may overwrite it
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int col = col0 + g3 * 32 + 8 * i, kb = col >> 6, c8 = (col & 63) >> 3;
+            const uint4 xv = (!p.inplace && grow < p.M) ? gx[g3 * 4 + i] : make_uint4(0u, 0u, 0u, 0u);
+            const uint4 bv = *reinterpret_cast<const uint4*>(s_bo + (col >> 1));
+            uint4 ov;
+            ov.x = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(r[8 * i + 0]), __uint_as_float(r[8 * i + 1])), bv.x), xv.x);
+            ov.y = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3])), bv.y), xv.y);
+            ov.z = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5])), bv.z), xv.z);
+            ov.w = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7])), bv.w), xv.w);
+            *reinterpret_cast<uint4*>(sptr + OFF_OC + kb * KBLK + row * 128 + ((((uint32_t)c8) ^ sw) << 4)) = ov;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_OUTREADY));
+        if (warp == W_SM0) FA2_STAMP(61);
+      }
     }
   } else {
     // =============================== conversion warps (12..23): thread = (row, part) ===============================
@@ -474,50 +512,6 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       if (warp == W_CV0) FA2_STAMP(31 + 2 * h);
     };
 
-    // ---- final epilogue: out = proj + bo' + x (residual from L2), staged over concat(O) K-block `part`, stored by the IO warp ----
-    auto final_epilogue = [&](int j) {
-      const int grow = tile_row(j) + row;
-      uint4 xr[8];
-      if (!p.inplace && grow < p.M) {                       // (in place: x += delta by the TMA reduce-add store, nothing to load)
-        const uint4* gx = reinterpret_cast<const uint4*>(p.x + (size_t)grow * D + part * 64);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) xr[c] = gx[c];
-      } else {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) xr[c] = make_uint4(0u, 0u, 0u, 0u);
-      }
-      mbar_wait_guard(bar(B_PROJFULL), j & 1);
-      tc_fence_after();
-      if (warp == W_CV0) FA2_STAMP(60);
-      uint8_t* orow = sptr + OFF_OC + part * KBLK + row * 128;
-      const uint4* bo = reinterpret_cast<const uint4*>(s_bo + part * 32);   // 64 columns = 32 packed pairs = 8 uint4
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + tm_lane + COL_PROJ + part * 64 + half * 32, r);
-        tmem_ld_wait();
-        if (half == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(B_PROJEMPTY));                    // accumulator drained: the next tile's S may overwrite it
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint4 xv = xr[half * 4 + c], bv = bo[half * 4 + c];
-          uint4 ov;
-          ov.x = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1])), bv.x), xv.x);
-          ov.y = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3])), bv.y), xv.y);
-          ov.z = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5])), bv.z), xv.z);
-          ov.w = bf16x2_add(bf16x2_add(pack_bf16(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7])), bv.w), xv.w);
-          *reinterpret_cast<uint4*>(orow + ((((uint32_t)(half * 4 + c)) ^ sw) << 4)) = ov;
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_OUTREADY));
-      if (warp == W_CV0) FA2_STAMP(61);
-    };
-
     // (A version software-pipelined over tiles -- next tile's first QKV epilogue before this tile's final epilogue, next
     // LayerNorm after head 1 -- measured slower, 146 -> 171 us: it lengthens the conversion warps' serial chain.)
     if (nt > 0) layer_norm(0);
@@ -531,7 +525,9 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       if (j + 1 < nt) layer_norm(j + 1);
       if (warp == W_CV0) FA2_STAMP(50);
       o_epilogue(j, NH - 1, n - 1);
-      final_epilogue(j);
+      // (the final epilogue of the tile runs on the softmax warps, which are idle from here to the next tile's first S: the
+      // conversion warps go straight on to the next tile's first QKV epilogue -- its projection was issued before this tile's
+      // output projection -- instead of sitting ~3000 cycles in the tile-boundary critical path)
     }
   }
   tc_fence_before();
