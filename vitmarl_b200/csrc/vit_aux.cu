@@ -181,6 +181,135 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
   }
 }
 
+
+// ---------------------------------------------------------------- LayerNorm, 16-byte-load variants for D = 24 * LANES * 8
+// (D = 192: 8 lanes per row, D = 384: 16, D = 768: 32; each lane owns 3 chunks of 8 features: chunk = lane_in_group + LANES * i).
+// The warp-per-row kernels above move 4 bytes per lane per load instruction and sit at ~67 % of the HBM roofline; these issue
+// a quarter of the load instructions and keep 32 / LANES rows in flight per warp.
+template <int LANES>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = 1; o < LANES; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& w, float (&f)[8]) {
+  f[0] = bf16_lo(w.x); f[1] = bf16_hi(w.x); f[2] = bf16_lo(w.y); f[3] = bf16_hi(w.y);
+  f[4] = bf16_lo(w.z); f[5] = bf16_hi(w.z); f[6] = bf16_lo(w.w); f[7] = bf16_hi(w.w);
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(256, 2) layernorm16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                           float* __restrict__ stats, int M, float eps) {
+  constexpr int D = LANES * 24, RPW = 32 / LANES;                    // rows per warp pass
+  const int lane = threadIdx.x & 31, lg = lane % LANES, grp = lane / LANES;
+  float g[3][8], bt[3][8];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { g[i][e] = gamma[(lg + LANES * i) * 8 + e]; bt[i][e] = beta[(lg + LANES * i) * 8 + e]; }
+  const int wpb = blockDim.x >> 5;
+  for (int row = (blockIdx.x * wpb + (threadIdx.x >> 5)) * RPW + grp; row < M; row += gridDim.x * wpb * RPW) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * D);
+    float v[3][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const uint4 w = __ldg(xr + lg + LANES * i);
+      unpack8(w, v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[i][e];
+    }
+    const float mean = group_sum<LANES>(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mean; q += d * d; }
+    const float rstd = rsqrtf(group_sum<LANES>(q) * (1.0f / D) + eps);
+    uint4* yr = reinterpret_cast<uint4*>(y + (size_t)row * D);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - mean) * rstd * g[i][e] + bt[i][e];
+      yr[lg + LANES * i] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+    }
+    if (stats && lg == 0) reinterpret_cast<float2*>(stats)[row] = make_float2(mean, rstd);
+  }
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(256, 2) layernorm16_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                               const float* __restrict__ stats, const __nv_bfloat16* __restrict__ dy,
+                                                               const __nv_bfloat16* __restrict__ dx_add, __nv_bfloat16* __restrict__ dx,
+                                                               float* __restrict__ dgamma, float* __restrict__ dbeta, int M) {
+  constexpr int D = LANES * 24, RPW = 32 / LANES;
+  const int lane = threadIdx.x & 31, lg = lane % LANES, grp = lane / LANES;
+  float g[3][8], dg[3][8], db[3][8];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { g[i][e] = gamma[(lg + LANES * i) * 8 + e]; dg[i][e] = 0.f; db[i][e] = 0.f; }
+  const int wpb = blockDim.x >> 5;
+  for (int row = (blockIdx.x * wpb + (threadIdx.x >> 5)) * RPW + grp; row < M; row += gridDim.x * wpb * RPW) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * D);
+    const uint4* yr = reinterpret_cast<const uint4*>(dy + (size_t)row * D);
+    uint4 wx[3], wy[3], wa[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      wx[i] = __ldg(xr + lg + LANES * i);
+      wy[i] = __ldg(yr + lg + LANES * i);
+      wa[i] = dx_add ? __ldg(reinterpret_cast<const uint4*>(dx_add + (size_t)row * D) + lg + LANES * i) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + row);
+    float v[3][8], d[3][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      unpack8(wx[i], v[i]);
+      unpack8(wy[i], d[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        v[i][e] = (v[i][e] - st.x) * st.y;     // xhat
+        dg[i][e] += d[i][e] * v[i][e];
+        db[i][e] += d[i][e];
+        d[i][e] *= g[i][e];                    // g
+        s1 += d[i][e];
+        s2 += d[i][e] * v[i][e];
+      }
+    }
+    s1 = group_sum<LANES>(s1) * (1.0f / D);
+    s2 = group_sum<LANES>(s2) * (1.0f / D);
+    uint4* outr = reinterpret_cast<uint4*>(dx + (size_t)row * D);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float a[8], o[8];
+      unpack8(wa[i], a);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = st.y * (d[i][e] - s1 - v[i][e] * s2) + a[e];
+      outr[lg + LANES * i] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+    }
+  }
+  // block-level reduction of the column partials, then one atomic per column per CTA
+  extern __shared__ float red[];   // [2][D]
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = (lg + LANES * i) * 8 + e;
+      atomicAdd(&red[c], dg[i][e]);
+      atomicAdd(&red[D + c], db[i][e]);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    atomicAdd(dgamma + i, red[i]);
+    atomicAdd(dbeta + i, red[D + i]);
+  }
+}
+
 #define VM_DISPATCH_NP(D, CALL)                                      \
   switch ((D) / 64) {                                                \
     case 1: { constexpr int NP = 1; CALL; } break;                   \
@@ -197,6 +326,15 @@ int launch_layernorm(cudaStream_t s, const __nv_bfloat16* x, const float* gamma,
                      int M, int D, float eps) {
   if (M <= 0) return VITMARL_OK;
   if (D % 64) { set_last_error("layernorm: D % 64 != 0"); return VITMARL_EINVAL; }
+  const bool al16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  if (al16 && (D == 192 || D == 384 || D == 768)) {
+    const int lanes = D / 24, rows_per_cta = 8 * (32 / lanes);
+    const int grid16 = min((M + rows_per_cta - 1) / rows_per_cta, num_sms() * 8);
+    if (lanes == 8) layernorm16_kernel<8><<<grid16, 256, 0, s>>>(x, gamma, beta, y, stats, M, eps);
+    else if (lanes == 16) layernorm16_kernel<16><<<grid16, 256, 0, s>>>(x, gamma, beta, y, stats, M, eps);
+    else layernorm16_kernel<32><<<grid16, 256, 0, s>>>(x, gamma, beta, y, stats, M, eps);
+    return check_cuda(cudaGetLastError());
+  }
   const int grid = min((M + 7) / 8, num_sms() * 8);
   VM_DISPATCH_NP(D, (layernorm_kernel<NP><<<grid, 256, 0, s>>>(x, gamma, beta, y, stats, M, D, eps)));
   return check_cuda(cudaGetLastError());
@@ -206,6 +344,17 @@ int launch_layernorm_bwd(cudaStream_t s, const __nv_bfloat16* x, const float* ga
                          const __nv_bfloat16* dx_add, __nv_bfloat16* dx, float* dgamma, float* dbeta, int M, int D) {
   if (M <= 0) return VITMARL_OK;
   if (D % 64) return VITMARL_EINVAL;
+  const bool al16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
+                      reinterpret_cast<uintptr_t>(dx_add)) & 15) == 0;
+  if (al16 && (D == 192 || D == 384 || D == 768)) {
+    const int lanes = D / 24, rows_per_cta = 8 * (32 / lanes);
+    const int grid16 = min((M + rows_per_cta - 1) / rows_per_cta, num_sms() * 4);
+    const size_t sm = 2 * D * sizeof(float);
+    if (lanes == 8) layernorm16_bwd_kernel<8><<<grid16, 256, sm, s>>>(x, gamma, stats, dy, dx_add, dx, dgamma, dbeta, M);
+    else if (lanes == 16) layernorm16_bwd_kernel<16><<<grid16, 256, sm, s>>>(x, gamma, stats, dy, dx_add, dx, dgamma, dbeta, M);
+    else layernorm16_bwd_kernel<32><<<grid16, 256, sm, s>>>(x, gamma, stats, dy, dx_add, dx, dgamma, dbeta, M);
+    return check_cuda(cudaGetLastError());
+  }
   const int grid = min((M + 7) / 8, num_sms() * 4);
   VM_DISPATCH_NP(D, (layernorm_bwd_kernel<NP><<<grid, 256, 2 * D * sizeof(float), s>>>(x, gamma, stats, dy, dx_add, dx, dgamma, dbeta, M, D)));
   return check_cuda(cudaGetLastError());
