@@ -478,18 +478,19 @@ fused_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 // ---- unfolding the gradients of the folded parameters (vit_fold.cu): W' = c W diag(gamma), b' = c (b + W beta) ----
 //     dW[o, i] += c (gamma[i] dW'[o, i] + beta[i] db'[o]);   dgamma[i] += c sum_o dW'[o, i] W[o, i];   dbeta[i] += c sum_o db'[o] W[o, i];
 //     db[o] += c db'[o]                      (b' depends on W through W beta, hence the beta[i] db'[o] term of dW)
-// One CTA per 64-row slab of W (rows o), 256 threads: thread = (row group, column); column sums through shared memory atomics.
+// One CTA per 8-row slab of W (rows o), 256 threads: thread = column; column sums through one global reduction per CTA and column.
 __global__ void __launch_bounds__(256) unfold_grads_kernel(int N, int K, float c, const __nv_bfloat16* __restrict__ W, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, const float* __restrict__ dWf, const float* __restrict__ dbf, float* __restrict__ dW,
                                                             float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   extern __shared__ float red[];   // [2][K]
   for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
-  const int o0 = blockIdx.x * 64;
+  constexpr int ROWS = 8;
+  const int o0 = blockIdx.x * ROWS;
   for (int i = threadIdx.x; i < K; i += blockDim.x) {
     const float gm = gamma ? gamma[i] : 1.0f, bt = (beta && dbf) ? beta[i] : 0.0f;
     float sg = 0.f, sb = 0.f;
-    for (int o = o0; o < min(o0 + 64, N); ++o) {
+    for (int o = o0; o < min(o0 + ROWS, N); ++o) {
       const float w = __bfloat162float(W[(size_t)o * K + i]);
       const float g = dWf[(size_t)o * K + i];
       dW[(size_t)o * K + i] += c * (gm * g + (dbf ? bt * dbf[o] : 0.0f));
@@ -504,13 +505,13 @@ __global__ void __launch_bounds__(256) unfold_grads_kernel(int N, int K, float c
     if (dbeta && dbf) atomicAdd(dbeta + i, red[K + i]);
   }
   if (db && dbf)
-    for (int o = o0 + threadIdx.x; o < min(o0 + 64, N); o += blockDim.x) db[o] += c * dbf[o];
+    for (int o = o0 + threadIdx.x; o < min(o0 + ROWS, N); o += blockDim.x) db[o] += c * dbf[o];
 }
 
 int launch_unfold_grads(cudaStream_t s, int N, int K, float c, const __nv_bfloat16* W, const float* gamma, const float* beta, const float* dWf,
                         const float* dbf, float* dW, float* db, float* dgamma, float* dbeta) {
   if (N <= 0 || K <= 0) return VITMARL_OK;
-  unfold_grads_kernel<<<(N + 63) / 64, 256, 2 * K * sizeof(float), s>>>(N, K, c, W, gamma, beta, dWf, dbf, dW, db, dgamma, dbeta);
+  unfold_grads_kernel<<<(N + 7) / 8, 256, 2 * K * sizeof(float), s>>>(N, K, c, W, gamma, beta, dWf, dbf, dW, db, dgamma, dbeta);
   return check_cuda(cudaGetLastError());
 }
 
