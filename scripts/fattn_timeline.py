@@ -24,6 +24,8 @@ for h in range(3):
 print(" epi(h1): ld+pack done", r(70), "waits done", r(71), "sts issued", r(72), "fence done", r(73))
 print(" LN(next): start", r(51), "xfull", r(52), "stats+bar", r(53), "xnfree", r(54))
 print(" LN(next) done", r(50), "| proj start", r(130), "issued", r(131), "| CV: projfull", r(60), "tile end", r(61))
+ts = [t[140 + j] for j in range(16) if t[140 + j]]
+print(" S(h0) issue per tile: periods:", [b - a for a, b in zip(ts, ts[1:])])
 tm = _capi.Timing(); enc.options.timing = tm.handle
 for _ in range(5): enc.apply_packed(packed, x)
 torch.cuda.synchronize()

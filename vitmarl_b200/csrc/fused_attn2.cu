@@ -157,8 +157,11 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         for (int kb = 0; kb < KB_X; ++kb) tma_load_2d(sbase + OFF_X + kb * KBLK, &tmX, kb * 64, tile_row(j), bar(B_XFULL));
       };
       load_x(0);
+      if (nt > 1) { mbar_wait_guard(bar(B_XFREE), 0); load_x(1); }
       for (int j = 0; j < nt; ++j) {
-        if (j + 1 < nt) { mbar_wait_guard(bar(B_XFREE), j & 1); load_x(j + 1); }      // LayerNorm(j) has read the x buffer
+        // the x tile of tile j+2 is requested as soon as LayerNorm(j+1) has read the buffer (in tile j's tail) and BEFORE this
+        // tile's output store is issued: a load queued behind the 48 KB reduce-add store reached the LayerNorm ~3000 cycles late
+        if (j + 2 < nt) { mbar_wait_guard(bar(B_XFREE), (j + 1) & 1); load_x(j + 2); }
         mbar_wait_guard(bar(B_OUTREADY), j & 1);
         for (int kb = 0; kb < KB_X; ++kb) {
           if (p.inplace) tma_reduce_add_2d(&tmOut, sbase + OFF_OC + kb * KBLK, kb * 64, tile_row(j));
@@ -278,6 +281,7 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             mbar_wait_guard(bar(B_QKREADY), ph);
             tc_fence_after();
             FA2_STAMP(100 + 4 * h);
+            if (p.dbg && blockIdx.x == 0 && h == 0 && j < 16 && lane == 0) p.dbg[140 + j] = clock64();   // per-tile period
             if (elect_one()) issue_s(n);
             __syncwarp();
           }
