@@ -316,25 +316,6 @@ __device__ __forceinline__ uint32_t gelu_tanh_bf16x2(uint32_t x) {
   asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(y) : "r"(hx), "r"(t));
   return y;
 }
-// d/dx gelu_tanh(x) on a packed bf16x2 pair: 0.5 + 0.5 (t + x (1 - t^2) k0 (1 + 3 k1 x^2)), t = tanh(k0 (x + k1 x^3)); 10 packed ops
-__device__ __forceinline__ uint32_t gelu_tanh_grad_bf16x2(uint32_t x) {
-  const uint32_t C0 = 0x3F4C3F4Cu;    // bf16(0.7978845608) x2
-  const uint32_t C1 = 0x3D123D12u;    // bf16(k0 * k1 = 0.0356774) x2
-  const uint32_t C3 = 0x3DDB3DDBu;    // bf16(3 * k0 * k1 = 0.1070322) x2
-  const uint32_t ONE = 0x3F803F80u, MONE = 0xBF80BF80u, HALF = 0x3F003F00u;
-  uint32_t x2, p, u, t, q, t2, om, r, sgm, g;
-  asm("mul.rn.bf16x2 %0, %1, %1;" : "=r"(x2) : "r"(x));
-  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(p) : "r"(x2), "r"(C1), "r"(C0));
-  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(u) : "r"(p), "r"(x));
-  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t) : "r"(u));
-  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(q) : "r"(x2), "r"(C3), "r"(C0));
-  asm("mul.rn.bf16x2 %0, %1, %1;" : "=r"(t2) : "r"(t));
-  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(om) : "r"(t2), "r"(MONE), "r"(ONE));
-  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(om));
-  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(sgm) : "r"(r), "r"(q), "r"(t));
-  asm("fma.rn.bf16x2 %0, %1, %2, %2;" : "=r"(g) : "r"(sgm), "r"(HALF));
-  return g;
-}
 // ---- packed bf16x2 / mixed-precision helpers (HFMA2.BF16, FHADD.BF16, FHFMA.BF16) ----
 __device__ __forceinline__ uint32_t bf16x2_fma(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t d;
