@@ -148,7 +148,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int acc = it & 1;
       const uint32_t tbar = tempty_bar(acc);
       staged_epilogue_tile<BN>(p, &tmC, &tmC2, &tmR, sgen, smem_base, out_base, res_bar(0), tfull_bar(acc), (it >> 1) & 1,
-                               tmem_base + acc * BN, it, tn * BN, tm * BM, warp, lane, [&] { mbar_arrive(tbar); });
+                               tmem_base + acc * BN, it, tn * BN, tm * BM, warp, lane, [&] { mbar_arrive(tbar); },
+                               w + (int)gridDim.x < num_work, ((w + (int)gridDim.x) % tiles_n) * BN, ((w + (int)gridDim.x) / tiles_n) * BM);
     }
     if (warp == 2 && lane == 0) bulk_wait0();
   } else {

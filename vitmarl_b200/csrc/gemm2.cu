@@ -194,7 +194,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t tbar = tempty_bar(acc) & kPeerMask;
       staged_epilogue_tile<BN>(p, &tmC, &tmC2, &tmR, sgen, smem_base, out_base, res_bar(0), tfull_bar(acc), (it >> 1) & 1,
                                tmem_base + acc * BN, it, tn * BN, tm * 2 * BM + (int)rank * BM, warp, lane,
-                               [&] { mbar_arrive_cluster(tbar); });
+                               [&] { mbar_arrive_cluster(tbar); }, w + num_clusters < num_work, ((w + num_clusters) % tiles_n) * BN,
+                               ((w + num_clusters) / tiles_n) * 2 * BM + (int)rank * BM);
     }
     if (warp == 2 && lane == 0) bulk_wait0();
   }

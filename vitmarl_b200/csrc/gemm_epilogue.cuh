@@ -118,7 +118,8 @@ template <int BN, typename ArriveEmpty>
 __device__ __forceinline__ void staged_epilogue_tile(const GemmParams& p, const CUtensorMap* tmC, const CUtensorMap* tmC2,
                                                      const CUtensorMap* tmR, uint8_t* sgen, uint32_t smem_base, uint32_t out_base,
                                                      uint32_t res_bar0, uint32_t tfull_bar, uint32_t acc_ph, uint32_t taddr_acc,
-                                                     int it, int col0, int grow0, int warp, int lane, ArriveEmpty arrive_empty) {
+                                                     int it, int col0, int grow0, int warp, int lane, ArriveEmpty arrive_empty,
+                                                     bool has_next = false, int next_col0 = 0, int next_grow0 = 0) {
   constexpr int kOutBytes = 128 * BN * 2;
   constexpr int kColsPerWarp = BN / 2;
   const int quad = warp & 3, chalf = (warp - 2) >> 2;
@@ -131,13 +132,17 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmParams& p, const 
   const uint32_t res_ph = two_out ? (it & 1) : ((it >> 1) & 1);
   const uint32_t out0 = out_base + buf * kOutBytes, out1 = out_base + kOutBytes;
   const uint32_t res_bar = res_bar0 + 8u * buf;
+  auto load_addend = [&](uint32_t dst, uint32_t bar_, int c0, int g0) {
+    mbar_arrive_expect_tx(bar_, kOutBytes);
+    for (int kb = 0; kb < BN / 64; ++kb) tma_load_2d(dst + kb * (128 * 128), tmR, c0 + kb * 64, p.add_mode == 2 ? 0 : g0, bar_);
+  };
   if (elected) {
     // the staging tile(s) of this iteration must have been read by their previous TMA store
-    if (two_out) bulk_wait_read0(); else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-    if (has_add) {                                                         // lands while the mainloop of this tile runs
-      mbar_arrive_expect_tx(res_bar, kOutBytes);
-      for (int kb = 0; kb < BN / 64; ++kb) tma_load_2d(out0 + kb * (128 * 128), tmR, col0 + kb * 64, p.add_mode == 2 ? 0 : grow0, res_bar);
-    }
+    if (two_out) bulk_wait_read0();
+    else if (!has_add) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    // addend tile: requested ONE TILE AHEAD (at the end of the previous tile's epilogue, below) so that its ~2000 cycles of
+    // TMA latency run under the previous epilogue instead of in front of this one; only the first tile requests its own
+    if (has_add && it == 0) load_addend(out0, res_bar, col0, grow0);
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");
   mbar_wait(tfull_bar, acc_ph);
@@ -209,6 +214,11 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmParams& p, const 
     if (two_out)
       for (int kb = 0; kb < BN / 64; ++kb) tma_store_2d(tmC2, out1 + kb * (128 * 128), col0 + kb * 64, grow0);
     bulk_commit();
+    if (has_add && has_next) {
+      // the other staging tile was last read by the store of tile it-1: all but the newest bulk group (this tile's store) done
+      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      load_addend(out_base + (buf ^ 1) * kOutBytes, res_bar0 + 8u * (buf ^ 1), next_col0, next_grow0);
+    }
   }
 }
 

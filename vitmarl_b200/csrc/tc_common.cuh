@@ -291,11 +291,14 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   float u = k0 * (x + k1 * x * x * x);
   return 0.5f * x * (1.0f + tanh_approx(u));
 }
+// 8 FP32 instructions + 1 MUFU (the epilogue that applies it is instruction-bound: 21 warp-instructions per element measured with
+// the textbook form): g' = 0.5 + 0.5 (t + x (1 - t^2) k0 (1 + 3 k1 x^2)),  t = tanh(x k0 (1 + k1 x^2))
 __device__ __forceinline__ float gelu_tanh_grad(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float u = k0 * (x + k1 * x * x * x);
-  float t = tanh_approx(u);
-  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x * x);
+  const float k0 = 0.7978845608028654f, k0k1 = 0.7978845608028654f * 0.044715f;
+  const float s = x * x;
+  const float t = tanh_approx(x * fmaf(s, k0k1, k0));
+  const float c = fmaf(x * fmaf(-t, t, 1.0f), fmaf(s, 3.0f * k0k1, k0), t);
+  return fmaf(c, 0.5f, 0.5f);
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
