@@ -10,7 +10,8 @@
 //     head h+1 and the next tile's LayerNorm overlaps this tile's projection;
 //   * OPERANDS IN TENSOR MEMORY: LayerNorm writes its bf16 result straight into TMEM and the QKV projections read it as
 //     the A operand (tcgen05.mma [d], [a_tmem], b_desc); softmax writes P over the S accumulator in place and P.V reads
-//     it from TMEM.  Shared memory holds only what must be a B operand (weights, K, V) plus Q and concat(O);
+//     it from TMEM; Q_h goes to TMEM as well (A operand of S).  Shared memory holds only what must be a B operand
+//     (weights, K, V) plus concat(O);
 //   * FOLDED PARAMETERS (vit_fold.cu): LayerNorm scale/shift, the 1/8 . log2(e) softmax scale and every bias except
 //     Q's are folded into the weights (the K bias cancels inside the softmax, the V bias moves into the output bias),
 //     so the epilogues are convert-and-store;
@@ -19,7 +20,8 @@
 //     from L2 instead was tried: its latency lands on the tile-boundary critical path, 146 -> 180 us);
 //   * tile boundary: the next tile's first QKV projection is issued BEFORE this tile's output projection, which
 //     accumulates into the (dead) S|O columns, so the tensor pipe never drains between tiles.
-// TMEM columns: XN 0..95 (LN(x), bf16 pairs) | QKV 96..287 | S / P 288..415 | O 416..479;  projection accumulator = 288..479.
+// TMEM columns: XN 0..95 (LN(x), bf16 pairs) | QKV 96..287 | S / P 288..415 | O 416..479 | Q_h 480..511 (bf16 pairs);  projection
+// accumulator = 288..479.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -40,8 +42,7 @@ constexpr int STAGE_BYTES = 192 * 128;             // 24 KB
 constexpr int KBLK = TM * 128;                     // one [128 x 64] bf16 K-block = 16 KB
 constexpr int X_BYTES = KB_X * KBLK;               // 48 KB
 constexpr int OFF_X = 0;                           // raw x tile (LayerNorm input)
-constexpr int OFF_Q = OFF_X + X_BYTES;
-constexpr int OFF_K = OFF_Q + KBLK;
+constexpr int OFF_K = OFF_X + X_BYTES;             // (Q_h lives in tensor memory)
 constexpr int OFF_V = OFF_K + KBLK;                // V_h [128 keys x 64 d]
 constexpr int OFF_OC = OFF_V + KBLK;               // concat(O_h) [128 x 192] = 3 K-blocks; reused as the output staging tile
 constexpr int OFF_W = OFF_OC + 3 * KBLK;
@@ -54,7 +55,7 @@ constexpr int N_CV = 12, N_SM = 8, N_OE = 4;   // conversion / softmax warps; co
                                                 // which wait for P.V anyway -- the Q / K warps stay decoupled from the softmax chain)
 constexpr int THREADS = 32 * (W_CV0 + N_CV);       // 768
 constexpr int TMEM_COLS = 512;
-constexpr int COL_XN = 0, COL_QKV = 96, COL_S = 288, COL_O = 416, COL_PROJ = 288;
+constexpr int COL_XN = 0, COL_QKV = 96, COL_S = 288, COL_O = 416, COL_PROJ = 288, COL_Q = 480;
 enum { B_XFULL = 0, B_XFREE, B_XNREADY, B_XNFREE, B_QKVFULL, B_QKVEMPTY, B_QKREADY, B_VREADY, B_SFULL, B_PREADY, B_OFULL, B_OCREADY,
        B_PROJFULL, B_PROJEMPTY, B_OUTREADY, B_OCFREE, B_OCDONE, B_SISSUED, B_WFULL, B_WEMPTY = B_WFULL + NSTW, B_TMEMSLOT = B_WEMPTY + NSTW, B_COUNT };
 static_assert(B_COUNT * 8 <= 256, "barrier area");
@@ -262,10 +263,10 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     if (nt > 0) {
       constexpr uint32_t id_s = umma_idesc_bf16(TM, 128, false, false);
       constexpr uint32_t id_pv = umma_idesc_bf16(TM, 64, false, true);      // B = V_h, MN-major
-      const uint32_t la_q = umma_desc_lo(sbase + OFF_Q), lb_k = umma_desc_lo(sbase + OFF_K), lv = umma_desc_lo(sbase + OFF_V, 8192);
-      auto issue_s = [&](uint32_t m) {        // elected lane only: S = Q K^T (both images; the diagonal 64x64 blocks are used)
+      const uint32_t lb_k = umma_desc_lo(sbase + OFF_K), lv = umma_desc_lo(sbase + OFF_V, 8192);
+      auto issue_s = [&](uint32_t m) {        // elected lane only: S = Q K^T (Q in tensor memory; both images, the diagonal 64x64 blocks are used)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + COL_S, umma_desc_from_lo(la_q + 2 * k), umma_desc_from_lo(lb_k + 2 * k), id_s, k ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem_base + COL_S, tmem_base + COL_Q + 8 * k, umma_desc_from_lo(lb_k + 2 * k), id_s, k ? 1u : 0u);
         umma_commit(bar(B_SFULL));
         mbar_arrive(bar(B_SISSUED));
       };
@@ -504,12 +505,21 @@ fused_attn2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         else mbar_wait_guard(bar(B_SFULL), (n - 1) & 1);
       }
       if (warp == W_CV0 && h == 1) FA2_STAMP(71);
-      uint8_t* dst = sptr + (part == 0 ? OFF_Q : (part == 1 ? OFF_K : OFF_V)) + row * 128;
+      if (part == 0) {
+        // Q_h goes to TENSOR MEMORY (32 columns of bf16 pairs, A operand of S = Q K^T): shared memory is the busiest resource of
+        // this kernel (ncu: LSU + tensor-core wavefronts ~50 % of the data pipe on average, before the TMA writes), and Q through
+        // shared memory cost 768 of its ~10 k wavefronts per tile
+        tmem_st_32x32(tmem_base + tm_lane + COL_Q, w);
+        tmem_st_wait();
+        tc_fence_before();
+      } else {
+        uint8_t* dst = sptr + (part == 1 ? OFF_K : OFF_V) + row * 128;
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(dst + ((((uint32_t)c) ^ sw) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(dst + ((((uint32_t)c) ^ sw) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+      }
       if (warp == W_CV0 && h == 1) FA2_STAMP(72);
-      fence_proxy_async_smem();
+      if (part != 0) fence_proxy_async_smem();
       if (warp == W_CV0 && h == 1) FA2_STAMP(73);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(part == 2 ? B_VREADY : B_QKREADY));

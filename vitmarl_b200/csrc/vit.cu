@@ -11,6 +11,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <new>
 
@@ -86,7 +88,8 @@ static Ws layout(const Dims& d, bool save, bool fused_train = false) {
   const int nl = save ? d.L : 1;
   w.patches = take(M * d.Kp * 2);
   w.x = take(w.sz_md * (save ? d.L + 1 : 1));
-  w.xm = save ? take(w.sz_md * nl) : w.x;          // inference: residual stream updated in place
+  w.xm = save ? take(w.sz_md * nl) : w.x;          // inference: residual stream updated in place (out of place was measured: the
+                                                   // per-thread residual re-reads cost both fused blocks ~15 %)
   w.ln1 = take(w.sz_md * nl);
   const bool mlp_saved = !(save && fused_train);
   w.ln2 = save ? (mlp_saved ? take(w.sz_md * nl) : 0) : w.ln1;
@@ -153,6 +156,18 @@ static int timed(cudaStream_t st, const RunOpts& o, int cat, double flops, F&& l
   }
   if (on) cudaEventRecord(t->ev[2 * t->n], st);
   int rc = launch();
+  // debugging aid: VITMARL_SYNC_EACH_LAUNCH=1 synchronises after every launch and names the kernel class that faulted
+  static const bool sync_each = [] { const char* e = getenv("VITMARL_SYNC_EACH_LAUNCH"); return e && e[0] == '1'; }();
+  if (sync_each && rc == VITMARL_OK) {
+    const cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      static const char* const names[CAT_COUNT] = {"gemm", "fused_mlp", "fused_attn", "attention", "layernorm", "other", "gemm_dW", "gemm_dX"};
+      char msg[160];
+      snprintf(msg, sizeof msg, "kernel class '%s' failed: %s", names[cat], cudaGetErrorString(e));
+      set_last_error(msg);
+      return VITMARL_ECUDA;
+    }
+  }
   if (on) {
     cudaEventRecord(t->ev[2 * t->n + 1], st);
     t->cat[t->n] = (unsigned char)cat;
