@@ -25,8 +25,10 @@ namespace vitmarl {
 namespace g2 {
 constexpr int BM = 128;            // rows per CTA (256 per pair)
 constexpr int BK = 64;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+// epilogue warps: 8 for the per-thread epilogue (large K, hidden behind the mainloop), 16 for the staged epilogue of the small-K
+// products, whose 8-warp form was longer than the tile's mainloop (gemm_epilogue.cuh)
+constexpr int epi_warps(bool tma_epi) { return tma_epi ? 16 : 8; }
+constexpr int threads(bool tma_epi) { return 64 + 32 * epi_warps(tma_epi); }
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 }  // namespace g2
 
@@ -51,11 +53,12 @@ struct Gemm2Cfg {
 // TMA-loaded into a swizzled staging tile while the mainloop runs, each thread adds its row segment in place, and the
 // tile (plus, for bias+GELU, a second tile with the pre-activation saved for backward) leaves through TMA stores.
 template <int BN, bool TMAEPI, bool A_MN = false, bool B_MN = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::threads(TMAEPI), 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
              const __grid_constant__ CUtensorMap tmC2, const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   using namespace g2;
   using Cfg = Gemm2Cfg<BN, TMAEPI, B_MN>;
+  constexpr int kEpiWarps = epi_warps(TMAEPI);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t out_base = smem_base + Cfg::kStages * Cfg::kStageBytes;                 // TMAEPI: two staging tiles
@@ -184,7 +187,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (lane == 0) mbar_arrive_cluster(tempty_bar(acc) & kPeerMask);
     }
   } else {
-    // ================= epilogue (both CTAs; warps 2..9): staged in shared memory, TMA in / out (gemm_epilogue.cuh) =================
+    // ================= epilogue (both CTAs; warps 2..17): staged in shared memory, TMA in / out (gemm_epilogue.cuh) =================
     extern __shared__ uint8_t smem_gen[];
     uint8_t* sgen = smem_gen + (smem_base - smem_u32(smem_gen));          // generic pointer to the aligned base
     int it = 0;
@@ -192,7 +195,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int tn = w % tiles_n, tm = w / tiles_n;
       const int acc = it & 1;
       const uint32_t tbar = tempty_bar(acc) & kPeerMask;
-      staged_epilogue_tile<BN>(p, &tmC, &tmC2, &tmR, sgen, smem_base, out_base, res_bar(0), tfull_bar(acc), (it >> 1) & 1,
+      staged_epilogue_tile<BN, kEpiWarps>(p, &tmC, &tmC2, &tmR, sgen, smem_base, out_base, res_bar(0), tfull_bar(acc), (it >> 1) & 1,
                                tmem_base + acc * BN, it, tn * BN, tm * 2 * BM + (int)rank * BM, warp, lane,
                                [&] { mbar_arrive_cluster(tbar); }, w + num_clusters < num_work, ((w + num_clusters) % tiles_n) * BN,
                                ((w + num_clusters) / tiles_n) * 2 * BM + (int)rank * BM);
@@ -254,7 +257,7 @@ static int launch_gemm2_t(cudaStream_t stream, const GemmDesc& g, int add_mode, 
   if (err != cudaSuccess) return check_cuda(err);
   const int work = tiles * p.splits;
   const int clusters = min(work, max_clusters);
-  kern<<<2 * clusters, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmC2, tmR, p);
+  kern<<<2 * clusters, threads(TMAEPI), Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmC2, tmR, p);
   return check_cuda(cudaGetLastError());
 }
 

@@ -105,7 +105,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
   }
 }
 
-// ---- shared-memory-staged epilogue of one [128 x BN] bf16 output tile (8 epilogue warps = 256 threads, named barrier 1) ----
+// ---- shared-memory-staged epilogue of one [128 x BN] bf16 output tile (NW epilogue warps = 32 NW threads, named barrier 1) ----
 // A tcgen05.ld hands every thread one ROW of the accumulator, so per-thread global loads / stores touch 32 different cache
 // lines per warp instruction (the residual, the pre-activation, the position embedding and the output all have that
 // shape) and the epilogue -- not the tensor pipe -- bounded the small-K projections of the ViT.  Here the addend tile is
@@ -114,15 +114,20 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
 // TMA stores.  Staging tiles: BN/64 sub-tiles of [128 rows x 64 cols], 128B swizzle (chunk ^ (row & 7)).
 //   out_base : two staging tiles of 128*BN*2 bytes (alternating per tile; C and C2 when both are written)
 //   res_bar0 : two mbarriers (one per staging tile) for the addend loads
-template <int BN, typename ArriveEmpty>
+// NW = 8: two warps per TMEM lane quadrant, BN/2 columns each in 32-column chunks.  NW = 16 (the CTA-pair kernel): FOUR warps per
+// quadrant, BN/4 columns each in 16-column chunks -- at K = 384 the 8-warp epilogue (~5.5 k cycles per tile, issue-active 25 %:
+// two warps per scheduler stalled on TMEM / shared-memory / bias loads) was more than twice the tile's 2.3 k-cycle mainloop.
+template <int BN, int NW = 8, typename ArriveEmpty>
 __device__ __forceinline__ void staged_epilogue_tile(const GemmParams& p, const CUtensorMap* tmC, const CUtensorMap* tmC2,
                                                      const CUtensorMap* tmR, uint8_t* sgen, uint32_t smem_base, uint32_t out_base,
                                                      uint32_t res_bar0, uint32_t tfull_bar, uint32_t acc_ph, uint32_t taddr_acc,
                                                      int it, int col0, int grow0, int warp, int lane, ArriveEmpty arrive_empty,
                                                      bool has_next = false, int next_col0 = 0, int next_grow0 = 0) {
   constexpr int kOutBytes = 128 * BN * 2;
-  constexpr int kColsPerWarp = BN / 2;
-  const int quad = warp & 3, chalf = (warp - 2) >> 2;
+  constexpr int kColsPerWarp = BN / (NW / 4);
+  constexpr int CW = (kColsPerWarp % 32 == 0) ? 32 : 16;             // columns per tcgen05.ld
+  static_assert(kColsPerWarp % CW == 0 && (NW == 8 || NW == 16), "epilogue warp layout");
+  const int quad = warp & 3, cpart = (warp - 2) >> 2;
   const int trow = quad * 32 + lane;
   const uint32_t sw = (uint32_t)(trow & 7);
   const bool has_add = p.add_mode != 0;
@@ -136,6 +141,10 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmParams& p, const 
     mbar_arrive_expect_tx(bar_, kOutBytes);
     for (int kb = 0; kb < BN / 64; ++kb) tma_load_2d(dst + kb * (128 * 128), tmR, c0 + kb * 64, p.add_mode == 2 ? 0 : g0, bar_);
   };
+  auto epi_barrier = [&]() {
+    if (NW == 8) asm volatile("bar.sync 1, 256;" ::: "memory");
+    else asm volatile("bar.sync 1, 512;" ::: "memory");
+  };
   if (elected) {
     // the staging tile(s) of this iteration must have been read by their previous TMA store
     if (two_out) bulk_wait_read0();
@@ -144,7 +153,7 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmParams& p, const 
     // TMA latency run under the previous epilogue instead of in front of this one; only the first tile requests its own
     if (has_add && it == 0) load_addend(out0, res_bar, col0, grow0);
   }
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+  epi_barrier();
   mbar_wait(tfull_bar, acc_ph);
   if (has_add) mbar_wait(res_bar, res_ph);
   tc_fence_after();
@@ -152,21 +161,22 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmParams& p, const 
   uint8_t* o0 = sgen + (out0 - smem_base);
   uint8_t* o1 = sgen + (out1 - smem_base);
 #pragma unroll 1
-  for (int c = chalf * kColsPerWarp; c < (chalf + 1) * kColsPerWarp; c += 32) {
-    uint32_t r[32];
-    tmem_ld_32x32(taddr + c, r);
+  for (int c = cpart * kColsPerWarp; c < (cpart + 1) * kColsPerWarp; c += CW) {
+    uint32_t r[CW];
+    if constexpr (CW == 32) tmem_ld_32x32(taddr + c, r);
+    else tmem_ld_32x16(taddr + c, r);
     tmem_ld_wait();
-    if (c + 32 >= (chalf + 1) * kColsPerWarp) {                            // last read of the accumulator by this warp
+    if (c + CW >= (cpart + 1) * kColsPerWarp) {                            // last read of the accumulator by this warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) arrive_empty();
     }
-    float v[32];
+    float v[CW];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
     if (p.bias) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
+      for (int j = 0; j < CW; j += 4) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c + j));   // same address in every lane
         v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
       }
@@ -178,7 +188,7 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmParams& p, const 
       // fused inference block uses: 6 packed instructions per 2 elements instead of ~12 fp32 instructions per element.  With K = 384
       // the fp32 form made this epilogue (3 k issue cycles per 128 x 192 tile on 8 warps) longer than the tile's mainloop (2.3 k).
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < CW / 8; ++j) {
         const uint4 pre = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                                      pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
         if (two_out) *reinterpret_cast<uint4*>(o1 + tile_off + (((ch0 + j) ^ sw) << 4)) = pre;
@@ -188,7 +198,7 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmParams& p, const 
       continue;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < CW / 8; ++j) {
       uint4* slot = reinterpret_cast<uint4*>(o0 + tile_off + (((ch0 + j) ^ sw) << 4));
       if (has_add) {
         const uint4 a = *slot;
@@ -208,7 +218,7 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmParams& p, const 
     }
   }
   fence_proxy_async_smem();
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+  epi_barrier();
   if (elected) {
     for (int kb = 0; kb < BN / 64; ++kb) tma_store_2d(tmC, out0 + kb * (128 * 128), col0 + kb * 64, grow0);
     if (two_out)
