@@ -11,8 +11,8 @@
 //     (vit_fold.cu: W1' = W1 . diag(gamma), b1' = b1 + W1 . beta), statistics use mixed-precision bf16->fp32 FMAs
 //     (FHFMA/FHADD, no unpacking), the bias add and GELU run on packed bf16x2 with the 0.5 folded into W2.
 //
-// Per-CTA warp roles (896 threads): warp 0 x-tile TMA loads + output TMA stores, warp 1 TMEM allocator + (leader only)
-// MMA issuer, warp 2 / 3 W1 / W2 weight-ring producers, warps 4-19 GELU epilogue (MUFU-bound), warps 20-27 LayerNorm of the
+// Per-CTA warp roles (640 threads): warp 0 x-tile TMA loads + output TMA stores, warp 1 TMEM allocator + (leader only)
+// MMA issuer, warp 2 / 3 W1 / W2 weight-ring producers, warps 4-11 GELU epilogue (MUFU-bound), warps 12-19 LayerNorm of the
 // next tile + final epilogue of the previous one (running concurrently with the GELU warps).
 // Hidden dimension in 6 chunks of 128: acc1[g&1] = LN(x) . W1'[c]^T (TMEM, double buffered); the GELU epilogue writes
 // H = gelu(acc1 + b1') as packed bf16 back into the SAME TMEM columns it was read from (tcgen05.st; thread (row, 32 cols)
@@ -58,7 +58,7 @@ constexpr int OFF_BAR = OFF_W2 + NS2 * S2_BYTES;
 constexpr int OFF_MISC = OFF_BAR + 512;
 constexpr int MISC_BYTES = 128 * 4 * 8 + HID * 2 + D * 4;         // LN partials [128][2] float2 (+ spare), b1' (bf16), b2 (packed bf16)
 constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;
-constexpr int NGW = 16, NAW = 8;                                    // GELU warps / aux warps (LayerNorm + final epilogue) per CTA
+constexpr int NGW = 8, NAW = 8;                                     // GELU warps / aux warps (LayerNorm + final epilogue) per CTA
 constexpr int NCW = NGW + NAW;
 constexpr int FIRST_CW = 4, FIRST_AUX = FIRST_CW + NGW;
 constexpr int THREADS = 32 * (FIRST_CW + NCW);
@@ -267,10 +267,11 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint32_t sw = (uint32_t)(row & 7);
     if (warp < FIRST_AUX) {
       // =============================== GELU warps: thread = (row, 32 or 64 of the chunk's 128 columns) ===============================
-      // The GELU epilogue's THROUGHPUT is bound by the MUFU pipe (tanh: 16 lanes/clk/SM), but what the MMA issuer waits for is its
-      // LATENCY per chunk (FC2(g) needs H(g)): with 16 warps (one 32-column group per thread) instead of 8 the issuer's HREADY waits
-      // drop from 2.4 k to 1.7 k cycles per tile (118 -> 115 us per launch).  It gets its own warps and nothing else: LayerNorm and
-      // the final epilogue run concurrently on the aux warps.
+      // The GELU epilogue is bound by the MUFU pipe (tanh: 16 lanes/clk/SM -> ~1000 cycles per chunk whatever the warp count), so it
+      // gets its own warps and nothing else: LayerNorm and the final epilogue run concurrently on the aux warps.
+      // NGW = 16 was measured: per launch it is 2.5 % FASTER in a short, un-throttled run (the MMA issuer's HREADY waits drop from
+      // 2.4 k to 1.7 k cycles per tile) but 1.8 % SLOWER in the sustained rollout loop, where the GPU runs at its power cap
+      // (~1740 MHz) and 256 more polling threads per SM cost more clock than the shorter waits return.  8 it is.
       constexpr int GROUPS = 4 / (NGW / 4);    // 32-column groups of a chunk per thread (NGW = 16 -> 1, NGW = 8 -> 2)
       const int cg = (warp - FIRST_CW) >> 2;   // column group set (0 .. NGW/4 - 1)
       const uint32_t l_hready = mapa_rank(bar(B_HREADY), 0);
