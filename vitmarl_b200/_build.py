@@ -50,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + headers):
-            cmd = [nvcc, *ARCH_FLAGS, *NVCC_FLAGS, "-c", src, "-o", obj]
+            cmd = [nvcc, *ARCH_FLAGS, *NVCC_FLAGS, *os.environ.get("VITMARL_NVCC_EXTRA", "").split(), "-c", src, "-o", obj]
             procs.append((src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, cmd, p in procs:
         out, _ = p.communicate()

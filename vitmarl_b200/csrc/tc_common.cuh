@@ -259,10 +259,20 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
       : "memory");
   return ok != 0;
 }
+// Build-time experiment knobs (the sustained rollout loop runs at the GPU's power cap, so polling costs clock):
+//   VITMARL_WAIT_SLEEP_NS  > 0 : __nanosleep between failed polls;  VITMARL_WAIT_SLEEP_ALL = 0 : only in warps >= 4 (the epilogue /
+//   softmax / conversion roles of the fused kernels; warps 0-3 are the TMA and MMA-issuing roles whose wake-up latency is critical)
+#ifndef VITMARL_WAIT_SLEEP_NS
+#define VITMARL_WAIT_SLEEP_NS 0
+#endif
+#ifndef VITMARL_WAIT_SLEEP_ALL
+#define VITMARL_WAIT_SLEEP_ALL 0
+#endif
 __device__ __forceinline__ void mbar_wait_guard(uint32_t bar, uint32_t parity) {
   uint32_t polls = 0;
   long long t0 = 0;
   while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if (VITMARL_WAIT_SLEEP_NS > 0 && (VITMARL_WAIT_SLEEP_ALL || threadIdx.x >= 128)) __nanosleep(VITMARL_WAIT_SLEEP_NS);
     if ((++polls & 63u) == 0) {
       const long long t = clock64();
       if (t0 == 0) t0 = t;
