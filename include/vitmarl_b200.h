@@ -42,7 +42,7 @@ extern "C" {
 #define VITMARL_ECUDA (-3)        /* launch failure (cudaGetLastError)                      */
 #define VITMARL_ENODEVICE (-4)    /* no sm_100 device                                       */
 
-#define VITMARL_ABI_VERSION 2
+#define VITMARL_ABI_VERSION 3
 
 int vitmarl_abi_version(void);
 /* Human-readable text for the last CUDA error seen by this thread (static storage). */
@@ -127,7 +127,12 @@ int vitmarl_env_step(void* stream, int E, int N, int T, int M,
  *                       the integer trade reductions of the reward functions for these trader ids, computed from the step's
  *                       trade log while it is still on chip; row layout and arithmetic of vitmarl_agent_trade_stats
  *                       (get_agent_trades JaxOrderBookArrays.py:824-831; vision_env.py:2076-2078,2156-2163,2191; mm_env.py:1906-1936).
- *   trades_out          may be NULL when n_stat_agents > 0: the [T,8] log is then never written to HBM (-3.2 KB per env-step). */
+ *   trades_out          may be NULL when n_stat_agents > 0: the [T,8] log is then never written to HBM (-3.2 KB per env-step).
+ *   time_in [E,2], time_out [E,2], delta_time [E]   (all or none; ABI 3)
+ *                       the world clock of MARLEnv.step_env (marl_env.py:406,468,482): time_out = final_time = the (seconds, ns)
+ *                       columns of the step's LAST message, delta_time = float32 of
+ *                       ((final_time[0] + final_time[1]/1e9) - time_in[0]) - time_in[1]/1e9, every operation rounded to float32 as
+ *                       JAX does with x64 disabled.  time_out may alias time_in.  Not written when M == 0. */
 typedef struct VitmarlEnvStepArgs {
   int E, N, T, M;
   const int32_t* asks_in; const int32_t* bids_in; const int32_t* msgs;
@@ -138,6 +143,7 @@ typedef struct VitmarlEnvStepArgs {
   void* image; int img_dtype; int H; int W;
   int cancel_mode; int32_t init_id;
   int n_stat_agents; int32_t stat_agent_ids[4]; int32_t* trade_stats;
+  const int32_t* time_in; int32_t* time_out; float* delta_time;
 } VitmarlEnvStepArgs;
 int vitmarl_env_step2(void* stream, const VitmarlEnvStepArgs* args);
 

@@ -512,3 +512,17 @@ def auto_reset(done, window, init_asks, init_bids, init_best_asks, init_best_bid
         ssum = (int(init_best_bids[w][0]) + int(init_best_asks[w][0]) + 2**31) % 2**32 - 2**31     # int32 wrap-around (XLA semantics)
         mid[e] = np.float32(np.float32(ssum) / np.float32(2))
     return asks, bids, trades, best_asks, best_bids, mid
+
+
+def world_time_update(msgs: np.ndarray, time: np.ndarray):
+    """World clock of MARLEnv.step_env (marl_env.py:406, 468, 482), one environment:
+        final_time = combined_msgs[-1, -2:]
+        new_delta_time = final_time[0] + final_time[1]/1e9 - time[0] - time[1]/1e9
+    with x64 disabled: the int32 operands are converted to float32, every division / addition / subtraction rounds to float32,
+    evaluated left to right as Python parses it: ((ft0 + ft1/1e9) - t0) - t1/1e9.  -> (final_time int32 [2], delta float32)."""
+    ft = np.array(msgs[-1, 6:8], np.int32)
+    f32 = np.float32
+    a = f32(f32(ft[0]) + f32(f32(ft[1]) / f32(1e9)))
+    b = f32(a - f32(time[0]))
+    d = f32(b - f32(f32(time[1]) / f32(1e9)))
+    return ft, d

@@ -27,7 +27,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_binding_covers_header_and_version():
     assert sorted(_capi.SIGNATURES) == _declared()
-    assert _capi.lib().vitmarl_abi_version() == 2
+    assert _capi.lib().vitmarl_abi_version() == 3
 
 
 def test_argument_validation_without_gpu():

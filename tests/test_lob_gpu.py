@@ -293,3 +293,39 @@ def test_fused_trade_stats_and_on_chip_trade_log(c_oracle):
     assert any_trade
     with pytest.raises(_capi.VitmarlError):
         venv.step(CFG, st_b, dev(blocks[0]), keep_trades=False)          # the log may stay on chip only when its reductions are asked for
+
+
+def test_world_clock_in_the_fused_step():
+    """marl_env.py:406,468,482: time <- the (s, ns) columns of the step's last message, delta_time in float32 with one rounding
+    per operation -- bit-exact vs the NumPy float32 restatement, over chained steps (the clock is updated in place), with
+    times around the LOBSTER session (34 200 .. 57 600 s, where float32 resolves ~4 ms) and at the int32 extremes."""
+    import dataclasses
+    from oracle import lob_oracle as O
+    E, M, steps = 97, 7, 4
+    asks, bids, blocks = synthetic_case(E, M, steps=steps, seed=5)
+    rng = np.random.default_rng(11)
+    t0 = np.stack([rng.integers(34200, 57600, E), rng.integers(0, 1_000_000_000, E)], 1).astype(np.int32)
+    t0[0] = (0, 0); t0[1] = (2**31 - 1, 999_999_999); t0[2] = (57599, 1)
+    st = dataclasses.replace(venv.reset(CFG, dev(asks), dev(bids), M), time=dev(t0))
+    tref = t0.copy()
+    for k, msgs in enumerate(blocks):
+        msgs = msgs.copy()
+        msgs[:, -1, 6] = tref[:, 0] + rng.integers(0, 3, E)                      # the last message carries the step's final time
+        msgs[:, -1, 7] = rng.integers(0, 1_000_000_000, E)
+        if k == 1:
+            msgs[3, -1, 6:8] = (2**31 - 1, 0); msgs[4, -1, 6:8] = (0, 5)
+        st, _ = venv.step(CFG, st, dev(msgs), want_obs=False)
+        torch.cuda.synchronize()
+        want = [O.world_time_update(msgs[e], tref[e]) for e in range(E)]
+        wt = np.stack([w[0] for w in want]); wd = np.array([w[1] for w in want], np.float32)
+        assert np.array_equal(host(st.time), wt)
+        assert host(st.delta_time).tobytes() == wd.tobytes()
+        tref = wt
+    # an untracked clock stays untracked; half a clock is rejected by the ABI
+    st2, _ = venv.step(CFG, venv.reset(CFG, dev(asks), dev(bids), M), dev(blocks[0]), want_obs=False)
+    assert st2.time is None and st2.delta_time is None
+    import ctypes
+    a = _capi.EnvStepArgs()
+    a.E, a.N, a.T, a.M = 1, 100, 100, 1
+    a.time_in = 16                                                               # (never dereferenced: the argument check comes first)
+    assert _capi.lib().vitmarl_env_step2(None, ctypes.byref(a)) == _capi.EINVAL

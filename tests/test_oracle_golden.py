@@ -240,3 +240,16 @@ def test_render_image_spec():
     assert img[:, :, 0].sum(axis=1).tolist() == [8, 0, O.bar_length(101, 64), 0, 0, 0, 0, 0]
     assert img[:, :, 1].sum(axis=1).tolist() == [4, 0, 0, 0, 0, 0, 0, 0]
     assert (img[2, :26, 0] == 1).all() and (img[2, 26:, 0] == 0).all()
+
+
+def test_world_clock_hand_derived():
+    """marl_env.py:406,468: final_time = last message's (s, ns); delta in float32.  34201.5 - 34200 - 0.25 = 1.25 exactly; at
+    57 599 s a nanosecond is far below the float32 grid (2^-8 s), so the delta collapses onto it."""
+    from oracle import lob_oracle as O
+    msgs = np.zeros((3, 8), np.int32)
+    msgs[-1, 6:8] = (34201, 500_000_000)
+    ft, d = O.world_time_update(msgs, np.array([34200, 250_000_000], np.int32))
+    assert ft.tolist() == [34201, 500_000_000] and d == np.float32(1.25) and d.dtype == np.float32
+    msgs[-1, 6:8] = (57599, 1)
+    _, d = O.world_time_update(msgs, np.array([57599, 0], np.int32))
+    assert d == np.float32(0.0)

@@ -89,7 +89,8 @@ class EnvStepArgs(ctypes.Structure):
                 ("n_levels", ctypes.c_int), ("tick_size", ctypes.c_int), ("raw", ctypes.c_void_p), ("l2", ctypes.c_void_p),
                 ("norm", ctypes.c_void_p), ("image", ctypes.c_void_p), ("img_dtype", ctypes.c_int), ("H", ctypes.c_int),
                 ("W", ctypes.c_int), ("cancel_mode", ctypes.c_int), ("init_id", ctypes.c_int32),
-                ("n_stat_agents", ctypes.c_int), ("stat_agent_ids", ctypes.c_int32 * 4), ("trade_stats", ctypes.c_void_p)]
+                ("n_stat_agents", ctypes.c_int), ("stat_agent_ids", ctypes.c_int32 * 4), ("trade_stats", ctypes.c_void_p),
+                ("time_in", ctypes.c_void_p), ("time_out", ctypes.c_void_p), ("delta_time", ctypes.c_void_p)]
 
 
 _lib = None

@@ -60,6 +60,7 @@ struct LobParams {
   int32_t* raw; int32_t* l2; float* norm;
   void* image; int img_dtype; int H; int W;
   int bulk_ok;            // 1: TMA bulk copies usable (16-byte aligned, N even)
+  const int32_t* time_in; int32_t* time_out; float* delta_time;   // world clock (marl_env.py:406,468,482); all or none
 };
 
 // ---------------------------------------------------------------- one book side: registers + shared memory
@@ -824,6 +825,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) lob_kernel(const LobP
       mid = __fdiv_rn((float)wadd(last_b, last_a), 2.0f);   // marl_env.py:467 (int32 sum -> f32 -> /2)
       have_mid = true;
       if (lane == 0 && P.mid_out) P.mid_out[e] = mid;
+      // world clock, marl_env.py:406,468,482: final_time = time columns of the LAST message; delta in float32, one rounding per
+      // operation, in the reference's order ((ft0 + ft1/1e9) - t0) - t1/1e9
+      if (lane == 0 && P.time_out && M > 0) {
+        const int2 ft = *reinterpret_cast<const int2*>(P.msgs + ((size_t)e * M + (M - 1)) * 8 + 6);
+        const int2 t = *reinterpret_cast<const int2*>(P.time_in + (size_t)e * 2);
+        const float a = __fadd_rn((float)ft.x, __fdiv_rn((float)ft.y, 1e9f));
+        P.delta_time[e] = __fsub_rn(__fsub_rn(a, (float)t.x), __fdiv_rn((float)t.y, 1e9f));
+        *reinterpret_cast<int2*>(P.time_out + (size_t)e * 2) = ft;
+      }
     }
     // ---- reward-function reductions over the step's trade log while it is still on chip ----
     if (P.n_stat > 0) {
@@ -988,6 +998,11 @@ extern "C" int vitmarl_env_step2(void* stream, const VitmarlEnvStepArgs* a) {
   P.image = img ? a->image : nullptr; P.img_dtype = a->img_dtype; P.H = a->H; P.W = a->W;
   P.n_stat = a->n_stat_agents; P.stats = a->trade_stats; P.stat_tick = a->tick_size;
   for (int i = 0; i < 4; ++i) P.stat_ids[i] = a->stat_agent_ids[i];
+  if ((a->time_in != nullptr) != (a->time_out != nullptr) || (a->time_out != nullptr) != (a->delta_time != nullptr)) {
+    vitmarl::set_last_error("env_step2: time_in / time_out / delta_time go together");
+    return VITMARL_EINVAL;
+  }
+  P.time_in = a->time_in; P.time_out = a->time_out; P.delta_time = a->delta_time;
   return vitmarl::launch_lob(static_cast<cudaStream_t>(stream), P);
 }
 

@@ -25,6 +25,8 @@ class BookState:
     best_asks: torch.Tensor           # int32 [E,M,2]
     best_bids: torch.Tensor           # int32 [E,M,2]
     mid_price: torch.Tensor           # float32 [E]
+    time: Optional[torch.Tensor] = None          # int32 [E,2] world clock (seconds, ns); None = not tracked
+    delta_time: Optional[torch.Tensor] = None    # float32 [E] (marl_env.py:468), valid after a step when `time` is tracked
 
 
 @dataclasses.dataclass
@@ -115,9 +117,11 @@ def step(cfg: World_EnvironmentConfig, state: BookState, msgs: torch.Tensor, *, 
             t["img"] = torch.empty(img_shape, dtype=image_dtype, device=dev)
         if ids:
             t["stats"] = torch.empty((E, len(ids), 8), dtype=torch.int32, device=dev)
+        if state.time is not None:
+            t["dt"] = torch.empty((E,), dtype=torch.float32, device=dev)
         return t
 
-    key = (E, M, N, T, n_levels, want_obs, want_raw, img_shape, image_dtype, len(ids), same_tracks, str(dev))
+    key = (E, M, N, T, n_levels, want_obs, want_raw, img_shape, image_dtype, len(ids), same_tracks, state.time is not None, str(dev))
     t = buffers.get(key, make) if buffers is not None else make()
     ba, bb = (pa, pb) if same_tracks else (t["ba"], t["bb"])
     a = _capi.EnvStepArgs()
@@ -135,9 +139,17 @@ def step(cfg: World_EnvironmentConfig, state: BookState, msgs: torch.Tensor, *, 
     for i, v in enumerate(ids):
         a.stat_agent_ids[i] = int(v)
     a.trade_stats = _ptr(t.get("stats"))
+    tm = None
+    if state.time is not None:                      # world clock: time <- the last message's time, delta_time (marl_env.py:468,482)
+        tm = state.time
+        if not (tm.is_cuda and tm.is_contiguous() and tm.dtype == torch.int32 and tuple(tm.shape) == (E, 2)):
+            raise _capi.VitmarlError(_capi.EINVAL, "state.time must be a contiguous int32 [E,2] CUDA tensor")
+        if not inplace:
+            tm = torch.empty_like(tm)
+        a.time_in, a.time_out, a.delta_time = _ptr(state.time), _ptr(tm), _ptr(t["dt"])
     import ctypes
     _capi.check(_capi.lib().vitmarl_env_step2(_stream(), ctypes.byref(a)))
-    return (BookState(a_out, b_out, t_out, ba, bb, t["mid"]),
+    return (BookState(a_out, b_out, t_out, ba, bb, t["mid"], tm, t.get("dt")),
             StepOutput(t.get("norm"), t.get("raw"), t.get("img"), t.get("stats")))
 
 
