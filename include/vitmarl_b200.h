@@ -190,6 +190,26 @@ int vitmarl_filter_messages(void* stream, int E, int n, const int32_t* action_ms
  * trades and out 16-byte aligned device memory. */
 int vitmarl_agent_trade_stats(void* stream, int E, int T, const int32_t* trades, int agent_id, int tick_size, int32_t* out);
 
+/* Default action -> message tables of the two agents, one call for all E environments:
+ *   ExecutionAgent._getActionMsgs_fixedQuant_complex (vision_env.py:1046-1142; action_space "fixed_quants_complex", the
+ *   Execution_EnvironmentConfig default jaxob_config.py:108)  -> out [E,4,8]: four limit orders at FT / M / NT / PP
+ *   MarketMakingAgent._getActionMsgs_spread_skew (mm_env.py:1352-1491; action_space "spread_skew", the MarketMaking_EnvironmentConfig
+ *   default jaxob_config.py:34; multiplier_type 0 = "tick" (default), 1 = "spread")  -> out [E,2,8]: a bid and an ask
+ * best_*_price + price_stride: world_state.best_asks[-1][0] / best_bids[-1][0] read by stride from the best-price tracks (as in
+ * vitmarl_env_step2); action, is_sell_task, task_to_execute, quant_executed: int32 [E]; time: int32 [E,2] (world_state.time; the
+ * reference adds time_delay_obs_act to BOTH fields).  Integer arithmetic wraps like XLA's; float arithmetic is float32 with one
+ * rounding per operation and jax.numpy.floor_divide's algorithm, float -> int32 by truncation.  Parity: bit-exact vs the NumPy
+ * restatement oracle/action_oracle.py; unpinned against JAX itself (not installed in this image). */
+int vitmarl_exec_action_msgs_fixed_quants_complex(void* stream, int E, const int32_t* action, const int32_t* best_ask_price,
+                                                  const int32_t* best_bid_price, int price_stride, const int32_t* is_sell_task,
+                                                  const int32_t* task_to_execute, const int32_t* quant_executed, const int32_t* time,
+                                                  int trader_id, int tick_size, int n_ticks_in_book, int fixed_quant_value,
+                                                  int time_delay_obs_act, int placeholder_order_id, int32_t* out);
+int vitmarl_mm_action_msgs_spread_skew(void* stream, int E, const int32_t* action, const int32_t* best_ask_price,
+                                       const int32_t* best_bid_price, int price_stride, const int32_t* time, int trader_id, int tick_size,
+                                       float spread_multiplier, float skew_multiplier, int multiplier_type, int fixed_quant_value,
+                                       int time_delay_obs_act, int placeholder_order_id, int32_t* out);
+
 /* Message assembly of MARLEnv.step_env (marl_env.py:272-344): combined[e] = [cancel_msgs[e]; action_msgs[e] with
  * order ids renumbered to order_id_counter[e] - arange(Ma) and rows permuted by perm[e] (jax.random.permutation
  * indices computed by the caller; NULL = no shuffle); data messages] where the data messages are

@@ -125,6 +125,8 @@ SIGNATURES = {
     "vitmarl_get_cancel_msgs": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "vitmarl_get_agent_trades": (_I, [_P, _I, _I, _P, _I, _P]),
     "vitmarl_agent_trade_stats": (_I, [_P, _I, _I, _P, _I, _I, _P]),
+    "vitmarl_exec_action_msgs_fixed_quants_complex": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "vitmarl_mm_action_msgs_spread_skew": (_I, [_P, _I, _P, _P, _P, _I, _P, _I, _I, ctypes.c_float, ctypes.c_float, _I, _I, _I, _I, _P]),
     "vitmarl_filter_messages": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "vitmarl_auto_reset": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vitmarl_env_step2": (_I, [_P, _P]),

@@ -216,6 +216,107 @@ __global__ void __launch_bounds__(128) filter_msgs_kernel(int E, int n, const in
   }
 }
 
+// ---- default action -> message tables of the two agents -----------------------------------------------------------
+// ExecutionAgent._getActionMsgs_fixedQuant_complex (vision_env.py:1046-1142) and MarketMakingAgent._getActionMsgs_spread_skew
+// (mm_env.py:1352-1491): one thread per environment.  Integer parts are exact; the float parts reproduce JAX with x64 disabled --
+// int32 operands converted to float32, ONE rounding per operation (no FMA contraction), `//` on floats as jax.numpy.floor_divide's
+// _float_divmod (fmod, subtract, divide, sign fix-up, round half away from zero), float -> int32 by truncation.
+__device__ __forceinline__ float jnp_floor_divide_f32(float x, float y) {
+  const float mod = fmodf(x, y);
+  float div = __fdiv_rn(__fsub_rn(x, mod), y);
+  const bool ind = (mod != 0.0f) && ((y < 0.0f) != (mod < 0.0f));     // sign(y) != sign(mod) with both non-zero
+  if (ind) div = __fsub_rn(div, 1.0f);
+  return copysignf(floorf(__fadd_rn(fabsf(div), 0.5f)), div);          // lax.round: half away from zero
+}
+__device__ __forceinline__ int f32_to_i32_trunc(float x) {              // convert_element_type: toward zero, saturating, NaN -> 0
+  if (x != x) return 0;
+  if (x >= 2147483648.0f) return 2147483647;
+  if (x <= -2147483648.0f) return (int)0x80000000;
+  return (int)x;
+}
+__device__ __forceinline__ int floordiv_i32(int a, int b) {            // jnp.floor_divide on int32
+  int q = a / b;
+  if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
+  return q;
+}
+
+struct ExecActionParams {
+  int E; const int32_t* action; const int32_t* best_ask; const int32_t* best_bid; int price_stride;
+  const int32_t* is_sell; const int32_t* task_to_execute; const int32_t* quant_executed; const int32_t* time;
+  int trader_id, tick, n_ticks, fixed_quant, delay, placeholder; int32_t* out;
+};
+__global__ void __launch_bounds__(128) exec_action_msgs_kernel(const ExecActionParams p) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.E) return;
+  const int tick = p.tick;
+  const int best_ask = (int)((unsigned)floordiv_i32(p.best_ask[(size_t)e * p.price_stride], tick) * (unsigned)tick);
+  const int best_bid = (int)((unsigned)floordiv_i32(p.best_bid[(size_t)e * p.price_stride], tick) * (unsigned)tick);
+  const bool sell = p.is_sell[e] != 0;
+  const int sum = (int)((unsigned)best_bid + (unsigned)best_ask);
+  int lv[4];
+  if (!sell) {
+    lv[0] = best_ask;
+    lv[1] = (int)((unsigned)floordiv_i32(floordiv_i32(sum, 2), tick) * (unsigned)tick);
+    lv[2] = best_bid;
+    lv[3] = (int)((unsigned)best_bid - (unsigned)(tick * p.n_ticks));
+  } else {
+    lv[0] = best_bid;
+    const float half = __fdiv_rn((float)sum, 2.0f);
+    lv[1] = f32_to_i32_trunc(__fmul_rn(ceilf(jnp_floor_divide_f32(half, (float)tick)), (float)tick));
+    lv[2] = best_ask;
+    lv[3] = (int)((unsigned)best_ask + (unsigned)(tick * p.n_ticks));
+  }
+  // quant_array (vision_env.py:1098-1112): action 0 = nothing; 1 + 4 k + c = column c with multiplier {1, 2, 5}[k]
+  const int a = p.action[e];
+  int q[4] = {0, 0, 0, 0};
+  if (a >= 1 && a <= 12) { const int k = (a - 1) >> 2, c = (a - 1) & 3; q[c] = (int)((unsigned)(k == 0 ? 1 : (k == 1 ? 2 : 5)) * (unsigned)p.fixed_quant); }
+  const int quant_left = (int)((unsigned)p.task_to_execute[e] - (unsigned)p.quant_executed[e]);
+  const int total = (int)((unsigned)q[0] + (unsigned)q[1] + (unsigned)q[2] + (unsigned)q[3]);
+  if (total <= quant_left) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) q[c] = f32_to_i32_trunc((float)q[c]);            // both branches of the jnp.where pass through float32
+  } else {
+    q[0] = f32_to_i32_trunc(floorf((float)quant_left)); q[1] = q[2] = q[3] = 0;
+  }
+  const int side = sell ? -1 : 1;
+  const int ts = (int)((unsigned)p.time[2 * e] + (unsigned)p.delay), tn = (int)((unsigned)p.time[2 * e + 1] + (unsigned)p.delay);
+  int4* o = reinterpret_cast<int4*>(p.out + (size_t)e * 32);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    o[2 * c] = make_int4(1, side, q[c], lv[c]);
+    o[2 * c + 1] = make_int4(p.placeholder, p.trader_id, ts, tn);
+  }
+}
+
+struct MmActionParams {
+  int E; const int32_t* action; const int32_t* best_ask; const int32_t* best_bid; int price_stride; const int32_t* time;
+  int trader_id, tick; float spread_mult, skew_mult; int spread_type_mult, fixed_quant, delay, placeholder; int32_t* out;
+};
+__global__ void __launch_bounds__(128) mm_action_msgs_kernel(const MmActionParams p) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.E) return;
+  const int tick = p.tick;
+  const float ftick = (float)tick;
+  const int best_ask = (int)((unsigned)floordiv_i32(p.best_ask[(size_t)e * p.price_stride], tick) * (unsigned)tick);
+  const int best_bid = (int)((unsigned)floordiv_i32(p.best_bid[(size_t)e * p.price_stride], tick) * (unsigned)tick);
+  const float mid = __fdiv_rn((float)(int)((unsigned)best_ask + (unsigned)best_bid), 2.0f);
+  const int spread = (int)((unsigned)best_ask - (unsigned)best_bid);
+  const int a = p.action[e];
+  const int spread_type = floordiv_i32(a, 3), skew_type = a - 3 * spread_type;      // jnp // and % (floor semantics)
+  const float new_spread = __fmul_rn((float)spread, spread_type == 0 ? 1.0f : p.spread_mult);
+  const float skew = skew_type == 0 ? -p.skew_mult : (skew_type == 1 ? 0.0f : p.skew_mult);
+  const float skewed_mid = __fadd_rn(mid, __fmul_rn(skew, p.spread_type_mult ? new_spread : ftick));
+  const float half = jnp_floor_divide_f32(new_spread, 2.0f);
+  const float bid = __fmul_rn(jnp_floor_divide_f32(__fsub_rn(skewed_mid, half), ftick), ftick);
+  const float ask = __fmul_rn(jnp_floor_divide_f32(__fadd_rn(skewed_mid, half), ftick), ftick);
+  const int ts = (int)((unsigned)p.time[2 * e] + (unsigned)p.delay), tn = (int)((unsigned)p.time[2 * e + 1] + (unsigned)p.delay);
+  int4* o = reinterpret_cast<int4*>(p.out + (size_t)e * 16);
+  o[0] = make_int4(1, 1, p.fixed_quant, f32_to_i32_trunc(bid));
+  o[1] = make_int4(p.placeholder, p.trader_id, ts, tn);
+  o[2] = make_int4(1, -1, p.fixed_quant, f32_to_i32_trunc(ask));
+  o[3] = make_int4(p.placeholder, p.trader_id, ts, tn);
+}
+
 }  // namespace vitmarl
 
 using namespace vitmarl;
@@ -292,5 +393,35 @@ extern "C" int vitmarl_auto_reset(void* stream, int E, int N, int T, int M, int 
   ResetParams p{E, N, T, M, n_windows, bad_window, done, window_index, init_asks, init_bids, init_trades, init_best_asks, init_best_bids,
                 asks, bids, trades, best_asks, best_bids, mid_price};
   auto_reset_kernel<<<(E + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_cuda(cudaGetLastError());
+}
+
+extern "C" int vitmarl_exec_action_msgs_fixed_quants_complex(void* stream, int E, const int32_t* action, const int32_t* best_ask_price,
+                                                             const int32_t* best_bid_price, int price_stride, const int32_t* is_sell_task,
+                                                             const int32_t* task_to_execute, const int32_t* quant_executed,
+                                                             const int32_t* time, int trader_id, int tick_size, int n_ticks_in_book,
+                                                             int fixed_quant_value, int time_delay_obs_act, int placeholder_order_id,
+                                                             int32_t* out) {
+  if (E == 0) return VITMARL_OK;
+  if (E < 0 || tick_size < 1 || price_stride < 1 || !action || !best_ask_price || !best_bid_price || !is_sell_task || !task_to_execute ||
+      !quant_executed || !time || !out || (reinterpret_cast<uintptr_t>(out) & 15))
+    return VITMARL_EINVAL;
+  ExecActionParams p{E, action, best_ask_price, best_bid_price, price_stride, is_sell_task, task_to_execute, quant_executed, time,
+                     trader_id, tick_size, n_ticks_in_book, fixed_quant_value, time_delay_obs_act, placeholder_order_id, out};
+  exec_action_msgs_kernel<<<(E + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_cuda(cudaGetLastError());
+}
+
+extern "C" int vitmarl_mm_action_msgs_spread_skew(void* stream, int E, const int32_t* action, const int32_t* best_ask_price,
+                                                  const int32_t* best_bid_price, int price_stride, const int32_t* time, int trader_id,
+                                                  int tick_size, float spread_multiplier, float skew_multiplier, int multiplier_type,
+                                                  int fixed_quant_value, int time_delay_obs_act, int placeholder_order_id, int32_t* out) {
+  if (E == 0) return VITMARL_OK;
+  if (E < 0 || tick_size < 1 || price_stride < 1 || (multiplier_type != 0 && multiplier_type != 1) || !action || !best_ask_price ||
+      !best_bid_price || !time || !out || (reinterpret_cast<uintptr_t>(out) & 15))
+    return VITMARL_EINVAL;
+  MmActionParams p{E, action, best_ask_price, best_bid_price, price_stride, time, trader_id, tick_size, spread_multiplier, skew_multiplier,
+                   multiplier_type, fixed_quant_value, time_delay_obs_act, placeholder_order_id, out};
+  mm_action_msgs_kernel<<<(E + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return check_cuda(cudaGetLastError());
 }
