@@ -268,10 +268,13 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
 #ifndef VITMARL_WAIT_SLEEP_ALL
 #define VITMARL_WAIT_SLEEP_ALL 0
 #endif
+#ifndef VITMARL_WAIT_HINT
+#define VITMARL_WAIT_HINT 20000u      // suspend-time hint of mbarrier.try_wait
+#endif
 __device__ __forceinline__ void mbar_wait_guard(uint32_t bar, uint32_t parity) {
   uint32_t polls = 0;
   long long t0 = 0;
-  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+  while (!mbar_try_wait_hint(bar, parity, VITMARL_WAIT_HINT)) {
     if (VITMARL_WAIT_SLEEP_NS > 0 && (VITMARL_WAIT_SLEEP_ALL || threadIdx.x >= 128)) __nanosleep(VITMARL_WAIT_SLEEP_NS);
     if ((++polls & 63u) == 0) {
       const long long t = clock64();
